@@ -1,0 +1,172 @@
+/*
+ * robocheck.h -- C ABI of the B200-native per-configuration collision check.
+ *
+ * Drop-in boundary for robo-check's hot path.  The reference has no FFI layer: its boundary
+ * is the set of C++ declarations in the stage headers, called directly by its test drivers.
+ * Each entry point below names the reference interface it replaces (paths relative to the
+ * reference tree).  include/robocheck_compat.hpp re-exposes the reference's own C++
+ * signatures on top of this ABI so existing call sites keep compiling.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++/torch types; every function returns an int
+ *    status (RC_OK or a negative RC_ERR_*) and never exits or prints.
+ *  - `valid` flags are bytes, 1 = collision free, 0 = in collision (reference: bool*,
+ *    true = valid, narrow-phase/narrow-phase.cu:341).
+ *  - pointers named d_* are DEVICE pointers on the context's device, h_* are host pointers.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = the context's own stream); stage
+ *    calls are asynchronous on it unless stated otherwise.
+ *  - one context per device; calls on one context are serialised by the caller.
+ *  - there is NO CPU fallback: without a usable CUDA device rc_create fails with
+ *    RC_ERR_NO_DEVICE.
+ */
+#ifndef ROBOCHECK_H
+#define ROBOCHECK_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RC_OK 0
+#define RC_ERR_INVALID (-1)     /* bad argument                                   */
+#define RC_ERR_CUDA (-2)        /* a CUDA runtime call failed (see rc_last_error) */
+#define RC_ERR_NOMEM (-3)
+#define RC_ERR_IO (-4)          /* file could not be opened                       */
+#define RC_ERR_FORMAT (-5)      /* file could not be parsed                       */
+#define RC_ERR_UNSUPPORTED (-6) /* mesh too large for the requested path          */
+#define RC_ERR_NO_DEVICE (-7)   /* no CUDA device: there is no CPU fallback       */
+
+/* POD types, layout-identical to the reference's (Utils_rai.h:51-58, 70-96). */
+typedef struct { float x, y, z, pitch, yaw, roll; } rc_config;                  /* Configuration */
+typedef struct { float x, y, z; } rc_vec3;                                      /* Vector3f      */
+typedef struct { int v1, v2, v3; } rc_tri;                                      /* Triangle      */
+typedef struct { float x_min, y_min, z_min, x_max, y_max, z_max; } rc_aabb;     /* AABB          */
+
+typedef struct rc_ctx rc_ctx;
+typedef struct rc_mesh rc_mesh;
+
+/* rc_check modes */
+#define RC_MODE_CULLED 0 /* BVH-culled fused kernel (default, fastest)                        */
+#define RC_MODE_BRUTE 1  /* fused kernel, all n_rob_t x n_obs_t pairs: the reference's sweep  */
+
+/* ---- context ------------------------------------------------------------------------------
+ * Replaces the per-call set-up inside broadPhaseFused_sep (broad-phase/broad-phase-fused.cu:
+ * 365-476: OBJ parse, cudaMalloc, 12x cudaMemcpyToSymbol into the __constant__ mesh tables
+ * declared at Utils_rai.h:118-129, obstacle AABB via generateAABBBaseline).  Meshes are SoA
+ * host arrays exactly as the reference's SoA loadOBJFile overload produces them
+ * (Utils_rai.cu:228-320).  Sizes are run-time values (the reference bakes 792/1008 in). */
+int rc_create(rc_ctx **out, const float *rob_x, const float *rob_y, const float *rob_z, int n_rob_v,
+              const int *rob_v1, const int *rob_v2, const int *rob_v3, int n_rob_t,
+              const float *obs_x, const float *obs_y, const float *obs_z, int n_obs_v,
+              const int *obs_v1, const int *obs_v2, const int *obs_v3, int n_obs_t, int device);
+int rc_create_from_meshes(rc_ctx **out, const rc_mesh *robot, const rc_mesh *obstacle, int device);
+void rc_destroy(rc_ctx *ctx);
+const char *rc_strerror(int code);
+const char *rc_last_error(const rc_ctx *ctx);
+int rc_device(const rc_ctx *ctx);
+int rc_mesh_sizes(const rc_ctx *ctx, int *n_rob_v, int *n_rob_t, int *n_obs_v, int *n_obs_t);
+/* obstacle AABB as generateAABBBaseline(x,y,z) computes it (generate-AABB/generate-AABB.cu:183-201) */
+int rc_obstacle_aabb(const rc_ctx *ctx, rc_aabb *out);
+
+/* ---- fused entry point ("MegaKernel") -------------------------------------------------------
+ * Replaces  MegaKernel<<<>>> / CallMegaKernel (test/MegaKernel.hu:6-9) and the live pipeline
+ * broadPhaseFused_sep = broadPhaseFusedKernel_sep + narrowPhaseKernel_coarse
+ * (broad-phase-fused.cu:365-520).  One persistent kernel: SE(3) transform, warp-shuffle AABB,
+ * broad phase, narrow phase with early exit.  Flags are bit-identical to the reference
+ * pipeline.  d_valid (n bytes) and d_bitmask (ceil(n/32) words, bit i%32 of word i/32 = valid)
+ * are both optional but at least one must be given.  Unlike MegaKernel the outputs need no
+ * pre-fill.  Asynchronous. */
+int rc_check(rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_valid, uint32_t *d_bitmask,
+             int mode, void *stream);
+/* Same, host buffers: pinned staging, H2D, rc_check, D2H, synchronised on return.  This is the
+ * call behind the broadPhaseFused_sep(std::vector<Configuration>&, bool*) shim. */
+int rc_check_host(rc_ctx *ctx, const rc_config *h_confs, long n, uint8_t *h_valid, int mode);
+
+/* ---- stage API ---------------------------------------------------------------------------- */
+/* transformation/transform.hu:10-12 genTransformedCopies: AoS copies [conf][vertex].  d_base
+ * may be NULL (use the context's robot).  Arithmetic is the live fused kernel's. */
+int rc_transform_aos(rc_ctx *ctx, const rc_config *d_confs, long n, const rc_vec3 *d_base, int n_v,
+                     rc_vec3 *d_out, void *stream);
+/* generate-AABB/generate-AABB.hu:14-27 generateAABBPrimitiveKernel on device pointers ... */
+int rc_generate_aabb(rc_ctx *ctx, const rc_vec3 *d_verts, unsigned n_v, unsigned n, rc_aabb *d_out,
+                     void *stream);
+/* ... and generateAABB(): host in/out, does its own H2D/D2H and synchronises. */
+int rc_generate_aabb_host(rc_ctx *ctx, const rc_vec3 *h_verts, unsigned n_v, unsigned n,
+                          rc_aabb *h_out);
+/* SoA variant for the arrays the fused stage writes. */
+int rc_generate_aabb_soa(rc_ctx *ctx, const float *d_x, const float *d_y, const float *d_z,
+                         unsigned n_v, unsigned n, rc_aabb *d_out, void *stream);
+/* broad-phase/broad-phase.hu:13 broadPhase: device pointers, asynchronous.  d_obstacle may be
+ * NULL (use the context's obstacle AABB). */
+int rc_broad_phase(rc_ctx *ctx, long n, const rc_aabb *d_robots, const rc_aabb *d_obstacle,
+                   uint8_t *d_valid, void *stream);
+/* broad-phase/broad-phase-fused.cu:157-207 broadPhaseFusedKernel_sep: transform + AABB + broad
+ * phase; writes the transformed vertices as three SoA arrays indexed [i * n_rob_v + v]
+ * (d_x/d_y/d_z may all be NULL to skip the store), optionally the per-config AABB, and
+ * d_valid[i] = !overlap. */
+int rc_broad_fused(rc_ctx *ctx, const rc_config *d_confs, long n, float *d_x, float *d_y, float *d_z,
+                   rc_aabb *d_aabb, uint8_t *d_valid, void *stream);
+/* narrow-phase/narrow-phase.hu:51-53 narrowPhaseKernel_coarse on the SoA arrays above:
+ * d_valid is in/out, entries already 1 are skipped (narrow-phase.cu:578). */
+int rc_narrow_phase(rc_ctx *ctx, const float *d_x, const float *d_y, const float *d_z, long n,
+                    uint8_t *d_valid, void *stream);
+/* narrow-phase/narrow-phase.hu:22-25 narrowPhase(): host AoS pointers, in/out flags, own
+ * copies and synchronisation; meshes are the arguments, not the context's. */
+int rc_narrow_phase_host(int n, int n_rob_t, int n_rob_v, int n_obs_t, int n_obs_v,
+                         const rc_tri *rob_trs, const rc_vec3 *rob_pts, const rc_tri *obs_trs,
+                         const rc_vec3 *obs_pts, uint8_t *valid, int device);
+
+/* ---- measurement ------------------------------------------------------------------------- */
+typedef struct {
+    unsigned long long broad_cleared, sphere_cleared, narrow_valid, narrow_invalid;
+    unsigned long long node_pairs, leaf_pairs, tri_pairs, tail_pairs, overflow, launches;
+} rc_stats;
+/* Statistics of rc_check calls since the last reset; counting is off by default. */
+int rc_stats_enable(rc_ctx *ctx, int on);
+int rc_stats_read(rc_ctx *ctx, rc_stats *out, int reset);
+/* CUDA-event time of the kernels of the last rc_check_host call, milliseconds. */
+float rc_last_kernel_ms(const rc_ctx *ctx);
+/* Sustained FP32 FMA rate of the device, TFLOP/s (2 flop per FMA), measured by a register-
+ * resident FMA kernel: the denominator of the narrow-phase roofline. */
+int rc_measure_fp32_peak(rc_ctx *ctx, double *tflops);
+
+/* ---- host side: meshes, .conf files, configuration sets ------------------------------------ */
+/* OBJ: `v x y z` and `f a b c ...` with `a//n` / `a/t/n` tokens, fan triangulation, 1-based ->
+ * 0-based (Utils_rai.cu:139-320).  BYU (.g): header "parts verts polys edges", part ranges,
+ * vertices, polygons terminated by a negative index (models/BYU_Model_Loader.cpp:33-89). */
+int rc_mesh_load_obj(const char *path, rc_mesh **out);
+int rc_mesh_load_byu(const char *path, rc_mesh **out);
+int rc_mesh_from_arrays(const float *x, const float *y, const float *z, int n_v, const int *v1,
+                        const int *v2, const int *v3, int n_t, rc_mesh **out);
+int rc_mesh_save_obj(const rc_mesh *m, const char *path);
+int rc_mesh_save_byu(const rc_mesh *m, const char *path);
+int rc_mesh_counts(const rc_mesh *m, int *n_v, int *n_t);
+const float *rc_mesh_x(const rc_mesh *m);
+const float *rc_mesh_y(const rc_mesh *m);
+const float *rc_mesh_z(const rc_mesh *m);
+const int *rc_mesh_v1(const rc_mesh *m);
+const int *rc_mesh_v2(const rc_mesh *m);
+const int *rc_mesh_v3(const rc_mesh *m);
+/* 1 -> 4 midpoint subdivision, `levels` times (BASELINE config 5: subdivided obstacle). */
+int rc_mesh_subdivide(const rc_mesh *m, int levels, rc_mesh **out);
+int rc_mesh_aabb(const rc_mesh *m, rc_aabb *out);
+void rc_mesh_free(rc_mesh *m);
+
+/* .conf: one header line, then `x y z pitch yaw roll tag` per line
+ * (readConfigurationFromFile / writeConfigurationToFileTagged, Utils_rai.cu:11-97).
+ * rc_conf_read allocates *confs (and *tags if tags != NULL) with malloc; free with rc_free. */
+int rc_conf_read(const char *path, rc_config **confs, uint8_t **tags, long *n);
+int rc_conf_write(const char *path, const rc_config *confs, const uint8_t *valid, long n);
+void rc_free(void *p);
+/* generateConfs (Utils_rai.cu:322-348) with a caller-supplied seed instead of
+ * std::random_device: mt19937, draw order x, y, z, pitch, yaw, roll per configuration. */
+int rc_conf_generate(rc_config *out, long n, float x_min, float x_max, float y_min, float y_max,
+                     float z_min, float z_max, uint32_t seed);
+/* createAlphaBotConfigurations (Utils_rai.cu:111-136): hard = +-range/200, easy = +-10*range. */
+int rc_conf_generate_alpha(rc_config *out, long n, int hard, uint32_t seed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROBOCHECK_H */

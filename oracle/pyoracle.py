@@ -1,0 +1,179 @@
+"""ctypes front-end of the CPU oracle (oracle/oracle.c) and of the compiled reference
+(oracle/_ref/libref.so).  TEST INFRASTRUCTURE ONLY: importable from tests/, from
+__graft_entry__.smoke() and from bench.py's cpu_baseline / --impl reference legs."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "liboracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libref.so")
+VARIANT_GPU, VARIANT_HOST = 0, 1
+
+
+class rco_mesh(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("y", C.c_void_p), ("z", C.c_void_p), ("v1", C.c_void_p),
+                ("v2", C.c_void_p), ("v3", C.c_void_p), ("n_v", C.c_int), ("n_t", C.c_int)]
+
+
+class rco_stats(C.Structure):
+    _fields_ = [(k, C.c_long) for k in ("broad_cleared", "narrow_valid", "narrow_invalid",
+                                        "pairs_stage1", "pairs_full", "hit_pairs", "coplanar")]
+
+
+def build():
+    import subprocess
+    subprocess.check_call(["make", "-C", HERE, "--no-print-directory"], stdout=subprocess.DEVNULL)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(ORACLE_SO):
+            build()
+        _lib = C.CDLL(ORACLE_SO)
+        _lib.rco_project.restype = C.c_float
+        _lib.rco_param.restype = C.c_float
+    return _lib
+
+
+def _f(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class OracleMesh:
+    def __init__(self, x, y, z, v1, v2, v3):
+        self.x, self.y, self.z = _f(x), _f(y), _f(z)
+        self.v1, self.v2, self.v3 = (np.ascontiguousarray(a, dtype=np.int32) for a in (v1, v2, v3))
+        self.c = rco_mesh(_p(self.x), _p(self.y), _p(self.z), _p(self.v1), _p(self.v2), _p(self.v3),
+                          len(self.x), len(self.v1))
+
+
+def check(rob, obs, confs, variant=VARIANT_GPU, nthreads=None, early_exit=True, want_stats=False):
+    """Flags (uint8, 1 = valid) for every configuration, brute force over all triangle pairs."""
+    confs = _f(confs).reshape(-1, 6)
+    valid = np.zeros(len(confs), np.uint8)
+    st = rco_stats()
+    nthreads = nthreads or os.cpu_count() or 1
+    rc = lib().rco_check(C.byref(rob.c), C.byref(obs.c), _p(confs), C.c_long(len(confs)), variant,
+                         nthreads, 1 if early_exit else 0, _p(valid), C.byref(st))
+    assert rc == 0
+    if want_stats:
+        return valid, {k: getattr(st, k) for k, _ in rco_stats._fields_}
+    return valid
+
+
+def transform(confs, x, y, z):
+    confs = _f(confs).reshape(-1, 6)
+    x, y, z = _f(x), _f(y), _f(z)
+    n, nv = len(confs), len(x)
+    ox, oy, oz = (np.zeros((n, nv), np.float32) for _ in range(3))
+    lib().rco_transform(_p(confs), n, _p(x), _p(y), _p(z), nv, _p(ox), _p(oy), _p(oz))
+    return ox, oy, oz
+
+
+def aabb(x, y, z):
+    x, y, z = _f(x), _f(y), _f(z)
+    out = np.zeros(6, np.float32)
+    lib().rco_aabb(_p(x), _p(y), _p(z), len(x), _p(out))
+    return out
+
+
+def broad_valid(rob_box, obs_box):
+    return int(lib().rco_broad_valid(_p(_f(rob_box)), _p(_f(obs_box))))
+
+
+def matrix(conf):
+    m = np.zeros(12, np.float32)
+    lib().rco_matrix(_p(_f(conf)), _p(m))
+    return m
+
+
+def sincos(x):
+    s, c = C.c_float(), C.c_float()
+    lib().rco_sincosf(C.c_float(x), C.byref(s), C.byref(c))
+    return s.value, c.value
+
+
+def narrow(rob, obs, px, py, pz, valid, variant=VARIANT_GPU):
+    px, py, pz = _f(px), _f(py), _f(pz)
+    valid = np.ascontiguousarray(valid, dtype=np.uint8).copy()
+    lib().rco_narrow(C.byref(rob.c), C.byref(obs.c), _p(px), _p(py), _p(pz), C.c_long(len(valid)),
+                     variant, _p(valid))
+    return valid
+
+
+def pair_hits(r9, o9, variant=VARIANT_GPU):
+    cop = C.c_int()
+    h = lib().rco_pair_hits(_p(_f(r9)), _p(_f(o9)), variant, C.byref(cop))
+    return int(h), int(cop.value)
+
+
+# ---- the compiled reference ------------------------------------------------------------------
+_ref = None
+
+
+def ref_available():
+    return os.path.exists(REF_SO)
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        _ref = C.CDLL(REF_SO)
+    return _ref
+
+
+def ref_cpu_narrow(rob, obs, px, py, pz, nthreads=None):
+    """narrowPhaseBaseline (reference narrow-phase.cu:342-424) on transformed SoA vertices
+    [n][n_v]; converts to the AoS layout the reference expects.  Threads split the configs."""
+    import threading
+    n, nv = px.shape
+    pts = np.ascontiguousarray(np.stack([px, py, pz], axis=-1), dtype=np.float32)  # [n][nv][3]
+    rtri = np.ascontiguousarray(np.stack([rob.v1, rob.v2, rob.v3], axis=-1), dtype=np.int32)
+    otri = np.ascontiguousarray(np.stack([obs.v1, obs.v2, obs.v3], axis=-1), dtype=np.int32)
+    opts = np.ascontiguousarray(np.stack([obs.x, obs.y, obs.z], axis=-1), dtype=np.float32)
+    flags = np.zeros(n, np.uint8)
+    nthreads = max(1, min(nthreads or os.cpu_count() or 1, n))
+    fn = ref().ref_cpu_narrow
+
+    def work(lo, hi):
+        if hi > lo:
+            fn(hi - lo, len(rtri), nv, len(otri), len(opts), _p(rtri),
+               C.c_void_p(pts.ctypes.data + lo * nv * 12), _p(otri), _p(opts),
+               C.c_void_p(flags.ctypes.data + lo))
+
+    ths = [threading.Thread(target=work, args=(n * t // nthreads, n * (t + 1) // nthreads))
+           for t in range(nthreads)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    return flags
+
+
+def ref_gpu_check(workdir, confs):
+    confs = _f(confs).reshape(-1, 6)
+    flags = np.zeros(len(confs), np.uint8)
+    rc = ref().ref_gpu_check(os.fsencode(workdir), _p(confs), C.c_long(len(confs)), _p(flags))
+    if rc != 0:
+        raise RuntimeError(f"ref_gpu_check failed: {rc}")
+    return flags
+
+
+def ref_gpu_transform(rob, obs_box, confs):
+    confs = _f(confs).reshape(-1, 6)
+    n, nv = len(confs), len(rob.x)
+    ox, oy, oz = (np.zeros((n, nv), np.float32) for _ in range(3))
+    flags = np.zeros(n, np.uint8)
+    rc = ref().ref_gpu_transform(_p(rob.x), _p(rob.y), _p(rob.z), nv, _p(_f(obs_box)), _p(confs), n,
+                                 _p(ox), _p(oy), _p(oz), _p(flags))
+    if rc != 0:
+        raise RuntimeError(f"ref_gpu_transform failed: {rc}")
+    return ox, oy, oz, flags

@@ -1,0 +1,550 @@
+// rc_api.cu -- the C ABI (include/robocheck.h): context, fused entry point, stage wrappers.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../host/rc_bvh.h"
+#include "../host/rc_mesh.h"
+#include "rc_internal.h"
+
+namespace rc {
+
+int set_error(rc_ctx *ctx, int code, const std::string &msg)
+{
+    if (ctx) ctx->last_error = msg;
+    return code;
+}
+
+int check_cuda(rc_ctx *ctx, cudaError_t e, const char *what)
+{
+    if (e == cudaSuccess) return RC_OK;
+    return set_error(ctx, RC_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+cudaError_t launch_fma_peak(float *d_out, int grid, int iters, cudaStream_t stream);
+
+namespace {
+
+// culling boxes are inflated by this much on each side (scene extent is ~90 units)
+constexpr float kBoxMargin = 1e-3f;
+
+template <class T>
+cudaError_t dev_alloc(rc_ctx *ctx, T **p, size_t count)
+{
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, std::max<size_t>(count * sizeof(T), 16));
+    if (e == cudaSuccess) {
+        ctx->allocations.push_back(q);
+        cudaMemset(q, 0, std::max<size_t>(count * sizeof(T), 16));
+    }
+    *p = static_cast<T *>(q);
+    return e;
+}
+
+template <class T>
+cudaError_t upload(rc_ctx *ctx, T **p, const std::vector<T> &h, size_t padded_count = 0)
+{
+    cudaError_t e = dev_alloc(ctx, p, std::max(padded_count, h.size()));
+    if (e != cudaSuccess) return e;
+    if (h.empty()) return cudaSuccess;
+    return cudaMemcpy(*p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+struct GatheredTris {
+    std::vector<float4> a, b, c;
+};
+
+GatheredTris gather(const std::vector<float> &x, const std::vector<float> &y,
+                    const std::vector<float> &z, const std::vector<int> &v1,
+                    const std::vector<int> &v2, const std::vector<int> &v3,
+                    const std::vector<int> *order)
+{
+    GatheredTris g;
+    const size_t n = v1.size();
+    g.a.resize(n); g.b.resize(n); g.c.resize(n);
+    for (size_t p = 0; p < n; p++) {
+        const size_t t = order ? (size_t)(*order)[p] : p;
+        g.a[p] = make_float4(x[v1[t]], y[v1[t]], z[v1[t]], 0.f);
+        g.b[p] = make_float4(x[v2[t]], y[v2[t]], z[v2[t]], 0.f);
+        g.c[p] = make_float4(x[v3[t]], y[v3[t]], z[v3[t]], 0.f);
+    }
+    return g;
+}
+
+int upload_obstacle(rc_ctx *ctx, const GatheredTris &g, float4 **a, float4 **b, float4 **c, float4 **d)
+{
+    float4 *ra = nullptr, *rb = nullptr, *rcv = nullptr;
+    const size_t n = g.a.size();
+    cudaError_t e;
+    if ((e = upload(ctx, &ra, g.a)) || (e = upload(ctx, &rb, g.b)) || (e = upload(ctx, &rcv, g.c)) ||
+        (e = dev_alloc(ctx, a, n)) || (e = dev_alloc(ctx, b, n)) || (e = dev_alloc(ctx, c, n)) ||
+        (e = dev_alloc(ctx, d, n)))
+        return check_cuda(ctx, e, "obstacle upload");
+    if ((e = launch_obstacle_planes(ra, rb, rcv, *a, *b, *c, *d, (int)n, ctx->own_stream)))
+        return check_cuda(ctx, e, "obstacle planes");
+    return check_cuda(ctx, cudaStreamSynchronize(ctx->own_stream), "obstacle planes sync");
+}
+
+cudaStream_t stream_of(rc_ctx *ctx, void *stream)
+{
+    return stream ? static_cast<cudaStream_t>(stream) : ctx->own_stream;
+}
+
+int ensure_staging(rc_ctx *ctx, long n)
+{
+    if (n <= ctx->stage_capacity) return RC_OK;
+    if (ctx->h_pinned_confs) cudaFreeHost(ctx->h_pinned_confs);
+    if (ctx->h_pinned_valid) cudaFreeHost(ctx->h_pinned_valid);
+    if (ctx->d_stage_confs) cudaFree(ctx->d_stage_confs);
+    if (ctx->d_stage_valid) cudaFree(ctx->d_stage_valid);
+    ctx->h_pinned_confs = nullptr; ctx->h_pinned_valid = nullptr;
+    ctx->d_stage_confs = nullptr; ctx->d_stage_valid = nullptr;
+    ctx->stage_capacity = 0;
+    const long cap = std::max(n, 1L << 16);
+    cudaError_t e;
+    if ((e = cudaMallocHost(&ctx->h_pinned_confs, (size_t)cap * sizeof(rc_config))) ||
+        (e = cudaMallocHost(&ctx->h_pinned_valid, (size_t)cap)) ||
+        (e = cudaMalloc(&ctx->d_stage_confs, (size_t)cap * sizeof(rc_config))) ||
+        (e = cudaMalloc(&ctx->d_stage_valid, (size_t)cap)))
+        return check_cuda(ctx, e, "staging buffers");
+    ctx->stage_capacity = cap;
+    return RC_OK;
+}
+
+}  // namespace
+}  // namespace rc
+
+using namespace rc;
+
+extern "C" {
+
+const char *rc_strerror(int code)
+{
+    switch (code) {
+    case RC_OK: return "ok";
+    case RC_ERR_INVALID: return "invalid argument";
+    case RC_ERR_CUDA: return "CUDA runtime error";
+    case RC_ERR_NOMEM: return "out of memory";
+    case RC_ERR_IO: return "cannot open file";
+    case RC_ERR_FORMAT: return "malformed file";
+    case RC_ERR_UNSUPPORTED: return "mesh too large for this path";
+    case RC_ERR_NO_DEVICE: return "no CUDA device (there is no CPU fallback)";
+    default: return "unknown error";
+    }
+}
+
+const char *rc_last_error(const rc_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+int rc_device(const rc_ctx *ctx) { return ctx ? ctx->device : -1; }
+
+int rc_create(rc_ctx **out, const float *rob_x, const float *rob_y, const float *rob_z, int n_rob_v,
+              const int *rob_v1, const int *rob_v2, const int *rob_v3, int n_rob_t,
+              const float *obs_x, const float *obs_y, const float *obs_z, int n_obs_v,
+              const int *obs_v1, const int *obs_v2, const int *obs_v3, int n_obs_t, int device)
+{
+    if (!out) return RC_ERR_INVALID;
+    *out = nullptr;
+    if (n_rob_v <= 0 || n_rob_t <= 0 || n_obs_v <= 0 || n_obs_t <= 0 || !rob_x || !rob_y || !rob_z ||
+        !rob_v1 || !rob_v2 || !rob_v3 || !obs_x || !obs_y || !obs_z || !obs_v1 || !obs_v2 || !obs_v3)
+        return RC_ERR_INVALID;
+    for (int t = 0; t < n_rob_t; t++)
+        if (rob_v1[t] < 0 || rob_v1[t] >= n_rob_v || rob_v2[t] < 0 || rob_v2[t] >= n_rob_v ||
+            rob_v3[t] < 0 || rob_v3[t] >= n_rob_v)
+            return RC_ERR_INVALID;
+    for (int t = 0; t < n_obs_t; t++)
+        if (obs_v1[t] < 0 || obs_v1[t] >= n_obs_v || obs_v2[t] < 0 || obs_v2[t] >= n_obs_v ||
+            obs_v3[t] < 0 || obs_v3[t] >= n_obs_v)
+            return RC_ERR_INVALID;
+    if (n_rob_v > 65535) return RC_ERR_UNSUPPORTED;  // robot triangle indices are packed in 16 bits
+
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+        cudaGetLastError();
+        return RC_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= count) return RC_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return RC_ERR_CUDA;
+
+    rc_ctx *ctx = new (std::nothrow) rc_ctx();
+    if (!ctx) return RC_ERR_NOMEM;
+    ctx->device = device;
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    ctx->rob_x.assign(rob_x, rob_x + n_rob_v); ctx->rob_y.assign(rob_y, rob_y + n_rob_v);
+    ctx->rob_z.assign(rob_z, rob_z + n_rob_v);
+    ctx->rob_v1.assign(rob_v1, rob_v1 + n_rob_t); ctx->rob_v2.assign(rob_v2, rob_v2 + n_rob_t);
+    ctx->rob_v3.assign(rob_v3, rob_v3 + n_rob_t);
+    ctx->obs_x.assign(obs_x, obs_x + n_obs_v); ctx->obs_y.assign(obs_y, obs_y + n_obs_v);
+    ctx->obs_z.assign(obs_z, obs_z + n_obs_v);
+    ctx->obs_v1.assign(obs_v1, obs_v1 + n_obs_t); ctx->obs_v2.assign(obs_v2, obs_v2 + n_obs_t);
+    ctx->obs_v3.assign(obs_v3, obs_v3 + n_obs_t);
+
+    DeviceTables &t = ctx->t;
+    t.n_rob_v = n_rob_v; t.n_rob_t = n_rob_t; t.n_obs_v = n_obs_v; t.n_obs_t = n_obs_t;
+    t.n_rob_v_pad = (n_rob_v + 31) / 32 * 32;
+
+    int rcode = RC_OK;
+    cudaError_t e;
+    do {
+        if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) ||
+            (e = cudaEventCreate(&ctx->ev0)) || (e = cudaEventCreate(&ctx->ev1))) {
+            rcode = check_cuda(ctx, e, "stream/event");
+            break;
+        }
+        // obstacle AABB: generateAABBBaseline(x, y, z), generate-AABB.cu:183-201
+        {
+            float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+            for (int v = 0; v < n_obs_v; v++) {
+                lo[0] = std::min(lo[0], obs_x[v]); hi[0] = std::max(hi[0], obs_x[v]);
+                lo[1] = std::min(lo[1], obs_y[v]); hi[1] = std::max(hi[1], obs_y[v]);
+                lo[2] = std::min(lo[2], obs_z[v]); hi[2] = std::max(hi[2], obs_z[v]);
+            }
+            t.obs_box = rc_aabb{lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]};
+        }
+        // robot bounding sphere (local frame), radius rounded up
+        {
+            double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+            for (int v = 0; v < n_rob_v; v++) {
+                lo[0] = std::min(lo[0], (double)rob_x[v]); hi[0] = std::max(hi[0], (double)rob_x[v]);
+                lo[1] = std::min(lo[1], (double)rob_y[v]); hi[1] = std::max(hi[1], (double)rob_y[v]);
+                lo[2] = std::min(lo[2], (double)rob_z[v]); hi[2] = std::max(hi[2], (double)rob_z[v]);
+            }
+            for (int k = 0; k < 3; k++) t.rob_center[k] = (float)(0.5 * (lo[k] + hi[k]));
+            double r2 = 0;
+            for (int v = 0; v < n_rob_v; v++) {
+                const double dx = rob_x[v] - t.rob_center[0], dy = rob_y[v] - t.rob_center[1],
+                             dz = rob_z[v] - t.rob_center[2];
+                r2 = std::max(r2, dx * dx + dy * dy + dz * dz);
+            }
+            t.rob_radius = (float)(std::sqrt(r2) * (1.0 + 1e-6)) + 1e-4f;
+        }
+        // robot vertices (padded with copies of vertex 0) and packed triangles
+        std::vector<float4> rv((size_t)t.n_rob_v_pad);
+        for (int v = 0; v < t.n_rob_v_pad; v++) {
+            const int s = v < n_rob_v ? v : 0;
+            rv[v] = make_float4(rob_x[s], rob_y[s], rob_z[s], 0.f);
+        }
+        std::vector<rc_vec3> raos((size_t)n_rob_v);
+        for (int v = 0; v < n_rob_v; v++) raos[v] = rc_vec3{rob_x[v], rob_y[v], rob_z[v]};
+        std::vector<uint2> rt((size_t)n_rob_t);
+        for (int k = 0; k < n_rob_t; k++)
+            rt[k] = make_uint2((uint32_t)rob_v1[k] | ((uint32_t)rob_v2[k] << 16), (uint32_t)rob_v3[k]);
+        // BVHs
+        const Bvh rb = build_bvh(rob_x, rob_y, rob_z, rob_v1, rob_v2, rob_v3, n_rob_t, kBoxMargin);
+        const Bvh ob = build_bvh(obs_x, obs_y, obs_z, obs_v1, obs_v2, obs_v3, n_obs_t, kBoxMargin);
+        t.n_rob_nodes = rb.n_nodes; t.n_obs_nodes = ob.n_nodes;
+        std::vector<uint2> rts((size_t)n_rob_t);
+        for (int p = 0; p < n_rob_t; p++) rts[p] = rt[rb.order[p]];
+        std::vector<float4> rbn((size_t)rb.n_nodes * 2), obn((size_t)ob.n_nodes * 2);
+        std::memcpy(rbn.data(), rb.nodes.data(), rb.nodes.size() * sizeof(float));
+        std::memcpy(obn.data(), ob.nodes.data(), ob.nodes.size() * sizeof(float));
+
+        const size_t rt_pad = (size_t)n_rob_t + (n_rob_t & 1);
+        if ((e = upload(ctx, &t.rob_v, rv)) || (e = upload(ctx, &t.rob_aos, raos)) ||
+            (e = upload(ctx, &t.rob_t, rt, rt_pad)) || (e = upload(ctx, &t.rob_t_sorted, rts, rt_pad)) ||
+            (e = upload(ctx, &t.rob_bvh, rbn)) || (e = upload(ctx, &t.obs_bvh, obn)) ||
+            (e = dev_alloc(ctx, &ctx->d_counters, RC_NUM_COUNTERS)) ||
+            (e = dev_alloc(ctx, &ctx->d_obs_box, 1)) ||
+            (e = cudaMemcpy(ctx->d_obs_box, &t.obs_box, sizeof(rc_aabb), cudaMemcpyHostToDevice))) {
+            rcode = check_cuda(ctx, e, "table upload");
+            break;
+        }
+        const GatheredTris g = gather(ctx->obs_x, ctx->obs_y, ctx->obs_z, ctx->obs_v1, ctx->obs_v2,
+                                      ctx->obs_v3, nullptr);
+        const GatheredTris gs = gather(ctx->obs_x, ctx->obs_y, ctx->obs_z, ctx->obs_v1, ctx->obs_v2,
+                                       ctx->obs_v3, &ob.order);
+        if ((rcode = upload_obstacle(ctx, g, &t.obs_a, &t.obs_b, &t.obs_c, &t.obs_d)) != RC_OK) break;
+        if ((rcode = upload_obstacle(ctx, gs, &t.obs_a_sorted, &t.obs_b_sorted, &t.obs_c_sorted,
+                                     &t.obs_d_sorted)) != RC_OK)
+            break;
+    } while (0);
+
+    if (rcode != RC_OK) {
+        // keep the message readable through rc_strerror; the context itself is discarded
+        fprintf(stderr, "rc_create: %s\n", ctx->last_error.c_str());
+        rc_destroy(ctx);
+        return rcode;
+    }
+    *out = ctx;
+    return RC_OK;
+}
+
+int rc_create_from_meshes(rc_ctx **out, const rc_mesh *r, const rc_mesh *o, int device)
+{
+    if (!r || !o) return RC_ERR_INVALID;
+    return rc_create(out, r->x.data(), r->y.data(), r->z.data(), (int)r->x.size(), r->v1.data(),
+                     r->v2.data(), r->v3.data(), (int)r->v1.size(), o->x.data(), o->y.data(),
+                     o->z.data(), (int)o->x.size(), o->v1.data(), o->v2.data(), o->v3.data(),
+                     (int)o->v1.size(), device);
+}
+
+void rc_destroy(rc_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (void *p : ctx->allocations) cudaFree(p);
+    if (ctx->h_pinned_confs) cudaFreeHost(ctx->h_pinned_confs);
+    if (ctx->h_pinned_valid) cudaFreeHost(ctx->h_pinned_valid);
+    if (ctx->d_stage_confs) cudaFree(ctx->d_stage_confs);
+    if (ctx->d_stage_valid) cudaFree(ctx->d_stage_valid);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+int rc_mesh_sizes(const rc_ctx *ctx, int *n_rob_v, int *n_rob_t, int *n_obs_v, int *n_obs_t)
+{
+    if (!ctx) return RC_ERR_INVALID;
+    if (n_rob_v) *n_rob_v = ctx->t.n_rob_v;
+    if (n_rob_t) *n_rob_t = ctx->t.n_rob_t;
+    if (n_obs_v) *n_obs_v = ctx->t.n_obs_v;
+    if (n_obs_t) *n_obs_t = ctx->t.n_obs_t;
+    return RC_OK;
+}
+
+int rc_obstacle_aabb(const rc_ctx *ctx, rc_aabb *out)
+{
+    if (!ctx || !out) return RC_ERR_INVALID;
+    *out = ctx->t.obs_box;
+    return RC_OK;
+}
+
+int rc_check(rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_valid, uint32_t *d_bitmask,
+             int mode, void *stream)
+{
+    if (!ctx || n < 0 || (n > 0 && !d_confs) || (!d_valid && !d_bitmask)) return RC_ERR_INVALID;
+    if (mode != RC_MODE_CULLED && mode != RC_MODE_BRUTE) return RC_ERR_INVALID;
+    if (n == 0) return RC_OK;
+    cudaSetDevice(ctx->device);
+    cudaError_t e = launch_check(ctx, d_confs, n, d_valid, d_bitmask, mode, ctx->stats_on,
+                                 stream_of(ctx, stream));
+    if (e == cudaErrorInvalidConfiguration)
+        return set_error(ctx, RC_ERR_UNSUPPORTED, "mesh tables do not fit in shared memory");
+    ctx->launches++;
+    return check_cuda(ctx, e, "rc_check launch");
+}
+
+int rc_check_host(rc_ctx *ctx, const rc_config *h_confs, long n, uint8_t *h_valid, int mode)
+{
+    if (!ctx || n < 0 || (n > 0 && (!h_confs || !h_valid))) return RC_ERR_INVALID;
+    if (n == 0) return RC_OK;
+    cudaSetDevice(ctx->device);
+    int rcode = ensure_staging(ctx, n);
+    if (rcode != RC_OK) return rcode;
+    cudaStream_t s = ctx->own_stream;
+    std::memcpy(ctx->h_pinned_confs, h_confs, (size_t)n * sizeof(rc_config));
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(ctx->d_stage_confs, ctx->h_pinned_confs, (size_t)n * sizeof(rc_config),
+                             cudaMemcpyHostToDevice, s)))
+        return check_cuda(ctx, e, "H2D configurations");
+    cudaEventRecord(ctx->ev0, s);
+    rcode = rc_check(ctx, ctx->d_stage_confs, n, ctx->d_stage_valid, nullptr, mode, s);
+    if (rcode != RC_OK) return rcode;
+    cudaEventRecord(ctx->ev1, s);
+    if ((e = cudaMemcpyAsync(ctx->h_pinned_valid, ctx->d_stage_valid, (size_t)n,
+                             cudaMemcpyDeviceToHost, s)) ||
+        (e = cudaStreamSynchronize(s)))
+        return check_cuda(ctx, e, "D2H flags");
+    cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev0, ctx->ev1);
+    std::memcpy(h_valid, ctx->h_pinned_valid, (size_t)n);
+    return RC_OK;
+}
+
+float rc_last_kernel_ms(const rc_ctx *ctx) { return ctx ? ctx->last_kernel_ms : 0.f; }
+
+// ---- stage API -----------------------------------------------------------------------------
+
+int rc_transform_aos(rc_ctx *ctx, const rc_config *d_confs, long n, const rc_vec3 *d_base, int n_v,
+                     rc_vec3 *d_out, void *stream)
+{
+    if (!ctx || n < 0 || (n > 0 && (!d_confs || !d_out))) return RC_ERR_INVALID;
+    if (!d_base) { d_base = ctx->t.rob_aos; n_v = ctx->t.n_rob_v; }
+    if (n_v <= 0) return RC_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    ctx->launches++;
+    return check_cuda(ctx, launch_transform_aos(ctx, d_confs, n, d_base, n_v, d_out, stream_of(ctx, stream)),
+                      "rc_transform_aos");
+}
+
+int rc_generate_aabb(rc_ctx *ctx, const rc_vec3 *d_verts, unsigned n_v, unsigned n, rc_aabb *d_out,
+                     void *stream)
+{
+    if (!ctx || (n > 0 && (!d_verts || !d_out)) || n_v == 0) return RC_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    ctx->launches++;
+    return check_cuda(ctx, launch_aabb_aos(d_verts, n_v, n, d_out, stream_of(ctx, stream)),
+                      "rc_generate_aabb");
+}
+
+int rc_generate_aabb_host(rc_ctx *ctx, const rc_vec3 *h_verts, unsigned n_v, unsigned n, rc_aabb *h_out)
+{
+    if (!ctx || (n > 0 && (!h_verts || !h_out)) || n_v == 0) return RC_ERR_INVALID;
+    if (n == 0) return RC_OK;
+    cudaSetDevice(ctx->device);
+    rc_vec3 *dv = nullptr;
+    rc_aabb *db = nullptr;
+    const size_t bytes = (size_t)n * n_v * sizeof(rc_vec3);
+    cudaError_t e;
+    int rcode = RC_OK;
+    if ((e = cudaMalloc(&dv, bytes)) || (e = cudaMalloc(&db, (size_t)n * sizeof(rc_aabb))) ||
+        (e = cudaMemcpyAsync(dv, h_verts, bytes, cudaMemcpyHostToDevice, ctx->own_stream)) ||
+        (e = launch_aabb_aos(dv, n_v, n, db, ctx->own_stream)) ||
+        (e = cudaMemcpyAsync(h_out, db, (size_t)n * sizeof(rc_aabb), cudaMemcpyDeviceToHost,
+                             ctx->own_stream)) ||
+        (e = cudaStreamSynchronize(ctx->own_stream)))
+        rcode = check_cuda(ctx, e, "rc_generate_aabb_host");
+    ctx->launches++;
+    cudaFree(dv);
+    cudaFree(db);
+    return rcode;
+}
+
+int rc_generate_aabb_soa(rc_ctx *ctx, const float *d_x, const float *d_y, const float *d_z,
+                         unsigned n_v, unsigned n, rc_aabb *d_out, void *stream)
+{
+    if (!ctx || (n > 0 && (!d_x || !d_y || !d_z || !d_out)) || n_v == 0) return RC_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    ctx->launches++;
+    return check_cuda(ctx, launch_aabb_soa(d_x, d_y, d_z, n_v, n, d_out, stream_of(ctx, stream)),
+                      "rc_generate_aabb_soa");
+}
+
+int rc_broad_phase(rc_ctx *ctx, long n, const rc_aabb *d_robots, const rc_aabb *d_obstacle,
+                   uint8_t *d_valid, void *stream)
+{
+    if (!ctx || n < 0 || (n > 0 && (!d_robots || !d_valid))) return RC_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    ctx->launches++;
+    return check_cuda(ctx, launch_broad(n, d_robots, d_obstacle ? d_obstacle : ctx->d_obs_box, d_valid,
+                                        stream_of(ctx, stream)),
+                      "rc_broad_phase");
+}
+
+int rc_broad_fused(rc_ctx *ctx, const rc_config *d_confs, long n, float *d_x, float *d_y, float *d_z,
+                   rc_aabb *d_aabb, uint8_t *d_valid, void *stream)
+{
+    if (!ctx || n < 0 || (n > 0 && !d_confs)) return RC_ERR_INVALID;
+    const int given = (d_x != nullptr) + (d_y != nullptr) + (d_z != nullptr);
+    if (given != 0 && given != 3) return RC_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    ctx->launches++;
+    return check_cuda(ctx, launch_transform_soa(ctx, d_confs, n, d_x, d_y, d_z, d_aabb, d_valid,
+                                                stream_of(ctx, stream)),
+                      "rc_broad_fused");
+}
+
+int rc_narrow_phase(rc_ctx *ctx, const float *d_x, const float *d_y, const float *d_z, long n,
+                    uint8_t *d_valid, void *stream)
+{
+    if (!ctx || n < 0 || (n > 0 && (!d_x || !d_y || !d_z || !d_valid))) return RC_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaError_t e = launch_narrow_soa(ctx, d_x, d_y, d_z, n, d_valid, stream_of(ctx, stream));
+    if (e == cudaErrorInvalidConfiguration)
+        return set_error(ctx, RC_ERR_UNSUPPORTED, "mesh tables do not fit in shared memory");
+    ctx->launches++;
+    return check_cuda(ctx, e, "rc_narrow_phase");
+}
+
+int rc_narrow_phase_host(int n, int n_rob_t, int n_rob_v, int n_obs_t, int n_obs_v,
+                         const rc_tri *rob_trs, const rc_vec3 *rob_pts, const rc_tri *obs_trs,
+                         const rc_vec3 *obs_pts, uint8_t *valid, int device)
+{
+    if (n < 0 || n_rob_t <= 0 || n_rob_v <= 0 || n_obs_t <= 0 || n_obs_v <= 0 || !rob_trs ||
+        !rob_pts || !obs_trs || !obs_pts || !valid)
+        return RC_ERR_INVALID;
+    if (n == 0) return RC_OK;
+    // The robot vertices arrive already transformed, [conf][vertex]; the context only needs the
+    // topology and the obstacle, so it is built from configuration 0's vertices.
+    std::vector<float> rx(n_rob_v), ry(n_rob_v), rz(n_rob_v), ox(n_obs_v), oy(n_obs_v), oz(n_obs_v);
+    std::vector<int> r1(n_rob_t), r2(n_rob_t), r3(n_rob_t), o1(n_obs_t), o2(n_obs_t), o3(n_obs_t);
+    for (int v = 0; v < n_rob_v; v++) { rx[v] = rob_pts[v].x; ry[v] = rob_pts[v].y; rz[v] = rob_pts[v].z; }
+    for (int v = 0; v < n_obs_v; v++) { ox[v] = obs_pts[v].x; oy[v] = obs_pts[v].y; oz[v] = obs_pts[v].z; }
+    for (int t = 0; t < n_rob_t; t++) { r1[t] = rob_trs[t].v1; r2[t] = rob_trs[t].v2; r3[t] = rob_trs[t].v3; }
+    for (int t = 0; t < n_obs_t; t++) { o1[t] = obs_trs[t].v1; o2[t] = obs_trs[t].v2; o3[t] = obs_trs[t].v3; }
+    rc_ctx *ctx = nullptr;
+    int rcode = rc_create(&ctx, rx.data(), ry.data(), rz.data(), n_rob_v, r1.data(), r2.data(),
+                          r3.data(), n_rob_t, ox.data(), oy.data(), oz.data(), n_obs_v, o1.data(),
+                          o2.data(), o3.data(), n_obs_t, device);
+    if (rcode != RC_OK) return rcode;
+    const size_t cnt = (size_t)n * n_rob_v;
+    std::vector<float> hx(cnt), hy(cnt), hz(cnt);
+    for (size_t e = 0; e < cnt; e++) { hx[e] = rob_pts[e].x; hy[e] = rob_pts[e].y; hz[e] = rob_pts[e].z; }
+    float *dx = nullptr, *dy = nullptr, *dz = nullptr;
+    uint8_t *dv = nullptr;
+    cudaError_t e;
+    if ((e = cudaMalloc(&dx, cnt * 4)) || (e = cudaMalloc(&dy, cnt * 4)) || (e = cudaMalloc(&dz, cnt * 4)) ||
+        (e = cudaMalloc(&dv, (size_t)n)) ||
+        (e = cudaMemcpy(dx, hx.data(), cnt * 4, cudaMemcpyHostToDevice)) ||
+        (e = cudaMemcpy(dy, hy.data(), cnt * 4, cudaMemcpyHostToDevice)) ||
+        (e = cudaMemcpy(dz, hz.data(), cnt * 4, cudaMemcpyHostToDevice)) ||
+        (e = cudaMemcpy(dv, valid, (size_t)n, cudaMemcpyHostToDevice)))
+        rcode = check_cuda(ctx, e, "rc_narrow_phase_host copies");
+    if (rcode == RC_OK) rcode = rc_narrow_phase(ctx, dx, dy, dz, n, dv, nullptr);
+    if (rcode == RC_OK &&
+        ((e = cudaStreamSynchronize(ctx->own_stream)) ||
+         (e = cudaMemcpy(valid, dv, (size_t)n, cudaMemcpyDeviceToHost))))
+        rcode = check_cuda(ctx, e, "rc_narrow_phase_host result");
+    cudaFree(dx); cudaFree(dy); cudaFree(dz); cudaFree(dv);
+    rc_destroy(ctx);
+    return rcode;
+}
+
+// ---- measurement --------------------------------------------------------------------------
+
+int rc_stats_enable(rc_ctx *ctx, int on)
+{
+    if (!ctx) return RC_ERR_INVALID;
+    ctx->stats_on = on ? 1 : 0;
+    return RC_OK;
+}
+
+int rc_stats_read(rc_ctx *ctx, rc_stats *out, int reset)
+{
+    if (!ctx || !out) return RC_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    unsigned long long h[RC_NUM_COUNTERS];
+    cudaError_t e;
+    if ((e = cudaStreamSynchronize(ctx->own_stream)) ||
+        (e = cudaMemcpy(h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost)))
+        return check_cuda(ctx, e, "rc_stats_read");
+    out->broad_cleared = h[CNT_BROAD_CLEARED]; out->sphere_cleared = h[CNT_SPHERE_CLEARED];
+    out->narrow_valid = h[CNT_NARROW_VALID]; out->narrow_invalid = h[CNT_NARROW_INVALID];
+    out->node_pairs = h[CNT_NODE_PAIRS]; out->leaf_pairs = h[CNT_LEAF_PAIRS];
+    out->tri_pairs = h[CNT_TRI_PAIRS]; out->tail_pairs = h[CNT_TAIL_PAIRS];
+    out->overflow = h[CNT_OVERFLOW]; out->launches = ctx->launches;
+    if (reset) {
+        ctx->launches = 0;
+        if ((e = cudaMemset(ctx->d_counters, 0, sizeof h))) return check_cuda(ctx, e, "rc_stats reset");
+    }
+    return RC_OK;
+}
+
+int rc_measure_fp32_peak(rc_ctx *ctx, double *tflops)
+{
+    if (!ctx || !tflops) return RC_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    const int grid = ctx->sm_count * 8, iters = 4096;
+    float *d = nullptr;
+    cudaError_t e;
+    if ((e = cudaMalloc(&d, (size_t)grid * 256 * 4))) return check_cuda(ctx, e, "fp32 peak alloc");
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; rep++) {
+        cudaEventRecord(ctx->ev0, ctx->own_stream);
+        e = launch_fma_peak(d, grid, iters, ctx->own_stream);
+        cudaEventRecord(ctx->ev1, ctx->own_stream);
+        if (e || (e = cudaStreamSynchronize(ctx->own_stream))) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        if (rep > 0) best = std::min(best, ms);
+    }
+    cudaFree(d);
+    if (e) return check_cuda(ctx, e, "fp32 peak");
+    const double fmas = (double)grid * 256 * iters * 64;
+    *tflops = 2.0 * fmas / (best * 1e-3) / 1e12;
+    return RC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,319 @@
+// rc_culled.cuh -- the headline kernel: fused transform + AABB + broad phase + BVH-culled narrow
+// phase, one warp per configuration, persistent grid fed by an atomic work queue.
+//
+// Flag semantics are the reference's: a configuration is invalid iff SOME (robot triangle,
+// obstacle triangle) pair passes the Moller test of narrowPhaseKernel_coarse
+// (narrow-phase.cu:586-677); the order in which pairs are visited does not matter, so the pairs
+// may be enumerated by a tree instead of two nested loops as long as no hitting pair is skipped.
+// A pair is skipped only when an ancestor pair of boxes is separated by more than the inflation
+// margin on one of six axes (three world axes, three robot axes), i.e. when the two triangles are
+// geometrically disjoint with clearance; every surviving pair is decided with the exact reference
+// arithmetic (rc_device.cuh).  RC_MODE_BRUTE keeps the exhaustive sweep for audits.
+//
+// Per warp and configuration:
+//   A0  bounding-sphere pre-test against the obstacle AABB (clears far-away configurations)
+//   A   all robot vertices transformed by the lanes, warp-shuffle AABB, exact broad-phase flag
+//   B   dual-tree descent: a LIFO of (robot node, obstacle node) pairs in shared memory, 32 pairs
+//       tested per step (one per lane), children appended with ballot/popc compaction
+//   C   leaf pairs (<= 4 x 4 triangles) are batched eight at a time: lane = (leaf pair, robot
+//       triangle), loop over the obstacle triangles of the leaf; warp vote early exit.
+#pragma once
+
+namespace rc {
+
+constexpr int kCulledWarps = 16;
+constexpr int kCulledThreads = kCulledWarps * 32;
+constexpr int kStackCap = 1024;  // node pairs per warp; overflow falls back to the exhaustive sweep
+constexpr int kLeafQCap = 64;
+constexpr int kLeafTrisDev = 4;  // must match rc::kLeafTris of the host builder (rc_bvh.h)
+
+struct CulledArgs {
+    CheckArgs c;                  // rob_t / obs_* point at the BVH-ordered tables
+    const float4 *rob_bvh, *obs_bvh;
+    int n_rob_nodes, n_obs_nodes;
+    float sph_x, sph_y, sph_z, sph_r;
+};
+
+__device__ __forceinline__ bool boxes_overlap(const Mat34 &m, const float4 r0, const float4 r1,
+                                              const float4 o0, const float4 o1)
+{
+    // robot box centre in the world frame, relative to the obstacle box centre
+    const float dx = fmaf(m.r02, r0.z, fmaf(m.r01, r0.y, fmaf(m.r00, r0.x, m.tx))) - o0.x;
+    const float dy = fmaf(m.r12, r0.z, fmaf(m.r11, r0.y, fmaf(m.r10, r0.x, m.ty))) - o0.y;
+    const float dz = fmaf(m.r22, r0.z, fmaf(m.r21, r0.y, fmaf(m.r20, r0.x, m.tz))) - o0.z;
+    // world axes: |d| <= |R| e_r + e_o
+    const float wx = fmaf(fabsf(m.r02), r1.z, fmaf(fabsf(m.r01), r1.y, fabsf(m.r00) * r1.x)) + o1.x;
+    const float wy = fmaf(fabsf(m.r12), r1.z, fmaf(fabsf(m.r11), r1.y, fabsf(m.r10) * r1.x)) + o1.y;
+    const float wz = fmaf(fabsf(m.r22), r1.z, fmaf(fabsf(m.r21), r1.y, fabsf(m.r20) * r1.x)) + o1.z;
+    bool sep = fabsf(dx) > wx || fabsf(dy) > wy || fabsf(dz) > wz;
+    // robot axes: |R^T d| <= e_r + |R^T| e_o
+    const float lx = fmaf(m.r20, dz, fmaf(m.r10, dy, m.r00 * dx));
+    const float ly = fmaf(m.r21, dz, fmaf(m.r11, dy, m.r01 * dx));
+    const float lz = fmaf(m.r22, dz, fmaf(m.r12, dy, m.r02 * dx));
+    const float ex = fmaf(fabsf(m.r20), o1.z, fmaf(fabsf(m.r10), o1.y, fabsf(m.r00) * o1.x)) + r1.x;
+    const float ey = fmaf(fabsf(m.r21), o1.z, fmaf(fabsf(m.r11), o1.y, fabsf(m.r01) * o1.x)) + r1.y;
+    const float ez = fmaf(fabsf(m.r22), o1.z, fmaf(fabsf(m.r12), o1.y, fabsf(m.r02) * o1.x)) + r1.z;
+    sep = sep || fabsf(lx) > ex || fabsf(ly) > ey || fabsf(lz) > ez;
+    return !sep;
+}
+
+// Exhaustive sweep for one configuration (used when the pair stack overflows): lane = robot
+// triangle, obstacle triangles broadcast.  Returns true when a hitting pair exists.
+__device__ __noinline__ bool narrow_exhaustive(const Mat34 m, const float4 *s_rob_v,
+                                               const uint2 *s_rob_t, int n_rob_t,
+                                               const float4 *s_obs_a, const float4 *s_obs_b,
+                                               const float4 *s_obs_c, const float4 *s_obs_d,
+                                               int n_obs_t, int lane)
+{
+    bool hit = false;
+    for (int jb = 0; jb < n_rob_t && !hit; jb += 32) {
+        const int j = jb + lane;
+        const bool active = j < n_rob_t;
+        const uint2 ti = s_rob_t[active ? j : n_rob_t - 1];
+        const float4 A = s_rob_v[ti.x & 0xffffu], B = s_rob_v[ti.x >> 16], C = s_rob_v[ti.y];
+        Tri r;
+        xform(m, A.x, A.y, A.z, r.ax, r.ay, r.az);
+        xform(m, B.x, B.y, B.z, r.bx, r.by, r.bz);
+        xform(m, C.x, C.y, C.z, r.cx, r.cy, r.cz);
+        const Plane pr = plane_of(r);
+        for (int k = 0; k < n_obs_t; k++) {
+            const float4 oa = s_obs_a[k], ob = s_obs_b[k], oc = s_obs_c[k];
+            const Tri o = {oa.x, oa.y, oa.z, ob.x, ob.y, ob.z, oc.x, oc.y, oc.z};
+            const Plane po = {oa.w, ob.w, oc.w, s_obs_d[k].x};
+            if (active && pair_hits(r, pr, o, po)) hit = true;
+        }
+        hit = __any_sync(kFull, hit);
+    }
+    return hit;
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(kCulledThreads, 1) check_culled_kernel(const CulledArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const CheckArgs &c = a.c;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    float4 *s_rob_v = reinterpret_cast<float4 *>(smem_raw + 16);
+    float4 *s_rob_bvh = s_rob_v + c.n_rob_v_pad;
+    float4 *s_obs_bvh = s_rob_bvh + 2 * a.n_rob_nodes;
+    float4 *s_obs_a = s_obs_bvh + 2 * a.n_obs_nodes;
+    float4 *s_obs_b = s_obs_a + c.n_obs_t;
+    float4 *s_obs_c = s_obs_b + c.n_obs_t;
+    float4 *s_obs_d = s_obs_c + c.n_obs_t;
+    uint2 *s_rob_t = reinterpret_cast<uint2 *>(s_obs_d + c.n_obs_t);
+    uint32_t *s_work = reinterpret_cast<uint32_t *>(s_rob_t + c.n_rob_t + (c.n_rob_t & 1));
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t bv = c.n_rob_v_pad * 16u, bo = c.n_obs_t * 16u,
+                       bt = (c.n_rob_t + (c.n_rob_t & 1)) * 8u;
+        const uint32_t brn = a.n_rob_nodes * 32u, bon = a.n_obs_nodes * 32u;
+        mbar_expect_tx(bar, bv + 4u * bo + bt + brn + bon);
+        tma_load_1d(s_rob_v, c.rob_v, bv, bar);
+        tma_load_1d(s_rob_bvh, a.rob_bvh, brn, bar);
+        tma_load_1d(s_obs_bvh, a.obs_bvh, bon, bar);
+        tma_load_1d(s_obs_a, c.obs_a, bo, bar);
+        tma_load_1d(s_obs_b, c.obs_b, bo, bar);
+        tma_load_1d(s_obs_c, c.obs_c, bo, bar);
+        tma_load_1d(s_obs_d, c.obs_d, bo, bar);
+        tma_load_1d(s_rob_t, c.rob_t, bt, bar);
+    }
+    mbar_wait(bar, 0);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    uint32_t *stack = s_work + warp * (kStackCap + kLeafQCap);
+    uint32_t *leafq = stack + kStackCap;
+    unsigned long long st_broad = 0, st_sphere = 0, st_valid = 0, st_invalid = 0, st_nodes = 0,
+                       st_leaves = 0, st_tris = 0, st_over = 0;
+
+    for (;;) {
+        long base = 0;
+        if (lane == 0) base = (long)atomicAdd(c.counters + CNT_QUEUE, (unsigned long long)c.chunk);
+        base = __shfl_sync(kFull, base, 0);
+        if (base >= c.n) break;
+        const long end = min(base + (long)c.chunk, c.n);
+        for (long i = base; i < end; i++) {
+            const Mat34 m = load_matrix(c.confs, i);
+
+            // A0: the robot lies inside its bounding sphere; if the sphere's box clears the
+            // obstacle AABB with margin, so does the exact vertex AABB of the reference.
+            {
+                const float sx = fmaf(m.r02, a.sph_z, fmaf(m.r01, a.sph_y, fmaf(m.r00, a.sph_x, m.tx)));
+                const float sy = fmaf(m.r12, a.sph_z, fmaf(m.r11, a.sph_y, fmaf(m.r10, a.sph_x, m.ty)));
+                const float sz = fmaf(m.r22, a.sph_z, fmaf(m.r21, a.sph_y, fmaf(m.r20, a.sph_x, m.tz)));
+                const float gx = a.sph_r + 0.01f + 4e-6f * (fabsf(sx) + a.sph_r);
+                const float gy = a.sph_r + 0.01f + 4e-6f * (fabsf(sy) + a.sph_r);
+                const float gz = a.sph_r + 0.01f + 4e-6f * (fabsf(sz) + a.sph_r);
+                const bool clear = sx - gx > c.obs_box.x_max || sx + gx < c.obs_box.x_min ||
+                                   sy - gy > c.obs_box.y_max || sy + gy < c.obs_box.y_min ||
+                                   sz - gz > c.obs_box.z_max || sz + gz < c.obs_box.z_min;
+                if (clear) {
+                    publish(c, i, true, lane);
+                    if (STATS) st_sphere++;
+                    continue;
+                }
+            }
+
+            // A: exact AABB and broad-phase flag
+            float box[6];
+            warp_aabb(m, s_rob_v, c.n_rob_v_pad, lane, box);
+            if (broad_valid(box[0], box[1], box[2], box[3], box[4], box[5], c.obs_box.x_min,
+                            c.obs_box.y_min, c.obs_box.z_min, c.obs_box.x_max, c.obs_box.y_max,
+                            c.obs_box.z_max)) {
+                publish(c, i, true, lane);
+                if (STATS) st_broad++;
+                continue;
+            }
+
+            // B + C
+            int sp = 1, lq = 0;
+            bool hit = false, overflow = false;
+            if (lane == 0) stack[0] = 0u;  // (root, root)
+            __syncwarp();
+            while (sp > 0 || lq > 0) {
+                if (lq >= 8 || sp == 0) {
+                    // ---- C: up to eight leaf pairs, lane = (slot, robot triangle of the leaf)
+                    const int cnt = min(lq, 8);
+                    lq -= cnt;
+                    const int slot = lane >> 2, ri = lane & 3;
+                    bool act = slot < cnt;
+                    const uint32_t e = leafq[lq + (act ? slot : 0)];
+                    const int na = e >> 16, nb = e & 0xffffu;
+                    const uint32_t rfirst = __float_as_uint(s_rob_bvh[2 * na].w) & 0x7fffffffu;
+                    const int rcount = (int)__float_as_uint(s_rob_bvh[2 * na + 1].w);
+                    const uint32_t ofirst = __float_as_uint(s_obs_bvh[2 * nb].w) & 0x7fffffffu;
+                    const int ocount = (int)__float_as_uint(s_obs_bvh[2 * nb + 1].w);
+                    act = act && ri < rcount;
+                    const uint2 ti = s_rob_t[rfirst + (act ? ri : 0)];
+                    const float4 A = s_rob_v[ti.x & 0xffffu], B = s_rob_v[ti.x >> 16], C = s_rob_v[ti.y];
+                    Tri r;
+                    xform(m, A.x, A.y, A.z, r.ax, r.ay, r.az);
+                    xform(m, B.x, B.y, B.z, r.bx, r.by, r.bz);
+                    xform(m, C.x, C.y, C.z, r.cx, r.cy, r.cz);
+                    const Plane pr = plane_of(r);
+                    bool h = false;
+#pragma unroll
+                    for (int q = 0; q < kLeafTrisDev; q++) {
+                        const int k = ofirst + min(q, ocount - 1);
+                        const float4 oa = s_obs_a[k], ob = s_obs_b[k], oc = s_obs_c[k];
+                        const Tri o = {oa.x, oa.y, oa.z, ob.x, ob.y, ob.z, oc.x, oc.y, oc.z};
+                        const Plane po = {oa.w, ob.w, oc.w, s_obs_d[k].x};
+                        if (act && q < ocount && pair_hits(r, pr, o, po)) h = true;
+                    }
+                    if (STATS) { st_leaves += cnt; st_tris += (act ? ocount : 0); }
+                    if (__any_sync(kFull, h)) { hit = true; break; }
+                    __syncwarp();
+                    continue;
+                }
+                // ---- B: pop up to 32 node pairs, test, push children
+                const int cnt = min(sp, 32);
+                sp -= cnt;
+                const bool act = lane < cnt;
+                const uint32_t e = stack[sp + (act ? lane : 0)];
+                const int na = e >> 16, nb = e & 0xffffu;
+                const float4 r0 = s_rob_bvh[2 * na], r1 = s_rob_bvh[2 * na + 1];
+                const float4 o0 = s_obs_bvh[2 * nb], o1 = s_obs_bvh[2 * nb + 1];
+                const bool ov = act && boxes_overlap(m, r0, r1, o0, o1);
+                const uint32_t ra = __float_as_uint(r0.w), rb = __float_as_uint(r1.w);
+                const uint32_t oa = __float_as_uint(o0.w), ob = __float_as_uint(o1.w);
+                const bool la = (ra & 0x80000000u) != 0, lb = (oa & 0x80000000u) != 0;
+                if (STATS) st_nodes += cnt;
+                __syncwarp();  // everybody has read its entry before the slots are reused
+                const bool ll = ov && la && lb;
+                const unsigned mll = __ballot_sync(kFull, ll);
+                if (ll) leafq[lq + __popc(mll & lt)] = e;
+                lq += __popc(mll);
+                const bool two = ov && (la != lb), four = ov && !la && !lb;
+                const unsigned m2 = __ballot_sync(kFull, two), m4 = __ballot_sync(kFull, four);
+                const int total = 2 * __popc(m2) + 4 * __popc(m4);
+                if (sp + total > kStackCap) { overflow = true; break; }
+                const int off = sp + 2 * __popc(m2 & lt) + 4 * __popc(m4 & lt);
+                if (two) {
+                    if (la) {  // robot node is a leaf: descend the obstacle node
+                        stack[off] = ((uint32_t)na << 16) | oa;
+                        stack[off + 1] = ((uint32_t)na << 16) | ob;
+                    } else {
+                        stack[off] = (ra << 16) | (uint32_t)nb;
+                        stack[off + 1] = (rb << 16) | (uint32_t)nb;
+                    }
+                } else if (four) {
+                    stack[off] = (ra << 16) | oa;
+                    stack[off + 1] = (ra << 16) | ob;
+                    stack[off + 2] = (rb << 16) | oa;
+                    stack[off + 3] = (rb << 16) | ob;
+                }
+                sp += total;
+                __syncwarp();
+            }
+            if (overflow) {
+                if (STATS) st_over++;
+                hit = narrow_exhaustive(m, s_rob_v, s_rob_t, c.n_rob_t, s_obs_a, s_obs_b, s_obs_c,
+                                        s_obs_d, c.n_obs_t, lane);
+            }
+            __syncwarp();
+            publish(c, i, !hit, lane);
+            if (STATS) { if (hit) st_invalid++; else st_valid++; }
+        }
+    }
+    if (STATS) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) st_tris += __shfl_xor_sync(kFull, st_tris, o);
+        if (lane == 0) {
+            atomicAdd(c.counters + CNT_BROAD_CLEARED, st_broad);
+            atomicAdd(c.counters + CNT_SPHERE_CLEARED, st_sphere);
+            atomicAdd(c.counters + CNT_NARROW_VALID, st_valid);
+            atomicAdd(c.counters + CNT_NARROW_INVALID, st_invalid);
+            atomicAdd(c.counters + CNT_NODE_PAIRS, st_nodes);
+            atomicAdd(c.counters + CNT_LEAF_PAIRS, st_leaves);
+            atomicAdd(c.counters + CNT_TRI_PAIRS, st_tris);
+            atomicAdd(c.counters + CNT_OVERFLOW, st_over);
+        }
+    }
+}
+
+static size_t culled_smem_bytes(const DeviceTables &t)
+{
+    size_t b = 16 + (size_t)t.n_rob_v_pad * 16 + (size_t)t.n_rob_nodes * 32 +
+               (size_t)t.n_obs_nodes * 32 + (size_t)t.n_obs_t * 64 +
+               (size_t)(t.n_rob_t + (t.n_rob_t & 1)) * 8;
+    b += (size_t)kCulledWarps * (kStackCap + kLeafQCap) * 4;
+    return b;
+}
+
+cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, long n,
+                                uint8_t *d_valid, uint32_t *d_bitmask, int want_stats,
+                                cudaStream_t stream)
+{
+    const DeviceTables &t = ctx->t;
+    const size_t smem = culled_smem_bytes(t);
+    if (smem > (size_t)ctx->max_smem_optin || t.n_rob_nodes > 65535 || t.n_obs_nodes > 65535 ||
+        t.n_rob_v > 65535)
+        return cudaErrorInvalidConfiguration;
+    CulledArgs a;
+    a.c.rob_v = t.rob_v; a.c.rob_t = t.rob_t_sorted;
+    a.c.obs_a = t.obs_a_sorted; a.c.obs_b = t.obs_b_sorted; a.c.obs_c = t.obs_c_sorted;
+    a.c.obs_d = t.obs_d_sorted;
+    a.c.n_rob_v_pad = t.n_rob_v_pad; a.c.n_rob_t = t.n_rob_t; a.c.n_obs_t = t.n_obs_t;
+    a.c.obs_box = t.obs_box;
+    a.c.confs = d_confs; a.c.n = n; a.c.valid = d_valid; a.c.bitmask = d_bitmask;
+    a.c.counters = ctx->d_counters;
+    a.rob_bvh = t.rob_bvh; a.obs_bvh = t.obs_bvh;
+    a.n_rob_nodes = t.n_rob_nodes; a.n_obs_nodes = t.n_obs_nodes;
+    a.sph_x = t.rob_center[0]; a.sph_y = t.rob_center[1]; a.sph_z = t.rob_center[2];
+    a.sph_r = t.rob_radius;
+    const int grid = ctx->sm_count;
+    const long warps = (long)grid * kCulledWarps;
+    a.c.chunk = (int)max(1L, min(16L, n / (warps * 8)));
+    auto kern = want_stats ? check_culled_kernel<true> : check_culled_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, kCulledThreads, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace rc

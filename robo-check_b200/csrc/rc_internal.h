@@ -1,0 +1,110 @@
+// rc_internal.h -- context layout shared by the C-ABI translation units (not installed).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/robocheck.h"
+
+namespace rc {
+
+// Device-resident mesh tables, laid out for 128-bit loads and for staging into shared
+// memory with one TMA bulk copy per table (every table starts 16-byte aligned and its
+// byte size is a multiple of 16).
+struct DeviceTables {
+    // robot, local frame
+    float4 *rob_v = nullptr;    // [n_rob_v]  (x, y, z, 0)
+    uint2 *rob_t = nullptr;     // [n_rob_t]  (v1 | v2 << 16, v3)          indices < 65536
+    rc_vec3 *rob_aos = nullptr; // [n_rob_v]  AoS copy for the genTransformedCopies stage
+    // obstacle, world frame, gathered per triangle ("SoA of float4")
+    float4 *obs_a = nullptr;    // [n_obs_t]  (p1.x, p1.y, p1.z, N.x)
+    float4 *obs_b = nullptr;    // [n_obs_t]  (p2.x, p2.y, p2.z, N.y)
+    float4 *obs_c = nullptr;    // [n_obs_t]  (p3.x, p3.y, p3.z, N.z)
+    float4 *obs_d = nullptr;    // [n_obs_t]  (s = N.p1, 0, 0, 0)
+    // BVHs for the culled path (see bvh.h): two float4 per node
+    float4 *rob_bvh = nullptr;  // [2 * n_rob_nodes]
+    float4 *obs_bvh = nullptr;  // [2 * n_obs_nodes]
+    uint2 *rob_t_sorted = nullptr;   // robot triangles in BVH leaf order
+    float4 *obs_a_sorted = nullptr, *obs_b_sorted = nullptr, *obs_c_sorted = nullptr,
+           *obs_d_sorted = nullptr;  // obstacle triangles in BVH leaf order
+    int n_rob_v = 0, n_rob_t = 0, n_obs_v = 0, n_obs_t = 0;
+    int n_rob_nodes = 0, n_obs_nodes = 0;
+    int n_rob_v_pad = 0;        // n_rob_v rounded up to 32 (padding repeats vertex 0)
+    rc_aabb obs_box;
+    float rob_center[3];        // bounding sphere of the robot in its local frame
+    float rob_radius;
+};
+
+}  // namespace rc
+
+struct rc_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    rc::DeviceTables t;
+    // host copies (for rc_get_* and for rebuilding)
+    std::vector<float> rob_x, rob_y, rob_z, obs_x, obs_y, obs_z;
+    std::vector<int> rob_v1, rob_v2, rob_v3, obs_v1, obs_v2, obs_v3;
+    // scratch owned by the context
+    unsigned long long *d_counters = nullptr;  // [RC_NUM_COUNTERS] work queue + statistics
+    rc_aabb *d_obs_box = nullptr;              // obstacle AABB on the device (broad-phase stage)
+    int stats_on = 0;
+    unsigned long long launches = 0;           // kernels launched through this context
+    rc_config *d_stage_confs = nullptr;        // device staging for rc_check_host
+    uint8_t *d_stage_valid = nullptr;
+    rc_config *h_pinned_confs = nullptr;
+    uint8_t *h_pinned_valid = nullptr;
+    long stage_capacity = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_kernel_ms = 0.f;
+    std::string last_error;
+    std::vector<void *> allocations;
+};
+
+namespace rc {
+
+enum Counter {
+    CNT_QUEUE = 0,        // next configuration index (persistent work queue)
+    CNT_BROAD_CLEARED,    // statistics below are only updated when stats are requested
+    CNT_SPHERE_CLEARED,
+    CNT_NARROW_VALID,
+    CNT_NARROW_INVALID,
+    CNT_NODE_PAIRS,
+    CNT_LEAF_PAIRS,
+    CNT_TRI_PAIRS,
+    CNT_TAIL_PAIRS,
+    CNT_OVERFLOW,
+    CNT_LAUNCHES,
+    RC_NUM_COUNTERS = 16
+};
+
+int set_error(rc_ctx *ctx, int code, const std::string &msg);
+int check_cuda(rc_ctx *ctx, cudaError_t e, const char *what);
+
+// kernels.cu launchers (all asynchronous on `stream`)
+cudaError_t launch_check(const rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_valid,
+                         uint32_t *d_bitmask, int mode, int want_stats, cudaStream_t stream);
+cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, long n,
+                                uint8_t *d_valid, uint32_t *d_bitmask, int want_stats,
+                                cudaStream_t stream);
+cudaError_t launch_fma_peak(float *d_out, int grid, int iters, cudaStream_t stream);
+cudaError_t launch_transform_soa(const rc_ctx *ctx, const rc_config *d_confs, long n, float *d_x,
+                                 float *d_y, float *d_z, rc_aabb *d_aabb, uint8_t *d_valid,
+                                 cudaStream_t stream);
+cudaError_t launch_transform_aos(const rc_ctx *ctx, const rc_config *d_confs, long n,
+                                 const rc_vec3 *d_base, int n_v, rc_vec3 *d_out, cudaStream_t stream);
+cudaError_t launch_aabb_aos(const rc_vec3 *d_verts, unsigned n_v, unsigned n, rc_aabb *d_out,
+                            cudaStream_t stream);
+cudaError_t launch_aabb_soa(const float *d_x, const float *d_y, const float *d_z, unsigned n_v,
+                            unsigned n, rc_aabb *d_out, cudaStream_t stream);
+cudaError_t launch_broad(long n, const rc_aabb *d_robots, const rc_aabb *d_obstacle,
+                         uint8_t *d_valid, cudaStream_t stream);
+cudaError_t launch_narrow_soa(const rc_ctx *ctx, const float *d_x, const float *d_y,
+                              const float *d_z, long n, uint8_t *d_valid, cudaStream_t stream);
+cudaError_t launch_obstacle_planes(const float4 *a, const float4 *b, const float4 *c, float4 *a_out,
+                                   float4 *b_out, float4 *c_out, float4 *d_out, int n,
+                                   cudaStream_t stream);
+
+}  // namespace rc

@@ -1,0 +1,284 @@
+// rc_kernels.cu -- sm_100a kernels of the per-configuration collision check.
+//
+//   check_brute_kernel   fused transform + AABB + broad + exhaustive narrow phase; one warp per
+//                        configuration, persistent grid with an atomic work queue.  Lane = robot
+//                        triangle, obstacle triangles are broadcast from shared memory (SoA of
+//                        float4 staged with TMA bulk copies).  Exact by construction: it decides
+//                        every one of the n_rob_t x n_obs_t pairs the reference decides
+//                        (narrowPhaseKernel_coarse, narrow-phase.cu:586-677).
+//   check_culled_kernel  same result, BVH-culled (rc_culled.cuh).
+//   stage kernels        the un-fused stage API (transform / AABB / broad / narrow).
+#include <float.h>
+
+#include "rc_device.cuh"
+#include "rc_internal.h"
+
+namespace rc {
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kThreads = kWarpsPerCta * 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+// ------------------------------------------------------------------------------------------
+// Obstacle planes: configuration independent, computed once per context with the same
+// arithmetic the reference re-executes per pair (compute_plane_sep, narrow-phase.cu:629).
+__global__ void obstacle_planes_kernel(const float4 *a, const float4 *b, const float4 *c,
+                                       float4 *a_out, float4 *b_out, float4 *c_out, float4 *d_out,
+                                       int n)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const float4 A = a[k], B = b[k], C = c[k];
+    const Tri t = {A.x, A.y, A.z, B.x, B.y, B.z, C.x, C.y, C.z};
+    const Plane p = plane_of(t);
+    a_out[k] = make_float4(A.x, A.y, A.z, p.nx);
+    b_out[k] = make_float4(B.x, B.y, B.z, p.ny);
+    c_out[k] = make_float4(C.x, C.y, C.z, p.nz);
+    d_out[k] = make_float4(p.s, 0.f, 0.f, 0.f);
+}
+
+cudaError_t launch_obstacle_planes(const float4 *a, const float4 *b, const float4 *c, float4 *a_out,
+                                   float4 *b_out, float4 *c_out, float4 *d_out, int n,
+                                   cudaStream_t stream)
+{
+    if (n <= 0) return cudaSuccess;
+    obstacle_planes_kernel<<<(n + 127) / 128, 128, 0, stream>>>(a, b, c, a_out, b_out, c_out, d_out, n);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// shared helpers
+
+__device__ __forceinline__ float warp_min(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+
+__device__ __forceinline__ Mat34 load_matrix(const rc_config *confs, long i)
+{
+    // 24-byte records: three 8-byte loads (always 8-byte aligned)
+    const float2 *p = reinterpret_cast<const float2 *>(confs + i);
+    const float2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    return make_matrix(a.x, a.y, b.x, b.y, c.x, c.y);
+}
+
+// Transform every robot vertex of one configuration with the lanes striding over the
+// (padded) vertex table, reduce the AABB with warp shuffles.  All lanes return the box.
+__device__ __forceinline__ void warp_aabb(const Mat34 &m, const float4 *__restrict__ s_rob_v,
+                                          int n_v_pad, int lane, float box[6])
+{
+    float lx = FLT_MAX, ly = FLT_MAX, lz = FLT_MAX, hx = -FLT_MAX, hy = -FLT_MAX, hz = -FLT_MAX;
+    for (int v = lane; v < n_v_pad; v += 32) {
+        const float4 p = s_rob_v[v];
+        float x, y, z;
+        xform(m, p.x, p.y, p.z, x, y, z);
+        lx = fminf(lx, x); hx = fmaxf(hx, x);
+        ly = fminf(ly, y); hy = fmaxf(hy, y);
+        lz = fminf(lz, z); hz = fmaxf(hz, z);
+    }
+    box[0] = warp_min(lx); box[1] = warp_min(ly); box[2] = warp_min(lz);
+    box[3] = warp_max(hx); box[4] = warp_max(hy); box[5] = warp_max(hz);
+}
+
+struct CheckArgs {
+    const float4 *rob_v;   // [n_rob_v_pad]
+    const uint2 *rob_t;    // [n_rob_t]
+    const float4 *obs_a, *obs_b, *obs_c, *obs_d;  // [n_obs_t]
+    int n_rob_v_pad, n_rob_t, n_obs_t;
+    rc_aabb obs_box;
+    const rc_config *confs;
+    long n;
+    uint8_t *valid;
+    uint32_t *bitmask;
+    unsigned long long *counters;
+    int chunk;
+};
+
+__device__ __forceinline__ void publish(const CheckArgs &a, long i, bool valid, int lane)
+{
+    if (lane == 0) {
+        if (a.valid) a.valid[i] = valid ? 1 : 0;
+        if (a.bitmask && valid) atomicOr(a.bitmask + (i >> 5), 1u << (i & 31));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Brute-force fused kernel.
+
+template <bool STATS>
+__global__ void __launch_bounds__(kThreads, 2) check_brute_kernel(const CheckArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    float4 *s_rob_v = reinterpret_cast<float4 *>(smem_raw + 16);
+    float4 *s_obs_a = s_rob_v + a.n_rob_v_pad;
+    float4 *s_obs_b = s_obs_a + a.n_obs_t;
+    float4 *s_obs_c = s_obs_b + a.n_obs_t;
+    float4 *s_obs_d = s_obs_c + a.n_obs_t;
+    uint2 *s_rob_t = reinterpret_cast<uint2 *>(s_obs_d + a.n_obs_t);
+
+    // Stage the mesh tables with TMA bulk copies (one elected thread issues them, everybody
+    // waits on the mbarrier's transaction count).
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t bv = a.n_rob_v_pad * 16u, bo = a.n_obs_t * 16u,
+                       bt = (a.n_rob_t + (a.n_rob_t & 1)) * 8u;
+        mbar_expect_tx(bar, bv + 4u * bo + bt);
+        tma_load_1d(s_rob_v, a.rob_v, bv, bar);
+        tma_load_1d(s_obs_a, a.obs_a, bo, bar);
+        tma_load_1d(s_obs_b, a.obs_b, bo, bar);
+        tma_load_1d(s_obs_c, a.obs_c, bo, bar);
+        tma_load_1d(s_obs_d, a.obs_d, bo, bar);
+        tma_load_1d(s_rob_t, a.rob_t, bt, bar);
+    }
+    mbar_wait(bar, 0);
+
+    const int lane = threadIdx.x & 31;
+    unsigned long long st_broad = 0, st_valid = 0, st_invalid = 0, st_tail = 0;
+
+    for (;;) {
+        long base = 0;
+        if (lane == 0) base = (long)atomicAdd(a.counters + CNT_QUEUE, (unsigned long long)a.chunk);
+        base = __shfl_sync(kFull, base, 0);
+        if (base >= a.n) break;
+        const long end = min(base + (long)a.chunk, a.n);
+        for (long i = base; i < end; i++) {
+            const Mat34 m = load_matrix(a.confs, i);
+            float box[6];
+            warp_aabb(m, s_rob_v, a.n_rob_v_pad, lane, box);
+            if (broad_valid(box[0], box[1], box[2], box[3], box[4], box[5], a.obs_box.x_min,
+                            a.obs_box.y_min, a.obs_box.z_min, a.obs_box.x_max, a.obs_box.y_max,
+                            a.obs_box.z_max)) {
+                publish(a, i, true, lane);
+                if (STATS) st_broad++;
+                continue;
+            }
+            bool hit = false;
+            for (int jb = 0; jb < a.n_rob_t && !hit; jb += 32) {
+                const int j = jb + lane;
+                const bool active = j < a.n_rob_t;
+                const uint2 ti = s_rob_t[active ? j : a.n_rob_t - 1];
+                const float4 A = s_rob_v[ti.x & 0xffffu], B = s_rob_v[ti.x >> 16], C = s_rob_v[ti.y];
+                Tri r;
+                xform(m, A.x, A.y, A.z, r.ax, r.ay, r.az);
+                xform(m, B.x, B.y, B.z, r.bx, r.by, r.bz);
+                xform(m, C.x, C.y, C.z, r.cx, r.cy, r.cz);
+                const Plane pr = plane_of(r);
+                int pend = -1;  // obstacle triangle that passed the first plane test, not yet finished
+
+                auto finish = [&](int k) {
+                    const float4 oa = s_obs_a[k], ob = s_obs_b[k], oc = s_obs_c[k];
+                    const Tri o = {oa.x, oa.y, oa.z, ob.x, ob.y, ob.z, oc.x, oc.y, oc.z};
+                    const Plane po = {oa.w, ob.w, oc.w, s_obs_d[k].x};
+                    const float dR0 = sdist(po, r.ax, r.ay, r.az), dR1 = sdist(po, r.bx, r.by, r.bz),
+                                dR2 = sdist(po, r.cx, r.cy, r.cz);
+                    if (straddles(dR0, dR1, dR2)) {
+                        if (STATS) st_tail++;
+                        const float dO0 = sdist(pr, o.ax, o.ay, o.az), dO1 = sdist(pr, o.bx, o.by, o.bz),
+                                    dO2 = sdist(pr, o.cx, o.cy, o.cz);
+                        if (pair_tail(r, pr, dR0, dR1, dR2, o, po, dO0, dO1, dO2)) hit = true;
+                    }
+                };
+
+                for (int k = 0; k < a.n_obs_t; k++) {
+                    const float4 oa = s_obs_a[k], ob = s_obs_b[k], oc = s_obs_c[k];  // broadcast
+                    const float d0 = sdist(pr, oa.x, oa.y, oa.z), d1 = sdist(pr, ob.x, ob.y, ob.z),
+                                d2 = sdist(pr, oc.x, oc.y, oc.z);
+                    const bool pass = active && straddles(d0, d1, d2);
+                    // The rest of the test runs at most once per lane between two warp-wide
+                    // flushes, so the rare path executes with several lanes instead of one.
+                    if (__any_sync(kFull, pass && pend >= 0)) {
+                        if (pend >= 0) finish(pend);
+                        pend = -1;
+                        if (__any_sync(kFull, hit)) break;
+                    }
+                    if (pass) pend = k;
+                }
+                if (pend >= 0) finish(pend);
+                hit = __any_sync(kFull, hit);
+            }
+            publish(a, i, !hit, lane);
+            if (STATS) { if (hit) st_invalid++; else st_valid++; }
+        }
+    }
+    if (STATS) {
+        // per-config counters are warp-uniform (count on lane 0); tail counts are per lane
+        st_tail = st_tail + __shfl_xor_sync(kFull, st_tail, 16);
+        st_tail = st_tail + __shfl_xor_sync(kFull, st_tail, 8);
+        st_tail = st_tail + __shfl_xor_sync(kFull, st_tail, 4);
+        st_tail = st_tail + __shfl_xor_sync(kFull, st_tail, 2);
+        st_tail = st_tail + __shfl_xor_sync(kFull, st_tail, 1);
+        if (lane == 0) {
+            atomicAdd(a.counters + CNT_BROAD_CLEARED, st_broad);
+            atomicAdd(a.counters + CNT_NARROW_VALID, st_valid);
+            atomicAdd(a.counters + CNT_NARROW_INVALID, st_invalid);
+            atomicAdd(a.counters + CNT_TAIL_PAIRS, st_tail);
+            atomicAdd(a.counters + CNT_TRI_PAIRS,
+                      (st_valid + st_invalid) * 0ull);  // exhaustive: derived on the host
+        }
+    }
+}
+
+}  // namespace rc
+
+#include "rc_culled.cuh"
+#include "rc_stages.cuh"
+
+namespace rc {
+
+static size_t brute_smem_bytes(const DeviceTables &t)
+{
+    return 16 + (size_t)t.n_rob_v_pad * 16 + (size_t)t.n_obs_t * 64 +
+           (size_t)(t.n_rob_t + (t.n_rob_t & 1)) * 8;
+}
+
+cudaError_t launch_check(const rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_valid,
+                         uint32_t *d_bitmask, int mode, int want_stats, cudaStream_t stream)
+{
+    const DeviceTables &t = ctx->t;
+    cudaError_t e;
+    if (n <= 0) return cudaSuccess;
+    if ((e = cudaMemsetAsync(ctx->d_counters + CNT_QUEUE, 0, sizeof(unsigned long long), stream)) !=
+        cudaSuccess)
+        return e;
+    if (d_bitmask &&
+        (e = cudaMemsetAsync(d_bitmask, 0, (size_t)((n + 31) / 32) * 4, stream)) != cudaSuccess)
+        return e;
+
+    if (mode == RC_MODE_BRUTE) {
+        CheckArgs a;
+        a.rob_v = t.rob_v; a.rob_t = t.rob_t;
+        a.obs_a = t.obs_a; a.obs_b = t.obs_b; a.obs_c = t.obs_c; a.obs_d = t.obs_d;
+        a.n_rob_v_pad = t.n_rob_v_pad; a.n_rob_t = t.n_rob_t; a.n_obs_t = t.n_obs_t;
+        a.obs_box = t.obs_box;
+        a.confs = d_confs; a.n = n; a.valid = d_valid; a.bitmask = d_bitmask;
+        a.counters = ctx->d_counters;
+        const size_t smem = brute_smem_bytes(t);
+        if (smem > (size_t)ctx->max_smem_optin) return cudaErrorInvalidConfiguration;
+        const int ctas_per_sm = (2 * smem + 2048 <= (size_t)ctx->max_smem_optin) ? 2 : 1;
+        const int grid = ctx->sm_count * ctas_per_sm;
+        const long warps = (long)grid * kWarpsPerCta;
+        a.chunk = (int)max(1L, min(8L, n / (warps * 16)));
+        auto kern = want_stats ? check_brute_kernel<true> : check_brute_kernel<false>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem)) != cudaSuccess)
+            return e;
+        kern<<<grid, kThreads, smem, stream>>>(a);
+        return cudaGetLastError();
+    }
+    return launch_check_culled(ctx, d_confs, n, d_valid, d_bitmask, want_stats, stream);
+}
+
+}  // namespace rc

@@ -1,0 +1,394 @@
+// rc_stages.cuh -- the un-fused stage API of the reference, one kernel per stage, for callers
+// that drive the stages themselves (transform.hu, generate-AABB.hu, broad-phase.hu,
+// broad-phase-fused.hu, narrow-phase.hu).  The materialising stages are HBM-bound: every
+// global access is coalesced (the reference's thread-per-configuration kernels stride by a whole
+// configuration between lanes) and configurations are spread over a grid of warps sized from the
+// SM count.
+#pragma once
+
+namespace rc {
+
+constexpr int kStageWarps = 8;
+constexpr int kStageThreads = kStageWarps * 32;
+
+// ---- broadPhaseFusedKernel_sep (broad-phase-fused.cu:157-207) ------------------------------
+// One warp per configuration.  Lane l owns vertices 4l..4l+3 of each group of 128, so the three
+// SoA rows are written with 128-bit stores that a warp coalesces into 512 contiguous bytes.
+// Row i starts at element i * n_v, which is 16-byte aligned when n_v % 4 == 0 (792 is); other
+// sizes take the scalar path.
+template <bool STORE>
+__global__ void __launch_bounds__(kStageThreads) transform_soa_kernel(
+    const float4 *__restrict__ rob_v, int n_v, int n_v_pad, const rc_config *__restrict__ confs,
+    long n, rc_aabb obs_box, float *__restrict__ ox, float *__restrict__ oy, float *__restrict__ oz,
+    rc_aabb *__restrict__ out_box, uint8_t *__restrict__ valid)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *sx = reinterpret_cast<float *>(smem_raw);  // SoA copies of the robot, padded
+    float *sy = sx + n_v_pad;
+    float *sz = sy + n_v_pad;
+    for (int v = threadIdx.x; v < n_v_pad; v += blockDim.x) {
+        const float4 p = rob_v[v];
+        sx[v] = p.x; sy[v] = p.y; sz[v] = p.z;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long warp = (long)blockIdx.x * kStageWarps + (threadIdx.x >> 5);
+    const long n_warps = (long)gridDim.x * kStageWarps;
+    const bool vec = STORE && (n_v % 4 == 0) && ((reinterpret_cast<uintptr_t>(ox) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(oy) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(oz) & 15) == 0);
+    for (long i = warp; i < n; i += n_warps) {
+        const Mat34 m = load_matrix(confs, i);
+        float lx = FLT_MAX, ly = FLT_MAX, lz = FLT_MAX, hx = -FLT_MAX, hy = -FLT_MAX, hz = -FLT_MAX;
+        const size_t row = (size_t)i * n_v;
+        if (vec) {
+            for (int v = 4 * lane; v < n_v; v += 128) {
+                const float4 X = *reinterpret_cast<const float4 *>(sx + v);
+                const float4 Y = *reinterpret_cast<const float4 *>(sy + v);
+                const float4 Z = *reinterpret_cast<const float4 *>(sz + v);
+                float4 wx, wy, wz;
+                xform(m, X.x, Y.x, Z.x, wx.x, wy.x, wz.x);
+                xform(m, X.y, Y.y, Z.y, wx.y, wy.y, wz.y);
+                xform(m, X.z, Y.z, Z.z, wx.z, wy.z, wz.z);
+                xform(m, X.w, Y.w, Z.w, wx.w, wy.w, wz.w);
+                __stcs(reinterpret_cast<float4 *>(ox + row + v), wx);
+                __stcs(reinterpret_cast<float4 *>(oy + row + v), wy);
+                __stcs(reinterpret_cast<float4 *>(oz + row + v), wz);
+                lx = fminf(lx, fminf(fminf(wx.x, wx.y), fminf(wx.z, wx.w)));
+                hx = fmaxf(hx, fmaxf(fmaxf(wx.x, wx.y), fmaxf(wx.z, wx.w)));
+                ly = fminf(ly, fminf(fminf(wy.x, wy.y), fminf(wy.z, wy.w)));
+                hy = fmaxf(hy, fmaxf(fmaxf(wy.x, wy.y), fmaxf(wy.z, wy.w)));
+                lz = fminf(lz, fminf(fminf(wz.x, wz.y), fminf(wz.z, wz.w)));
+                hz = fmaxf(hz, fmaxf(fmaxf(wz.x, wz.y), fmaxf(wz.z, wz.w)));
+            }
+        } else {
+            for (int v = lane; v < n_v; v += 32) {
+                float x, y, z;
+                xform(m, sx[v], sy[v], sz[v], x, y, z);
+                if (STORE) {
+                    ox[row + v] = x; oy[row + v] = y; oz[row + v] = z;
+                }
+                lx = fminf(lx, x); hx = fmaxf(hx, x);
+                ly = fminf(ly, y); hy = fmaxf(hy, y);
+                lz = fminf(lz, z); hz = fmaxf(hz, z);
+            }
+        }
+        lx = warp_min(lx); ly = warp_min(ly); lz = warp_min(lz);
+        hx = warp_max(hx); hy = warp_max(hy); hz = warp_max(hz);
+        if (lane == 0) {
+            if (out_box) out_box[i] = rc_aabb{lx, ly, lz, hx, hy, hz};
+            if (valid)
+                valid[i] = broad_valid(lx, ly, lz, hx, hy, hz, obs_box.x_min, obs_box.y_min,
+                                       obs_box.z_min, obs_box.x_max, obs_box.y_max, obs_box.z_max)
+                               ? 1 : 0;
+        }
+    }
+}
+
+cudaError_t launch_transform_soa(const rc_ctx *ctx, const rc_config *d_confs, long n, float *d_x,
+                                 float *d_y, float *d_z, rc_aabb *d_aabb, uint8_t *d_valid,
+                                 cudaStream_t stream)
+{
+    if (n <= 0) return cudaSuccess;
+    const DeviceTables &t = ctx->t;
+    const size_t smem = (size_t)t.n_rob_v_pad * 12;
+    const long want = (n + kStageWarps - 1) / kStageWarps;
+    const int grid = (int)min(want, (long)ctx->sm_count * 8);
+    const bool store = d_x && d_y && d_z;
+    auto kern = store ? transform_soa_kernel<true> : transform_soa_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, kStageThreads, smem, stream>>>(t.rob_v, t.n_rob_v, t.n_rob_v_pad, d_confs, n,
+                                                t.obs_box, d_x, d_y, d_z, d_aabb, d_valid);
+    return cudaGetLastError();
+}
+
+// ---- genTransformedCopies (transformation/transform.cu:65-97) ------------------------------
+// AoS output [conf][vertex] of 12-byte records.  The reference writes it with a stride of a
+// whole configuration between lanes; here a warp transposes 32 vertices through shared memory
+// and writes 3 x 128 contiguous bytes.
+__global__ void __launch_bounds__(kStageThreads) transform_aos_kernel(
+    const rc_vec3 *__restrict__ base, int n_v, const rc_config *__restrict__ confs, long n,
+    rc_vec3 *__restrict__ out)
+{
+    __shared__ float tile[kStageWarps][96];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long warp = (long)blockIdx.x * kStageWarps + w;
+    const long n_warps = (long)gridDim.x * kStageWarps;
+    const float *bf = reinterpret_cast<const float *>(base);
+    float *of = reinterpret_cast<float *>(out);
+    for (long i = warp; i < n; i += n_warps) {
+        const Mat34 m = load_matrix(confs, i);
+        for (int v0 = 0; v0 < n_v; v0 += 32) {
+            const int cnt = min(32, n_v - v0);
+            // coalesced read of 3*cnt floats, transposed through the tile
+            for (int e = lane; e < 3 * cnt; e += 32) tile[w][e] = __ldg(bf + 3 * (size_t)v0 + e);
+            __syncwarp();
+            float x = 0.f, y = 0.f, z = 0.f;
+            if (lane < cnt) xform(m, tile[w][3 * lane], tile[w][3 * lane + 1], tile[w][3 * lane + 2], x, y, z);
+            __syncwarp();
+            if (lane < cnt) {
+                tile[w][3 * lane] = x; tile[w][3 * lane + 1] = y; tile[w][3 * lane + 2] = z;
+            }
+            __syncwarp();
+            float *dst = of + 3 * ((size_t)i * n_v + v0);
+            for (int e = lane; e < 3 * cnt; e += 32) dst[e] = tile[w][e];
+            __syncwarp();
+        }
+    }
+}
+
+cudaError_t launch_transform_aos(const rc_ctx *ctx, const rc_config *d_confs, long n,
+                                 const rc_vec3 *d_base, int n_v, rc_vec3 *d_out, cudaStream_t stream)
+{
+    if (n <= 0 || n_v <= 0) return cudaSuccess;
+    const long want = (n + kStageWarps - 1) / kStageWarps;
+    const int grid = (int)min(want, (long)ctx->sm_count * 8);
+    transform_aos_kernel<<<grid, kStageThreads, 0, stream>>>(d_base, n_v, d_confs, n, d_out);
+    return cudaGetLastError();
+}
+
+// ---- generateAABBPrimitiveKernel (generate-AABB.cu:7-35) ----------------------------------
+// min/max per configuration over AoS vertices; one warp per configuration reads the 3*n_v floats
+// of the row contiguously, each lane keeping the running min/max of the component it lands on.
+__global__ void __launch_bounds__(kStageThreads) aabb_aos_kernel(const rc_vec3 *__restrict__ verts,
+                                                                 unsigned n_v, unsigned n,
+                                                                 rc_aabb *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const size_t warp = (size_t)blockIdx.x * kStageWarps + (threadIdx.x >> 5);
+    const size_t n_warps = (size_t)gridDim.x * kStageWarps;
+    const float *f = reinterpret_cast<const float *>(verts);
+    for (size_t i = warp; i < n; i += n_warps) {
+        float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        const float *row = f + 3 * i * n_v;
+        const unsigned total = 3 * n_v;
+        // 96 = lcm(32, 3): within a block of 96 floats lane l sees components (l, l+32, l+64) % 3
+        const int c0 = lane % 3, c1 = (lane + 32) % 3, c2 = (lane + 64) % 3;
+        for (unsigned e = lane; e < total; e += 96) {
+            const float a = __ldcs(row + e);
+            if (c0 == 0) { lo[0] = fminf(lo[0], a); hi[0] = fmaxf(hi[0], a); }
+            else if (c0 == 1) { lo[1] = fminf(lo[1], a); hi[1] = fmaxf(hi[1], a); }
+            else { lo[2] = fminf(lo[2], a); hi[2] = fmaxf(hi[2], a); }
+            if (e + 32 < total) {
+                const float b = __ldcs(row + e + 32);
+                if (c1 == 0) { lo[0] = fminf(lo[0], b); hi[0] = fmaxf(hi[0], b); }
+                else if (c1 == 1) { lo[1] = fminf(lo[1], b); hi[1] = fmaxf(hi[1], b); }
+                else { lo[2] = fminf(lo[2], b); hi[2] = fmaxf(hi[2], b); }
+            }
+            if (e + 64 < total) {
+                const float c = __ldcs(row + e + 64);
+                if (c2 == 0) { lo[0] = fminf(lo[0], c); hi[0] = fmaxf(hi[0], c); }
+                else if (c2 == 1) { lo[1] = fminf(lo[1], c); hi[1] = fmaxf(hi[1], c); }
+                else { lo[2] = fminf(lo[2], c); hi[2] = fmaxf(hi[2], c); }
+            }
+        }
+        const float lx = warp_min(lo[0]), ly = warp_min(lo[1]), lz = warp_min(lo[2]);
+        const float hx = warp_max(hi[0]), hy = warp_max(hi[1]), hz = warp_max(hi[2]);
+        if (lane == 0) out[i] = rc_aabb{lx, ly, lz, hx, hy, hz};
+    }
+}
+
+cudaError_t launch_aabb_aos(const rc_vec3 *d_verts, unsigned n_v, unsigned n, rc_aabb *d_out,
+                            cudaStream_t stream)
+{
+    if (n == 0) return cudaSuccess;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long want = ((long)n + kStageWarps - 1) / kStageWarps;
+    const int grid = (int)min(want, (long)sms * 8);
+    aabb_aos_kernel<<<grid, kStageThreads, 0, stream>>>(d_verts, n_v, n, d_out);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(kStageThreads) aabb_soa_kernel(const float *__restrict__ x,
+                                                                 const float *__restrict__ y,
+                                                                 const float *__restrict__ z,
+                                                                 unsigned n_v, unsigned n,
+                                                                 rc_aabb *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const size_t warp = (size_t)blockIdx.x * kStageWarps + (threadIdx.x >> 5);
+    const size_t n_warps = (size_t)gridDim.x * kStageWarps;
+    for (size_t i = warp; i < n; i += n_warps) {
+        float lx = FLT_MAX, ly = FLT_MAX, lz = FLT_MAX, hx = -FLT_MAX, hy = -FLT_MAX, hz = -FLT_MAX;
+        const size_t row = i * n_v;
+        for (unsigned v = lane; v < n_v; v += 32) {
+            const float a = __ldcs(x + row + v), b = __ldcs(y + row + v), c = __ldcs(z + row + v);
+            lx = fminf(lx, a); hx = fmaxf(hx, a);
+            ly = fminf(ly, b); hy = fmaxf(hy, b);
+            lz = fminf(lz, c); hz = fmaxf(hz, c);
+        }
+        lx = warp_min(lx); ly = warp_min(ly); lz = warp_min(lz);
+        hx = warp_max(hx); hy = warp_max(hy); hz = warp_max(hz);
+        if (lane == 0) out[i] = rc_aabb{lx, ly, lz, hx, hy, hz};
+    }
+}
+
+cudaError_t launch_aabb_soa(const float *d_x, const float *d_y, const float *d_z, unsigned n_v,
+                            unsigned n, rc_aabb *d_out, cudaStream_t stream)
+{
+    if (n == 0) return cudaSuccess;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long want = ((long)n + kStageWarps - 1) / kStageWarps;
+    const int grid = (int)min(want, (long)sms * 8);
+    aabb_soa_kernel<<<grid, kStageThreads, 0, stream>>>(d_x, d_y, d_z, n_v, n, d_out);
+    return cudaGetLastError();
+}
+
+// ---- broadPhaseKernel (broad-phase/broad-phase.cu:10-28) -----------------------------------
+__global__ void __launch_bounds__(256) broad_kernel(long n, const rc_aabb *__restrict__ robots,
+                                                    const rc_aabb *__restrict__ obstacle,
+                                                    uint8_t *__restrict__ valid)
+{
+    const rc_aabb o = *obstacle;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        // 24-byte records: three 8-byte loads
+        const float2 *p = reinterpret_cast<const float2 *>(robots + i);
+        const float2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+        valid[i] = broad_valid(a.x, a.y, b.x, b.y, c.x, c.y, o.x_min, o.y_min, o.z_min, o.x_max,
+                               o.y_max, o.z_max) ? 1 : 0;
+    }
+}
+
+cudaError_t launch_broad(long n, const rc_aabb *d_robots, const rc_aabb *d_obstacle,
+                         uint8_t *d_valid, cudaStream_t stream)
+{
+    if (n <= 0) return cudaSuccess;
+    const int grid = (int)min((n + 255) / 256, 148L * 16);
+    broad_kernel<<<grid, 256, 0, stream>>>(n, d_robots, d_obstacle, d_valid);
+    return cudaGetLastError();
+}
+
+// ---- narrowPhaseKernel_coarse (narrow-phase.cu:551-688) on materialised vertices ----------
+// valid[] is in/out: entries that are already 1 are skipped (:578).  One warp per remaining
+// configuration, lane = robot triangle (vertices gathered from the SoA rows), obstacle triangles
+// broadcast from shared memory, exhaustive like the reference.
+__global__ void __launch_bounds__(kThreads, 2) narrow_soa_kernel(const CheckArgs a,
+                                                                 const float *__restrict__ px,
+                                                                 const float *__restrict__ py,
+                                                                 const float *__restrict__ pz,
+                                                                 int n_rob_v)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    float4 *s_obs_a = reinterpret_cast<float4 *>(smem_raw + 16);
+    float4 *s_obs_b = s_obs_a + a.n_obs_t;
+    float4 *s_obs_c = s_obs_b + a.n_obs_t;
+    float4 *s_obs_d = s_obs_c + a.n_obs_t;
+    uint2 *s_rob_t = reinterpret_cast<uint2 *>(s_obs_d + a.n_obs_t);
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t bo = a.n_obs_t * 16u, bt = (a.n_rob_t + (a.n_rob_t & 1)) * 8u;
+        mbar_expect_tx(bar, 4u * bo + bt);
+        tma_load_1d(s_obs_a, a.obs_a, bo, bar);
+        tma_load_1d(s_obs_b, a.obs_b, bo, bar);
+        tma_load_1d(s_obs_c, a.obs_c, bo, bar);
+        tma_load_1d(s_obs_d, a.obs_d, bo, bar);
+        tma_load_1d(s_rob_t, a.rob_t, bt, bar);
+    }
+    mbar_wait(bar, 0);
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        long i = 0;
+        if (lane == 0) i = (long)atomicAdd(a.counters + CNT_QUEUE, 1ull);
+        i = __shfl_sync(kFull, i, 0);
+        if (i >= a.n) break;
+        if (a.valid[i]) continue;
+        const float *x = px + (size_t)i * n_rob_v, *y = py + (size_t)i * n_rob_v,
+                    *z = pz + (size_t)i * n_rob_v;
+        bool hit = false;
+        for (int jb = 0; jb < a.n_rob_t && !hit; jb += 32) {
+            const int j = jb + lane;
+            const bool active = j < a.n_rob_t;
+            const uint2 ti = s_rob_t[active ? j : a.n_rob_t - 1];
+            const int va = ti.x & 0xffffu, vb = ti.x >> 16, vc = ti.y;
+            const Tri r = {__ldg(x + va), __ldg(y + va), __ldg(z + va), __ldg(x + vb), __ldg(y + vb),
+                           __ldg(z + vb), __ldg(x + vc), __ldg(y + vc), __ldg(z + vc)};
+            const Plane pr = plane_of(r);
+            int pend = -1;
+            auto finish = [&](int k) {
+                const float4 oa = s_obs_a[k], ob = s_obs_b[k], oc = s_obs_c[k];
+                const Tri o = {oa.x, oa.y, oa.z, ob.x, ob.y, ob.z, oc.x, oc.y, oc.z};
+                const Plane po = {oa.w, ob.w, oc.w, s_obs_d[k].x};
+                const float dR0 = sdist(po, r.ax, r.ay, r.az), dR1 = sdist(po, r.bx, r.by, r.bz),
+                            dR2 = sdist(po, r.cx, r.cy, r.cz);
+                if (straddles(dR0, dR1, dR2)) {
+                    const float dO0 = sdist(pr, o.ax, o.ay, o.az), dO1 = sdist(pr, o.bx, o.by, o.bz),
+                                dO2 = sdist(pr, o.cx, o.cy, o.cz);
+                    if (pair_tail(r, pr, dR0, dR1, dR2, o, po, dO0, dO1, dO2)) hit = true;
+                }
+            };
+            for (int k = 0; k < a.n_obs_t; k++) {
+                const float4 oa = s_obs_a[k], ob = s_obs_b[k], oc = s_obs_c[k];
+                const float d0 = sdist(pr, oa.x, oa.y, oa.z), d1 = sdist(pr, ob.x, ob.y, ob.z),
+                            d2 = sdist(pr, oc.x, oc.y, oc.z);
+                const bool pass = active && straddles(d0, d1, d2);
+                if (__any_sync(kFull, pass && pend >= 0)) {
+                    if (pend >= 0) finish(pend);
+                    pend = -1;
+                    if (__any_sync(kFull, hit)) break;
+                }
+                if (pass) pend = k;
+            }
+            if (pend >= 0) finish(pend);
+            hit = __any_sync(kFull, hit);
+        }
+        if (lane == 0) a.valid[i] = hit ? 0 : 1;
+    }
+}
+
+cudaError_t launch_narrow_soa(const rc_ctx *ctx, const float *d_x, const float *d_y,
+                              const float *d_z, long n, uint8_t *d_valid, cudaStream_t stream)
+{
+    if (n <= 0) return cudaSuccess;
+    const DeviceTables &t = ctx->t;
+    cudaError_t e = cudaMemsetAsync(ctx->d_counters + CNT_QUEUE, 0, sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) return e;
+    CheckArgs a;
+    a.rob_v = t.rob_v; a.rob_t = t.rob_t;
+    a.obs_a = t.obs_a; a.obs_b = t.obs_b; a.obs_c = t.obs_c; a.obs_d = t.obs_d;
+    a.n_rob_v_pad = t.n_rob_v_pad; a.n_rob_t = t.n_rob_t; a.n_obs_t = t.n_obs_t;
+    a.obs_box = t.obs_box;
+    a.confs = nullptr; a.n = n; a.valid = d_valid; a.bitmask = nullptr;
+    a.counters = ctx->d_counters; a.chunk = 1;
+    const size_t smem = 16 + (size_t)t.n_obs_t * 64 + (size_t)(t.n_rob_t + (t.n_rob_t & 1)) * 8;
+    if (smem > (size_t)ctx->max_smem_optin) return cudaErrorInvalidConfiguration;
+    e = cudaFuncSetAttribute(narrow_soa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int ctas_per_sm = (2 * smem + 2048 <= (size_t)ctx->max_smem_optin) ? 2 : 1;
+    narrow_soa_kernel<<<ctx->sm_count * ctas_per_sm, kThreads, smem, stream>>>(a, d_x, d_y, d_z,
+                                                                             t.n_rob_v);
+    return cudaGetLastError();
+}
+
+// ---- FP32 FMA peak ------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fma_peak_kernel(float *out, int iters)
+{
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f,
+          a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float b = 0.9999f, c = 1e-4f;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
+            a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+cudaError_t launch_fma_peak(float *d_out, int grid, int iters, cudaStream_t stream)
+{
+    fma_peak_kernel<<<grid, 256, 0, stream>>>(d_out, iters);
+    return cudaGetLastError();
+}
+
+}  // namespace rc

@@ -1,0 +1,328 @@
+// rc_host.cpp -- host side of the hot path's callers: mesh loaders, .conf reader/writer and
+// configuration generator.  Clean-room C++ with the behaviour of the reference's utilities:
+//   OBJ loader     Utils_rai.cu:139-320   (v / vn / vt lines, `a//n` face tokens, fan split)
+//   BYU loader     models/BYU_Model_Loader.cpp:33-89, models/byu-to-obj.cpp:27-88
+//   .conf I/O      Utils_rai.cu:11-97
+//   generators     Utils_rai.cu:111-136, 322-348
+// No CUDA in this file.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <random>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/robocheck.h"
+#include "rc_mesh.h"
+
+namespace {
+
+bool is_blank(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n'; }
+
+// split a line into whitespace separated tokens (the reference uses strtok with "\t \r\n")
+std::vector<std::string> tokens_of(const std::string &line)
+{
+    std::vector<std::string> out;
+    size_t i = 0;
+    while (i < line.size()) {
+        while (i < line.size() && is_blank(line[i])) i++;
+        size_t j = i;
+        while (j < line.size() && !is_blank(line[j])) j++;
+        if (j > i) out.emplace_back(line.substr(i, j - i));
+        i = j;
+    }
+    return out;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rc_mesh_load_obj(const char *path, rc_mesh **out)
+{
+    if (!path || !out) return RC_ERR_INVALID;
+    std::ifstream in(path, std::ios::binary);
+    if (!in.good()) return RC_ERR_IO;
+    rc_mesh *m = new rc_mesh();
+    std::string line;
+    while (std::getline(in, line)) {
+        const std::vector<std::string> tok = tokens_of(line);
+        if (tok.empty() || tok[0][0] == '#') continue;
+        const std::string &head = tok[0];
+        if (head[0] == 'v') {
+            if (head.size() > 1 && (head[1] == 'n' || head[1] == 't')) continue;  // normals / uvs
+            if (tok.size() < 4) { delete m; return RC_ERR_FORMAT; }
+            // the reference converts with (float)atof(): decimal -> double -> float
+            m->x.push_back((float)atof(tok[1].c_str()));
+            m->y.push_back((float)atof(tok[2].c_str()));
+            m->z.push_back((float)atof(tok[3].c_str()));
+        } else if (head[0] == 'f') {
+            // atoi() stops at the first '/', so `a`, `a/t`, `a//n`, `a/t/n` all yield a.
+            // A polygon with k corners becomes the fan (0, t+1, t+2), t = 0..k-3.
+            const int k = (int)tok.size() - 1;
+            if (k < 3) { delete m; return RC_ERR_FORMAT; }
+            const int a = atoi(tok[1].c_str()) - 1;
+            for (int t = 0; t < k - 2; t++) {
+                m->v1.push_back(a);
+                m->v2.push_back(atoi(tok[2 + t].c_str()) - 1);
+                m->v3.push_back(atoi(tok[3 + t].c_str()) - 1);
+            }
+        }
+    }
+    const int nv = (int)m->x.size();
+    for (size_t t = 0; t < m->v1.size(); t++) {
+        if (m->v1[t] < 0 || m->v1[t] >= nv || m->v2[t] < 0 || m->v2[t] >= nv || m->v3[t] < 0 ||
+            m->v3[t] >= nv) {
+            delete m;
+            return RC_ERR_FORMAT;
+        }
+    }
+    *out = m;
+    return RC_OK;
+}
+
+int rc_mesh_load_byu(const char *path, rc_mesh **out)
+{
+    if (!path || !out) return RC_ERR_INVALID;
+    std::ifstream in(path);
+    if (!in.good()) return RC_ERR_IO;
+    long parts = 0, nverts = 0, npolys = 0, nedges = 0;
+    if (!(in >> parts >> nverts >> npolys >> nedges)) return RC_ERR_FORMAT;
+    if (parts < 0 || nverts < 0 || npolys < 0 || parts > (1 << 24) || nverts > (1L << 30) ||
+        npolys > (1L << 30))
+        return RC_ERR_FORMAT;
+    for (long p = 0; p < parts; p++) {
+        long first, last;
+        if (!(in >> first >> last)) return RC_ERR_FORMAT;
+    }
+    rc_mesh *m = new rc_mesh();
+    m->x.reserve(nverts); m->y.reserve(nverts); m->z.reserve(nverts);
+    for (long v = 0; v < nverts; v++) {
+        std::string sx, sy, sz;
+        if (!(in >> sx >> sy >> sz)) { delete m; return RC_ERR_FORMAT; }
+        m->x.push_back((float)atof(sx.c_str()));
+        m->y.push_back((float)atof(sy.c_str()));
+        m->z.push_back((float)atof(sz.c_str()));
+    }
+    // polygons: 1-based indices, the last one of each polygon is negated.  The PMPL loader
+    // insists on triangles; like the OBJ path, larger polygons are fan-split here.
+    for (long p = 0; p < npolys; p++) {
+        std::vector<int> idx;
+        long id = 0;
+        do {
+            if (!(in >> id)) { delete m; return RC_ERR_FORMAT; }
+            idx.push_back((int)(id < 0 ? -id : id) - 1);
+        } while (id >= 0);
+        if (idx.size() < 3) { delete m; return RC_ERR_FORMAT; }
+        for (size_t t = 0; t + 2 < idx.size(); t++) {
+            m->v1.push_back(idx[0]);
+            m->v2.push_back(idx[t + 1]);
+            m->v3.push_back(idx[t + 2]);
+        }
+    }
+    for (size_t t = 0; t < m->v1.size(); t++) {
+        if (m->v1[t] < 0 || m->v1[t] >= nverts || m->v2[t] < 0 || m->v2[t] >= nverts ||
+            m->v3[t] < 0 || m->v3[t] >= nverts) {
+            delete m;
+            return RC_ERR_FORMAT;
+        }
+    }
+    *out = m;
+    return RC_OK;
+}
+
+int rc_mesh_from_arrays(const float *x, const float *y, const float *z, int n_v, const int *v1,
+                        const int *v2, const int *v3, int n_t, rc_mesh **out)
+{
+    if (!out || n_v < 0 || n_t < 0 || (n_v && (!x || !y || !z)) || (n_t && (!v1 || !v2 || !v3)))
+        return RC_ERR_INVALID;
+    for (int t = 0; t < n_t; t++)
+        if (v1[t] < 0 || v1[t] >= n_v || v2[t] < 0 || v2[t] >= n_v || v3[t] < 0 || v3[t] >= n_v)
+            return RC_ERR_INVALID;
+    rc_mesh *m = new rc_mesh();
+    m->x.assign(x, x + n_v); m->y.assign(y, y + n_v); m->z.assign(z, z + n_v);
+    m->v1.assign(v1, v1 + n_t); m->v2.assign(v2, v2 + n_t); m->v3.assign(v3, v3 + n_t);
+    *out = m;
+    return RC_OK;
+}
+
+// Writers print 9 significant digits so that every float survives the text round trip.
+int rc_mesh_save_obj(const rc_mesh *m, const char *path)
+{
+    if (!m || !path) return RC_ERR_INVALID;
+    FILE *f = fopen(path, "w");
+    if (!f) return RC_ERR_IO;
+    fprintf(f, "# robocheck-b200 mesh\n");
+    for (size_t v = 0; v < m->x.size(); v++)
+        fprintf(f, "v %.9g %.9g %.9g\n", m->x[v], m->y[v], m->z[v]);
+    for (size_t t = 0; t < m->v1.size(); t++)
+        fprintf(f, "f %d %d %d\n", m->v1[t] + 1, m->v2[t] + 1, m->v3[t] + 1);
+    fclose(f);
+    return RC_OK;
+}
+
+int rc_mesh_save_byu(const rc_mesh *m, const char *path)
+{
+    if (!m || !path) return RC_ERR_INVALID;
+    FILE *f = fopen(path, "w");
+    if (!f) return RC_ERR_IO;
+    const size_t nt = m->v1.size();
+    fprintf(f, "1 %zu %zu %zu\n1 %zu\n", m->x.size(), nt, 3 * nt, nt);
+    for (size_t v = 0; v < m->x.size(); v++)
+        fprintf(f, "%.9g %.9g %.9g\n", m->x[v], m->y[v], m->z[v]);
+    for (size_t t = 0; t < nt; t++)
+        fprintf(f, "%d %d -%d\n", m->v1[t] + 1, m->v2[t] + 1, m->v3[t] + 1);
+    fclose(f);
+    return RC_OK;
+}
+
+int rc_mesh_counts(const rc_mesh *m, int *n_v, int *n_t)
+{
+    if (!m) return RC_ERR_INVALID;
+    if (n_v) *n_v = (int)m->x.size();
+    if (n_t) *n_t = (int)m->v1.size();
+    return RC_OK;
+}
+const float *rc_mesh_x(const rc_mesh *m) { return m ? m->x.data() : nullptr; }
+const float *rc_mesh_y(const rc_mesh *m) { return m ? m->y.data() : nullptr; }
+const float *rc_mesh_z(const rc_mesh *m) { return m ? m->z.data() : nullptr; }
+const int *rc_mesh_v1(const rc_mesh *m) { return m ? m->v1.data() : nullptr; }
+const int *rc_mesh_v2(const rc_mesh *m) { return m ? m->v2.data() : nullptr; }
+const int *rc_mesh_v3(const rc_mesh *m) { return m ? m->v3.data() : nullptr; }
+void rc_mesh_free(rc_mesh *m) { delete m; }
+
+int rc_mesh_aabb(const rc_mesh *m, rc_aabb *out)
+{
+    // generateAABBBaseline(x, y, z, AABB*), generate-AABB/generate-AABB.cu:183-201
+    if (!m || !out) return RC_ERR_INVALID;
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (size_t v = 0; v < m->x.size(); v++) {
+        lo[0] = std::min(lo[0], m->x[v]); hi[0] = std::max(hi[0], m->x[v]);
+        lo[1] = std::min(lo[1], m->y[v]); hi[1] = std::max(hi[1], m->y[v]);
+        lo[2] = std::min(lo[2], m->z[v]); hi[2] = std::max(hi[2], m->z[v]);
+    }
+    *out = rc_aabb{lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]};
+    return RC_OK;
+}
+
+// 1 -> 4 midpoint subdivision.  Midpoints are shared between the two triangles of an edge
+// (keyed on the sorted vertex pair), computed as 0.5f * (a + b) in float.
+int rc_mesh_subdivide(const rc_mesh *src, int levels, rc_mesh **out)
+{
+    if (!src || !out || levels < 0 || levels > 8) return RC_ERR_INVALID;
+    rc_mesh *cur = new rc_mesh(*src);
+    for (int l = 0; l < levels; l++) {
+        rc_mesh *nxt = new rc_mesh();
+        nxt->x = cur->x; nxt->y = cur->y; nxt->z = cur->z;
+        std::map<std::pair<int, int>, int> mid;
+        auto midpoint = [&](int a, int b) {
+            const std::pair<int, int> key(std::min(a, b), std::max(a, b));
+            auto it = mid.find(key);
+            if (it != mid.end()) return it->second;
+            const int id = (int)nxt->x.size();
+            nxt->x.push_back(0.5f * (cur->x[key.first] + cur->x[key.second]));
+            nxt->y.push_back(0.5f * (cur->y[key.first] + cur->y[key.second]));
+            nxt->z.push_back(0.5f * (cur->z[key.first] + cur->z[key.second]));
+            mid.emplace(key, id);
+            return id;
+        };
+        for (size_t t = 0; t < cur->v1.size(); t++) {
+            const int a = cur->v1[t], b = cur->v2[t], c = cur->v3[t];
+            const int ab = midpoint(a, b), bc = midpoint(b, c), ca = midpoint(c, a);
+            const int tri[4][3] = {{a, ab, ca}, {ab, b, bc}, {ca, bc, c}, {ab, bc, ca}};
+            for (auto &q : tri) {
+                nxt->v1.push_back(q[0]); nxt->v2.push_back(q[1]); nxt->v3.push_back(q[2]);
+            }
+        }
+        delete cur;
+        cur = nxt;
+    }
+    *out = cur;
+    return RC_OK;
+}
+
+// ---- .conf ---------------------------------------------------------------------------------
+
+int rc_conf_read(const char *path, rc_config **confs, uint8_t **tags, long *n)
+{
+    if (!path || !confs || !n) return RC_ERR_INVALID;
+    std::ifstream in(path);
+    if (!in.is_open()) return RC_ERR_IO;
+    std::string header;
+    std::getline(in, header);  // "There are V valid configurations and I invalid configurations"
+    std::vector<rc_config> v;
+    std::vector<uint8_t> t;
+    rc_config c;
+    // operator>>(float) is what the reference uses (Utils_rai.cu:90): strtof semantics
+    while (in >> c.x >> c.y >> c.z >> c.pitch >> c.yaw >> c.roll) {
+        std::string tag;
+        in >> tag;  // validity column (may be absent on the last line)
+        v.push_back(c);
+        t.push_back((uint8_t)(!tag.empty() && tag != "0"));
+    }
+    *n = (long)v.size();
+    *confs = (rc_config *)malloc(sizeof(rc_config) * std::max<size_t>(v.size(), 1));
+    if (!*confs) return RC_ERR_NOMEM;
+    if (!v.empty()) memcpy(*confs, v.data(), sizeof(rc_config) * v.size());
+    if (tags) {
+        *tags = (uint8_t *)malloc(std::max<size_t>(t.size(), 1));
+        if (!*tags) { free(*confs); *confs = nullptr; return RC_ERR_NOMEM; }
+        if (!t.empty()) memcpy(*tags, t.data(), t.size());
+    }
+    return RC_OK;
+}
+
+int rc_conf_write(const char *path, const rc_config *confs, const uint8_t *valid, long n)
+{
+    if (!path || n < 0 || (n && !confs)) return RC_ERR_INVALID;
+    std::ofstream out(path);
+    if (!out.is_open()) return RC_ERR_IO;
+    long nv = 0;
+    for (long i = 0; i < n; i++) nv += (valid && valid[i]) ? 1 : 0;
+    out << "There are " << nv << " valid configurations and " << (n - nv)
+        << " invalid configurations\n";
+    // default ostream formatting (6 significant digits), as the reference writes them
+    for (long i = 0; i < n; i++)
+        out << confs[i].x << " " << confs[i].y << " " << confs[i].z << " " << confs[i].pitch << " "
+            << confs[i].yaw << " " << confs[i].roll << " " << (int)((valid && valid[i]) ? 1 : 0)
+            << "\n";
+    return out.good() ? RC_OK : RC_ERR_IO;
+}
+
+void rc_free(void *p) { free(p); }
+
+int rc_conf_generate(rc_config *out, long n, float x_min, float x_max, float y_min, float y_max,
+                     float z_min, float z_max, uint32_t seed)
+{
+    if (n < 0 || (n && !out)) return RC_ERR_INVALID;
+    std::mt19937 gen(seed);
+    std::uniform_real_distribution<float> dis_x(x_min, x_max), dis_y(y_min, y_max),
+        dis_z(z_min, z_max), dis_rot(-M_PI, M_PI);
+    for (long i = 0; i < n; i++) {
+        rc_config c;
+        c.x = dis_x(gen); c.y = dis_y(gen); c.z = dis_z(gen);
+        c.pitch = dis_rot(gen); c.yaw = dis_rot(gen); c.roll = dis_rot(gen);
+        out[i] = c;
+    }
+    return RC_OK;
+}
+
+int rc_conf_generate_alpha(rc_config *out, long n, int hard, uint32_t seed)
+{
+    // extents of alpha1.0/robot.obj as hard-coded by the reference (Utils_rai.cu:113-118)
+    const float x_min = 3.72119f, y_min = -11.0518f, z_min = -0.608012f;
+    const float x_max = 65.9453f, y_max = 26.0984f, z_max = 18.6984f;
+    const float xr = x_max - x_min, yr = y_max - y_min, zr = z_max - z_min;
+    if (hard)
+        return rc_conf_generate(out, n, -xr / 200, xr / 200, -yr / 200, yr / 200, -zr / 200,
+                                zr / 200, seed);
+    return rc_conf_generate(out, n, -xr * 10, xr * 10, -yr * 10, yr * 10, -zr * 10, zr * 10, seed);
+}
+
+}  // extern "C"
