@@ -1,0 +1,215 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against (a) the CPU oracle,
+(b) the committed golden fixtures (FCL tags, reference CPU flags), (c) ORACLE-GPU = the
+reference's own kernels compiled for sm_100a (oracle/_ref/libref.so) on the same inputs.
+Integer/flag work: bit-exact.  Transformed vertices: bit-exact vs the reference kernel and the
+oracle (tolerance stated by north_star is 1e-6 relative; we assert equality)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def run_check(ctx, confs, mode, bitmask=False):
+    torch = _torch()
+    d_confs = torch.from_numpy(np.ascontiguousarray(confs, dtype=np.float32)).cuda()
+    n = len(confs)
+    d_valid = torch.full((n,), 7, dtype=torch.uint8, device="cuda")
+    d_mask = torch.zeros((n + 31) // 32, dtype=torch.int32, device="cuda") if bitmask else None
+    ctx.check(d_confs, n, d_valid, d_mask, mode, torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    if bitmask:
+        bits = np.unpackbits(d_mask.cpu().numpy().view(np.uint8), bitorder="little")[:n]
+        return d_valid.cpu().numpy(), bits
+    return d_valid.cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def mixed_confs(rc):
+    return np.concatenate([rc.createAlphaBotConfigurations(1500, True, 508),
+                           rc.createAlphaBotConfigurations(500, False, 509)]).astype(np.float32)
+
+
+@pytest.fixture(scope="module")
+def mixed_oracle(po, omeshes, mixed_confs):
+    return po.check(omeshes[0], omeshes[1], mixed_confs, po.VARIANT_GPU)
+
+
+def test_brute_matches_oracle(rc, ctx, mixed_confs, mixed_oracle):
+    got = run_check(ctx, mixed_confs, rc.RC_MODE_BRUTE)
+    assert np.array_equal(got, mixed_oracle)
+
+
+def test_culled_matches_oracle(rc, ctx, mixed_confs, mixed_oracle):
+    got, bits = run_check(ctx, mixed_confs, rc.RC_MODE_CULLED, bitmask=True)
+    assert np.array_equal(got, mixed_oracle)
+    assert np.array_equal(bits, mixed_oracle)
+
+
+def test_golden_fcl_tags(rc, ctx, golden):
+    """Every FCL verdict of the reference's shipped sets is reproduced (the expected
+    disagreement count is 0, so the contact tolerance is never needed)."""
+    for key in ("easy_confs10k", "hard_confs10k"):
+        g = golden[key]
+        got = run_check(ctx, g["confs"], rc.RC_MODE_CULLED)
+        assert int((got != g["tags"]).sum()) == 0, key
+
+
+def test_golden_reference_cpu_flags(rc, ctx, golden):
+    g = golden["refcpu_hard"]
+    for mode in (rc.RC_MODE_CULLED, rc.RC_MODE_BRUTE):
+        got = run_check(ctx, g["confs"], mode)
+        assert np.array_equal(got, g["flags"])
+
+
+def test_check_host_matches_device(rc, ctx, mixed_confs, mixed_oracle):
+    assert np.array_equal(ctx.check_host(mixed_confs), mixed_oracle)
+    assert np.array_equal(ctx.check_host(mixed_confs, rc.RC_MODE_BRUTE), mixed_oracle)
+
+
+def test_empty_and_ragged_sizes(rc, ctx, po, omeshes):
+    torch = _torch()
+    ctx.check(None, 0, torch.zeros(1, dtype=torch.uint8, device="cuda"), None)
+    assert len(ctx.check_host(np.zeros((0, 6), np.float32))) == 0
+    confs = rc.createAlphaBotConfigurations(97, True, 7)
+    want = po.check(omeshes[0], omeshes[1], confs, po.VARIANT_GPU)
+    for n in (1, 31, 32, 33, 97):
+        got, bits = run_check(ctx, confs[:n], rc.RC_MODE_CULLED, bitmask=True)
+        assert np.array_equal(got, want[:n])
+        assert np.array_equal(bits, want[:n])
+
+
+def test_culled_equals_brute_large(rc, ctx):
+    """Size-independent property at a scale the CPU oracle cannot reach: the culled kernel and
+    the exhaustive kernel agree on every flag (culling never drops a hitting pair)."""
+    confs = np.concatenate([rc.createAlphaBotConfigurations(60000, True, 4242),
+                            rc.createAlphaBotConfigurations(20000, False, 4243)])
+    a = run_check(ctx, confs, rc.RC_MODE_CULLED)
+    b = run_check(ctx, confs, rc.RC_MODE_BRUTE)
+    assert int((a != b).sum()) == 0
+    st_on = ctx.stats_enable(True)
+    ctx.stats(reset=True)
+    run_check(ctx, confs, rc.RC_MODE_CULLED)
+    st = ctx.stats(reset=True)
+    ctx.stats_enable(False)
+    assert st["overflow"] == 0
+    assert st["broad_cleared"] + st["sphere_cleared"] + st["narrow_valid"] + st["narrow_invalid"] == len(confs)
+    assert st["narrow_valid"] + st["broad_cleared"] + st["sphere_cleared"] == int(a.sum())
+
+
+# ---- stage API -------------------------------------------------------------------------------
+def test_transform_bit_exact_vs_oracle(rc, ctx, po, omeshes):
+    torch = _torch()
+    confs = np.concatenate([rc.createAlphaBotConfigurations(300, True, 11),
+                            rc.createAlphaBotConfigurations(300, False, 12)]).astype(np.float32)
+    n, nv = len(confs), ctx.n_rob_v
+    d_confs = torch.from_numpy(confs).cuda()
+    dx, dy, dz = (torch.zeros(n * nv, dtype=torch.float32, device="cuda") for _ in range(3))
+    d_box = torch.zeros(n * 6, dtype=torch.float32, device="cuda")
+    d_valid = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    ctx.broad_fused(d_confs, n, dx, dy, dz, d_box, d_valid, torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    ox, oy, oz = po.transform(confs, omeshes[0].x, omeshes[0].y, omeshes[0].z)
+    for got, want in ((dx, ox), (dy, oy), (dz, oz)):
+        got = got.cpu().numpy().reshape(n, nv)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    boxes = d_box.cpu().numpy().reshape(n, 6)
+    obs_box = ctx.obstacle_aabb()
+    assert np.array_equal(obs_box, po.aabb(omeshes[1].x, omeshes[1].y, omeshes[1].z))
+    for i in range(n):
+        want = po.aabb(ox[i], oy[i], oz[i])
+        assert np.array_equal(boxes[i], want)
+        assert int(d_valid[i]) == po.broad_valid(want, obs_box)
+    # AoS stage (genTransformedCopies layout) carries the same bits
+    d_aos = torch.zeros(n * nv * 3, dtype=torch.float32, device="cuda")
+    ctx.transform_aos(d_confs, n, d_aos, stream=torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    aos = d_aos.cpu().numpy().reshape(n, nv, 3)
+    assert np.array_equal(aos[..., 0], ox) and np.array_equal(aos[..., 1], oy) and np.array_equal(aos[..., 2], oz)
+    # AABB stages on the materialised vertices, exact equality like test-generate-AABB.cu:83-96
+    d_box2 = torch.zeros(n * 6, dtype=torch.float32, device="cuda")
+    ctx.generate_aabb(d_aos, nv, n, d_box2, torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    assert np.array_equal(d_box2.cpu().numpy().reshape(n, 6), boxes)
+    d_box3 = torch.zeros(n * 6, dtype=torch.float32, device="cuda")
+    ctx.generate_aabb_soa(dx, dy, dz, nv, n, d_box3, torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    assert np.array_equal(d_box3.cpu().numpy().reshape(n, 6), boxes)
+    assert np.array_equal(ctx.generate_aabb_host(aos, nv, n), boxes)
+    # broad-phase stage
+    d_valid2 = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    ctx.broad_phase(n, d_box, d_valid2, stream=torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    assert torch.equal(d_valid, d_valid2)
+
+
+def test_stage_pipeline_equals_fused(rc, ctx, po, omeshes):
+    """transform+AABB+broad stage followed by the narrow stage == fused entry point == oracle."""
+    torch = _torch()
+    confs = rc.createAlphaBotConfigurations(600, True, 13)
+    n, nv = len(confs), ctx.n_rob_v
+    d_confs = torch.from_numpy(confs).cuda()
+    dx, dy, dz = (torch.zeros(n * nv, dtype=torch.float32, device="cuda") for _ in range(3))
+    d_valid = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    s = torch.cuda.current_stream()
+    ctx.broad_fused(d_confs, n, dx, dy, dz, None, d_valid, s)
+    ctx.narrow_phase(dx, dy, dz, n, d_valid, s)
+    torch.cuda.synchronize()
+    want = po.check(omeshes[0], omeshes[1], confs, po.VARIANT_GPU)
+    assert np.array_equal(d_valid.cpu().numpy(), want)
+    # in/out semantics: entries already 1 are left untouched (narrow-phase.cu:578)
+    d_valid.fill_(1)
+    ctx.narrow_phase(dx, dy, dz, n, d_valid, s)
+    torch.cuda.synchronize()
+    assert int(d_valid.sum()) == n
+
+
+def test_narrow_phase_host_tetrahedra(rc):
+    """test-narrow-phase.cu:628-686 (test_baseline): two configurations of a tetrahedron against a
+    tetrahedron, the first interpenetrating, the second far away -> [false, true]."""
+    tet = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], np.float32)
+    tris = np.array([[0, 1, 2], [0, 1, 3], [0, 2, 3], [1, 2, 3]], np.int32)
+    rob = np.stack([tet + np.float32(0.25), tet + np.float32(10.0)])
+    valid = np.zeros(2, np.uint8)
+    rc.narrowPhase(tris, rob, tris, tet, valid)
+    assert valid.tolist() == [0, 1]
+
+
+# ---- ORACLE-GPU: the reference's own CUDA kernels on this GPU --------------------------------
+def test_flags_match_reference_gpu_pipeline(rc, ctx, po):
+    if not po.ref_available():
+        pytest.skip("oracle/_ref/libref.so not built (needs /root/reference at build time)")
+    from tests import refpipe
+    confs = np.concatenate([rc.createAlphaBotConfigurations(20000, True, 601),
+                            rc.createAlphaBotConfigurations(5000, False, 602)]).astype(np.float32)
+    want = refpipe.oracle_gpu_flags(rc, po, confs)
+    for mode in (rc.RC_MODE_CULLED, rc.RC_MODE_BRUTE):
+        got = run_check(ctx, confs, mode)
+        assert int((got != want).sum()) == 0
+
+
+def test_vertices_match_reference_gpu_kernel(rc, ctx, po, omeshes):
+    if not po.ref_available():
+        pytest.skip("oracle/_ref/libref.so not built")
+    torch = _torch()
+    confs = np.concatenate([rc.createAlphaBotConfigurations(2000, True, 603),
+                            rc.createAlphaBotConfigurations(2000, False, 604)]).astype(np.float32)
+    rx, ry, rz, rflags = po.ref_gpu_transform(omeshes[0], ctx.obstacle_aabb(), confs)
+    n, nv = len(confs), ctx.n_rob_v
+    d_confs = torch.from_numpy(confs).cuda()
+    dx, dy, dz = (torch.zeros(n * nv, dtype=torch.float32, device="cuda") for _ in range(3))
+    d_valid = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    ctx.broad_fused(d_confs, n, dx, dy, dz, None, d_valid, torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    for got, want in ((dx, rx), (dy, ry), (dz, rz)):
+        assert np.array_equal(got.cpu().numpy().reshape(n, nv).view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(d_valid.cpu().numpy(), rflags)
+    # and the CPU oracle's libdevice sinf/cosf restatement agrees with the GPU bit for bit
+    ox, oy, oz = po.transform(confs, omeshes[0].x, omeshes[0].y, omeshes[0].z)
+    assert np.array_equal(ox.view(np.uint32), rx.view(np.uint32))
+    assert np.array_equal(oy.view(np.uint32), ry.view(np.uint32))
+    assert np.array_equal(oz.view(np.uint32), rz.view(np.uint32))
