@@ -13,8 +13,9 @@
  *  - `valid` flags are bytes, 1 = collision free, 0 = in collision (reference: bool*,
  *    true = valid, narrow-phase/narrow-phase.cu:341).
  *  - pointers named d_* are DEVICE pointers on the context's device, h_* are host pointers.
- *  - `stream` is a cudaStream_t passed as void* (NULL = the context's own stream); stage
- *    calls are asynchronous on it unless stated otherwise.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = CUDA's legacy default stream, as in
+ *    the runtime API); stage calls are asynchronous on it unless stated otherwise.  The *_host
+ *    convenience calls use a private stream of the context and synchronise before returning.
  *  - one context per device; calls on one context are serialised by the caller.
  *  - there is NO CPU fallback: without a usable CUDA device rc_create fails with
  *    RC_ERR_NO_DEVICE.

@@ -88,10 +88,9 @@ int upload_obstacle(rc_ctx *ctx, const GatheredTris &g, float4 **a, float4 **b, 
     return check_cuda(ctx, cudaStreamSynchronize(ctx->own_stream), "obstacle planes sync");
 }
 
-cudaStream_t stream_of(rc_ctx *ctx, void *stream)
-{
-    return stream ? static_cast<cudaStream_t>(stream) : ctx->own_stream;
-}
+// NULL is CUDA's legacy default stream (which is also torch's default stream), NOT the
+// context's private stream: work must land on the stream the caller times and orders.
+cudaStream_t stream_of(rc_ctx *, void *stream) { return static_cast<cudaStream_t>(stream); }
 
 int ensure_staging(rc_ctx *ctx, long n)
 {
@@ -335,21 +334,32 @@ int rc_check_host(rc_ctx *ctx, const rc_config *h_confs, long n, uint8_t *h_vali
     int rcode = ensure_staging(ctx, n);
     if (rcode != RC_OK) return rcode;
     cudaStream_t s = ctx->own_stream;
-    std::memcpy(ctx->h_pinned_confs, h_confs, (size_t)n * sizeof(rc_config));
     cudaError_t e;
-    if ((e = cudaMemcpyAsync(ctx->d_stage_confs, ctx->h_pinned_confs, (size_t)n * sizeof(rc_config),
+    // page-locked caller buffers are used in place; pageable ones go through the pinned staging
+    cudaPointerAttributes pa_in{}, pa_out{};
+    const bool in_pinned = cudaPointerGetAttributes(&pa_in, h_confs) == cudaSuccess &&
+                           pa_in.type == cudaMemoryTypeHost;
+    const bool out_pinned = cudaPointerGetAttributes(&pa_out, h_valid) == cudaSuccess &&
+                            pa_out.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    const rc_config *src = h_confs;
+    if (!in_pinned) {
+        std::memcpy(ctx->h_pinned_confs, h_confs, (size_t)n * sizeof(rc_config));
+        src = ctx->h_pinned_confs;
+    }
+    if ((e = cudaMemcpyAsync(ctx->d_stage_confs, src, (size_t)n * sizeof(rc_config),
                              cudaMemcpyHostToDevice, s)))
         return check_cuda(ctx, e, "H2D configurations");
     cudaEventRecord(ctx->ev0, s);
     rcode = rc_check(ctx, ctx->d_stage_confs, n, ctx->d_stage_valid, nullptr, mode, s);
     if (rcode != RC_OK) return rcode;
     cudaEventRecord(ctx->ev1, s);
-    if ((e = cudaMemcpyAsync(ctx->h_pinned_valid, ctx->d_stage_valid, (size_t)n,
-                             cudaMemcpyDeviceToHost, s)) ||
+    uint8_t *dst = out_pinned ? h_valid : ctx->h_pinned_valid;
+    if ((e = cudaMemcpyAsync(dst, ctx->d_stage_valid, (size_t)n, cudaMemcpyDeviceToHost, s)) ||
         (e = cudaStreamSynchronize(s)))
         return check_cuda(ctx, e, "D2H flags");
     cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev0, ctx->ev1);
-    std::memcpy(h_valid, ctx->h_pinned_valid, (size_t)n);
+    if (!out_pinned) std::memcpy(h_valid, ctx->h_pinned_valid, (size_t)n);
     return RC_OK;
 }
 
@@ -507,7 +517,7 @@ int rc_stats_read(rc_ctx *ctx, rc_stats *out, int reset)
     cudaSetDevice(ctx->device);
     unsigned long long h[RC_NUM_COUNTERS];
     cudaError_t e;
-    if ((e = cudaStreamSynchronize(ctx->own_stream)) ||
+    if ((e = cudaDeviceSynchronize()) ||
         (e = cudaMemcpy(h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost)))
         return check_cuda(ctx, e, "rc_stats_read");
     out->broad_cleared = h[CNT_BROAD_CLEARED]; out->sphere_cleared = h[CNT_SPHERE_CLEARED];

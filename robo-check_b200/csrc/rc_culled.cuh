@@ -16,7 +16,10 @@
 //   B   dual-tree descent: a LIFO of (robot node, obstacle node) pairs in shared memory, 32 pairs
 //       tested per step (one per lane), children appended with ballot/popc compaction
 //   C   leaf pairs (<= 4 x 4 triangles) are batched eight at a time: lane = (leaf pair, robot
-//       triangle), loop over the obstacle triangles of the leaf; warp vote early exit.
+//       triangle), loop over the obstacle triangles of the leaf: the two plane tests
+//   D   the few pairs that pass both plane tests are queued and finished (coplanarity,
+//       intersection line, interval test) 32 at a time, so the long rare path runs with full
+//       warps instead of a handful of lanes; warp vote early exit.
 #pragma once
 
 namespace rc {
@@ -25,6 +28,8 @@ constexpr int kCulledWarps = 16;
 constexpr int kCulledThreads = kCulledWarps * 32;
 constexpr int kStackCap = 1024;  // node pairs per warp; overflow falls back to the exhaustive sweep
 constexpr int kLeafQCap = 64;
+constexpr int kTailQCap = 160;   // pairs that passed both plane tests, finished 32 at a time
+constexpr int kWarpWork = kStackCap + kLeafQCap + kTailQCap;
 constexpr int kLeafTrisDev = 4;  // must match rc::kLeafTris of the host builder (rc_bvh.h)
 
 struct CulledArgs {
@@ -126,10 +131,11 @@ __global__ void __launch_bounds__(kCulledThreads, 1) check_culled_kernel(const C
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
-    uint32_t *stack = s_work + warp * (kStackCap + kLeafQCap);
+    uint32_t *stack = s_work + warp * kWarpWork;
     uint32_t *leafq = stack + kStackCap;
+    uint32_t *tailq = leafq + kLeafQCap;
     unsigned long long st_broad = 0, st_sphere = 0, st_valid = 0, st_invalid = 0, st_nodes = 0,
-                       st_leaves = 0, st_tris = 0, st_over = 0;
+                       st_leaves = 0, st_tris = 0, st_over = 0, st_tails = 0;
 
     for (;;) {
         long base = 0;
@@ -170,12 +176,39 @@ __global__ void __launch_bounds__(kCulledThreads, 1) check_culled_kernel(const C
                 continue;
             }
 
-            // B + C
-            int sp = 1, lq = 0;
+            // B + C + D
+            int sp = 1, lq = 0, tq = 0;
             bool hit = false, overflow = false;
             if (lane == 0) stack[0] = 0u;  // (root, root)
             __syncwarp();
-            while (sp > 0 || lq > 0) {
+            while (sp > 0 || lq > 0 || tq > 0) {
+                if (tq >= 32 || (sp == 0 && lq == 0)) {
+                    // ---- D: finish up to 32 queued pairs, one per lane
+                    const int cnt = min(tq, 32);
+                    tq -= cnt;
+                    const bool act = lane < cnt;
+                    const uint32_t e = tailq[tq + (act ? lane : 0)];
+                    const uint2 ti = s_rob_t[e >> 16];
+                    const int k = e & 0xffffu;
+                    const float4 A = s_rob_v[ti.x & 0xffffu], B = s_rob_v[ti.x >> 16], C = s_rob_v[ti.y];
+                    Tri r;
+                    xform(m, A.x, A.y, A.z, r.ax, r.ay, r.az);
+                    xform(m, B.x, B.y, B.z, r.bx, r.by, r.bz);
+                    xform(m, C.x, C.y, C.z, r.cx, r.cy, r.cz);
+                    const Plane pr = plane_of(r);
+                    const float4 oa = s_obs_a[k], ob = s_obs_b[k], oc = s_obs_c[k];
+                    const Tri o = {oa.x, oa.y, oa.z, ob.x, ob.y, ob.z, oc.x, oc.y, oc.z};
+                    const Plane po = {oa.w, ob.w, oc.w, s_obs_d[k].x};
+                    const float dO0 = sdist(pr, o.ax, o.ay, o.az), dO1 = sdist(pr, o.bx, o.by, o.bz),
+                                dO2 = sdist(pr, o.cx, o.cy, o.cz);
+                    const float dR0 = sdist(po, r.ax, r.ay, r.az), dR1 = sdist(po, r.bx, r.by, r.bz),
+                                dR2 = sdist(po, r.cx, r.cy, r.cz);
+                    const bool h = act && pair_tail(r, pr, dR0, dR1, dR2, o, po, dO0, dO1, dO2);
+                    if (STATS) st_tails += cnt;
+                    if (__any_sync(kFull, h)) { hit = true; break; }
+                    __syncwarp();
+                    continue;
+                }
                 if (lq >= 8 || sp == 0) {
                     // ---- C: up to eight leaf pairs, lane = (slot, robot triangle of the leaf)
                     const int cnt = min(lq, 8);
@@ -189,24 +222,31 @@ __global__ void __launch_bounds__(kCulledThreads, 1) check_culled_kernel(const C
                     const uint32_t ofirst = __float_as_uint(s_obs_bvh[2 * nb].w) & 0x7fffffffu;
                     const int ocount = (int)__float_as_uint(s_obs_bvh[2 * nb + 1].w);
                     act = act && ri < rcount;
-                    const uint2 ti = s_rob_t[rfirst + (act ? ri : 0)];
+                    const uint32_t j = rfirst + (act ? ri : 0);
+                    const uint2 ti = s_rob_t[j];
                     const float4 A = s_rob_v[ti.x & 0xffffu], B = s_rob_v[ti.x >> 16], C = s_rob_v[ti.y];
                     Tri r;
                     xform(m, A.x, A.y, A.z, r.ax, r.ay, r.az);
                     xform(m, B.x, B.y, B.z, r.bx, r.by, r.bz);
                     xform(m, C.x, C.y, C.z, r.cx, r.cy, r.cz);
                     const Plane pr = plane_of(r);
-                    bool h = false;
 #pragma unroll
                     for (int q = 0; q < kLeafTrisDev; q++) {
                         const int k = ofirst + min(q, ocount - 1);
                         const float4 oa = s_obs_a[k], ob = s_obs_b[k], oc = s_obs_c[k];
-                        const Tri o = {oa.x, oa.y, oa.z, ob.x, ob.y, ob.z, oc.x, oc.y, oc.z};
-                        const Plane po = {oa.w, ob.w, oc.w, s_obs_d[k].x};
-                        if (act && q < ocount && pair_hits(r, pr, o, po)) h = true;
+                        bool pass = act && q < ocount &&
+                                    straddles(sdist(pr, oa.x, oa.y, oa.z), sdist(pr, ob.x, ob.y, ob.z),
+                                              sdist(pr, oc.x, oc.y, oc.z));
+                        if (pass) {
+                            const Plane po = {oa.w, ob.w, oc.w, s_obs_d[k].x};
+                            pass = straddles(sdist(po, r.ax, r.ay, r.az), sdist(po, r.bx, r.by, r.bz),
+                                             sdist(po, r.cx, r.cy, r.cz));
+                        }
+                        const unsigned mp = __ballot_sync(kFull, pass);
+                        if (pass) tailq[tq + __popc(mp & lt)] = (j << 16) | (uint32_t)k;
+                        tq += __popc(mp);
                     }
                     if (STATS) { st_leaves += cnt; st_tris += (act ? ocount : 0); }
-                    if (__any_sync(kFull, h)) { hit = true; break; }
                     __syncwarp();
                     continue;
                 }
@@ -271,6 +311,7 @@ __global__ void __launch_bounds__(kCulledThreads, 1) check_culled_kernel(const C
             atomicAdd(c.counters + CNT_NODE_PAIRS, st_nodes);
             atomicAdd(c.counters + CNT_LEAF_PAIRS, st_leaves);
             atomicAdd(c.counters + CNT_TRI_PAIRS, st_tris);
+            atomicAdd(c.counters + CNT_TAIL_PAIRS, st_tails);
             atomicAdd(c.counters + CNT_OVERFLOW, st_over);
         }
     }
@@ -281,7 +322,7 @@ static size_t culled_smem_bytes(const DeviceTables &t)
     size_t b = 16 + (size_t)t.n_rob_v_pad * 16 + (size_t)t.n_rob_nodes * 32 +
                (size_t)t.n_obs_nodes * 32 + (size_t)t.n_obs_t * 64 +
                (size_t)(t.n_rob_t + (t.n_rob_t & 1)) * 8;
-    b += (size_t)kCulledWarps * (kStackCap + kLeafQCap) * 4;
+    b += (size_t)kCulledWarps * kWarpWork * 4;
     return b;
 }
 
