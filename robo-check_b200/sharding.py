@@ -1,0 +1,47 @@
+"""Multi-GPU host logic: configurations are independent, so they shard across ranks with no
+data-path exchange; the only collective is the all-gather of the per-configuration validity
+bitmask.  One process per GPU, torch.distributed for the plumbing (NCCL on GPUs, gloo
+in the CPU tests).  The reference has no multi-device code at all."""
+import numpy as np
+
+
+def shard_bounds(n, world, rank):
+    """Contiguous shard [lo, hi) of rank `rank`: ceil(n / world / 32) * 32 configurations per rank,
+    so every shard is a whole number of 32-bit bitmask words (the last shards may be short or
+    empty)."""
+    per = ((n + world - 1) // world + 31) // 32 * 32
+    lo = min(n, rank * per)
+    hi = min(n, lo + per)
+    return lo, hi, per
+
+
+def words_per_shard(n, world):
+    return shard_bounds(n, world, 0)[2] // 32
+
+
+def pack_bitmask(flags, words):
+    """uint8 flags -> `words` little-endian 32-bit words (bit i%32 of word i/32 = flag i)."""
+    bits = np.zeros(words * 32, np.uint8)
+    bits[: len(flags)] = flags
+    return np.packbits(bits, bitorder="little").view(np.uint32).copy()
+
+
+def unpack_bitmask(words, n):
+    return np.unpackbits(np.ascontiguousarray(words).view(np.uint8), bitorder="little")[:n]
+
+
+def check_sharded(check_local, confs, dist, device=None):
+    """Every rank checks its shard with `check_local(confs_shard, d_mask_words)` -- on a GPU that is
+    Context.check writing the bitmask straight into this rank's slot of the gather buffer -- then
+    one all_gather_into_tensor leaves the full bitmask on every rank.  Returns the flags of all
+    `len(confs)` configurations (uint8)."""
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    n = len(confs)
+    lo, hi, per = shard_bounds(n, world, rank)
+    words = per // 32
+    gather = torch.zeros(world * words, dtype=torch.int32, device=device)
+    mine = gather[rank * words:(rank + 1) * words]
+    check_local(confs[lo:hi], mine)
+    dist.all_gather_into_tensor(gather, mine.clone() if device is None else mine)
+    return unpack_bitmask(gather.cpu().numpy(), world * per)[:n] if world * per >= n else None

@@ -169,14 +169,32 @@ def test_stage_pipeline_equals_fused(rc, ctx, po, omeshes):
 
 
 def test_narrow_phase_host_tetrahedra(rc):
-    """test-narrow-phase.cu:628-686 (test_baseline): two configurations of a tetrahedron against a
-    tetrahedron, the first interpenetrating, the second far away -> [false, true]."""
-    tet = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], np.float32)
+    """test-narrow-phase.cu:628-686 (test_baseline) through narrowPhase(): two configurations of a
+    tetrahedron against a tetrahedron, the first interpenetrating, the second 100 units away
+    -> res = [false, true]; and :688-739 (test_single_triangle): must stay valid."""
+    rob = np.array([[0, 0, 0], [0, 1, 2], [0, 2, 0], [2, 2, 2],
+                    [100, 0, 0], [100, 1, 2], [100, 2, 0], [102, 2, 2]], np.float32).reshape(2, 4, 3)
+    obs = np.array([[1, 0.1, 0], [1.5, 1, 2.2], [1, 2.4, 0], [3.3, 2, 2]], np.float32)
     tris = np.array([[0, 1, 2], [0, 1, 3], [0, 2, 3], [1, 2, 3]], np.int32)
-    rob = np.stack([tet + np.float32(0.25), tet + np.float32(10.0)])
     valid = np.zeros(2, np.uint8)
-    rc.narrowPhase(tris, rob, tris, tet, valid)
+    rc.narrowPhase(tris, rob, tris, obs, valid)
     assert valid.tolist() == [0, 1]
+    r = np.array([[1.441547, -14.800514, 62.841087], [-4.215309, 8.199282, 23.057938],
+                  [1.883977, -15.487457, 62.381035]], np.float32).reshape(1, 3, 3)
+    o = np.array([[1.681669, 2.616245, 1.069425], [3.561536, 0.677467, 1.707230],
+                  [1.172210, 2.534812, 1.852433]], np.float32)
+    one = np.zeros(1, np.uint8)
+    rc.narrowPhase(np.array([[0, 1, 2]], np.int32), r, np.array([[0, 1, 2]], np.int32), o, one)
+    assert one.tolist() == [1]
+    # test_gpu (:742-836): 4096 configurations alternating collide / valid
+    n = 4096
+    alt = np.stack([rob[i % 2] for i in range(n)])
+    flags = np.zeros(n, np.uint8)
+    rc.narrowPhase(tris, alt, tris, obs, flags)
+    assert np.array_equal(flags, np.arange(n) % 2)
+    flags[:] = 1  # "all pre-valid -> untouched"
+    rc.narrowPhase(tris, alt, tris, obs, flags)
+    assert int(flags.sum()) == n
 
 
 # ---- ORACLE-GPU: the reference's own CUDA kernels on this GPU --------------------------------

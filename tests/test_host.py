@@ -1,0 +1,177 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol
+include/robocheck.h declares, mesh loaders, .conf I/O, generators, subdivision, error codes.
+No compute calls: there is no GPU here and the product has no CPU fallback."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_exports_every_declared_symbol(rc):
+    import ctypes
+    hdr = open(os.path.join(ROOT, "include", "robocheck.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(rc_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 40
+    lib = ctypes.CDLL(rc.LIB_PATH)
+    missing = [name for name in sorted(declared) if not hasattr(lib, name)]
+    assert not missing, missing
+    assert declared == {name for name, _, _ in rc.ABI}, "python binding and header disagree"
+
+
+def test_compat_symbols_link():
+    """The reference's own C++ signatures (include/robocheck_compat.hpp) are exported, and the
+    C++ harness written against them links (robocheck_cli is built by the Makefile)."""
+    out = subprocess.run(["nm", "-DC", os.path.join(ROOT, "robo-check_b200", "librobocheck.so")],
+                         capture_output=True, text=True, check=True).stdout
+    for sig in ("broadPhaseFused_sep(std::vector<Configuration", "CallMegaKernel(std::vector<Configuration",
+                "generateAABB(Vector3f*, unsigned int, unsigned int, AABB*)", "broadPhase(int, AABB const*",
+                "narrowPhase(int, int, int, int, int, Triangle const*", "loadOBJFile(char const*",
+                "readConfigurationFromFile(", "createAlphaBotConfigurations("):
+        assert sig in out, sig
+    assert os.path.exists(os.path.join(ROOT, "robo-check_b200", "robocheck_cli"))
+
+
+def test_no_cpu_fallback(rc, meshes):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(rc.RoboCheckError) as e:
+        rc.Context(meshes[0], meshes[1])
+    assert e.value.code == rc.RC_ERR_NO_DEVICE
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under the package may mention it."""
+    pkg = os.path.join(ROOT, "robo-check_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle" not in text.lower(), os.path.join(dirpath, f)
+
+
+def test_alpha_assets(rc, meshes):
+    rob, obs = meshes
+    assert rob.counts() == (792, 1008) and obs.counts() == (792, 1008)  # models/alpha1.0/README.txt:16
+    # obstacle AABB quoted in SURVEY 8a (generateAABBBaseline)
+    assert np.allclose(obs.aabb(), [-1.8928, -3.17052, -4.36586, 58.7349, 39.457, 10.6521], atol=1e-4)
+    # robot extents hard-coded by the reference generator (Utils_rai.cu:113-118)
+    assert np.allclose(rob.aabb(), [3.72119, -11.0518, -0.608012, 65.9453, 26.0984, 18.6984], atol=1e-4)
+    for m in (rob, obs):
+        for v in (m.v1, m.v2, m.v3):
+            assert v.min() >= 0 and v.max() < m.n_v
+
+
+def test_obj_loader(rc, tmp_path):
+    p = tmp_path / "m.obj"
+    p.write_text("# comment\no thing\nv 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0.5\nvn 0 0 1\nvt 0 0\n"
+                 "f 1//1 2//1 3//1\nf 1/1/1 2/1/1 3/1/1 4/1/1\n\nf 4 3 2\n")
+    x, y, z, v1, v2, v3 = rc.loadOBJFile(str(p))
+    assert x.tolist() == [0, 1, 1, 0] and z.tolist() == [0, 0, 0, 0.5]
+    # `a//n` and `a/t/n` tokens, 1-based -> 0-based, quad fanned around its first corner
+    assert list(zip(v1, v2, v3)) == [(0, 1, 2), (0, 1, 2), (0, 2, 3), (3, 2, 1)]
+    with pytest.raises(rc.RoboCheckError) as e:
+        rc.Mesh.from_obj(str(tmp_path / "missing.obj"))
+    assert e.value.code == rc.RC_ERR_IO
+    bad = tmp_path / "bad.obj"
+    bad.write_text("v 0 0 0\nf 1 2 3\n")
+    with pytest.raises(rc.RoboCheckError) as e:
+        rc.Mesh.from_obj(str(bad))
+    assert e.value.code == rc.RC_ERR_FORMAT
+
+
+def test_byu_loader_and_round_trips(rc, meshes, tmp_path):
+    p = tmp_path / "t.g"
+    p.write_text("1 4 2 6\n1 2\n0 0 0\n1 0 0\n1 1 0\n0 1 0\n1 2 -3\n1 3 -4\n")
+    m = rc.Mesh.from_byu(str(p))
+    assert m.counts() == (4, 2)
+    assert list(zip(m.v1, m.v2, m.v3)) == [(0, 1, 2), (0, 2, 3)]
+    # quads are fan-split (the PMPL loader the reference carries would throw)
+    q = tmp_path / "q.g"
+    q.write_text("1 4 1 4\n1 1\n0 0 0\n1 0 0\n1 1 0\n0 1 0\n1 2 3 -4\n")
+    assert rc.Mesh.from_byu(str(q)).counts() == (4, 2)
+    with pytest.raises(rc.RoboCheckError):
+        rc.Mesh.from_byu(str(tmp_path / "nope.g"))
+    trunc = tmp_path / "trunc.g"
+    trunc.write_text("1 4 2 6\n1 2\n0 0 0\n1 0 0\n")
+    with pytest.raises(rc.RoboCheckError) as e:
+        rc.Mesh.from_byu(str(trunc))
+    assert e.value.code == rc.RC_ERR_FORMAT
+    # OBJ <-> BYU round trips keep every float bit
+    rob = meshes[0]
+    rob.save_obj(str(tmp_path / "r.obj"))
+    rob.save_byu(str(tmp_path / "r.g"))
+    for back in (rc.Mesh.from_obj(str(tmp_path / "r.obj")), rc.Mesh.from_byu(str(tmp_path / "r.g"))):
+        for a, b in zip(rob.arrays(), back.arrays()):
+            assert np.array_equal(a, b)
+
+
+def test_conf_io(rc, golden, tmp_path):
+    confs = golden["hard_confs10k"]["confs"][:257]
+    tags = golden["hard_confs10k"]["tags"][:257]
+    p = str(tmp_path / "c.conf")
+    rc.writeConfigurationToFileTagged(confs, tags, p)
+    head = open(p).readline()
+    assert head == f"There are {int(tags.sum())} valid configurations and {int(257 - tags.sum())} invalid configurations\n"
+    back, tback = rc.readConfigurationFromFileTagged(p)
+    assert np.array_equal(tback, tags)
+    # the reference writes 6 significant digits (default ostream precision), so the text
+    # quantises; what was read from a 6-digit file survives a second round trip exactly
+    assert np.allclose(back, confs, rtol=1e-5, atol=1e-6)
+    rc.writeConfigurationToFileTagged(back, tback, p)
+    assert np.array_equal(rc.readConfigurationFromFile(p), back)
+    empty = str(tmp_path / "e.conf")
+    rc.writeConfigurationToFileTagged(np.zeros((0, 6), np.float32), None, empty)
+    assert rc.readConfigurationFromFile(empty).shape == (0, 6)
+    with pytest.raises(rc.RoboCheckError):
+        rc.readConfigurationFromFile(str(tmp_path / "missing.conf"))
+
+
+def test_generators(rc):
+    a = rc.createAlphaBotConfigurations(1000, True, 508)
+    b = rc.createAlphaBotConfigurations(1000, True, 508)
+    c = rc.createAlphaBotConfigurations(1000, True, 509)
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+    rng = np.array([65.9453 - 3.72119, 26.0984 + 11.0518, 18.6984 + 0.608012], np.float32)
+    assert np.all(np.abs(a[:, :3]) <= rng / 200 + 1e-6)   # hard: +-range/200 (Utils_rai.cu:124-128)
+    assert np.all(np.abs(a[:, 3:]) <= np.pi + 1e-6)
+    e = rc.createAlphaBotConfigurations(1000, False, 1)
+    assert np.all(np.abs(e[:, :3]) <= rng * 10 + 1e-3) and np.abs(e[:, 0]).max() > 100
+    # draw order x, y, z, pitch, yaw, roll from ONE mt19937 stream (Utils_rai.cu:337-346):
+    # a prefix of a longer run is the shorter run
+    assert np.array_equal(rc.createAlphaBotConfigurations(10, True, 508), a[:10])
+    g = rc.generateConfs(5, -1, 1, -2, 2, -3, 3, 7)
+    assert g.shape == (5, 6) and np.all(np.abs(g[:, 1]) <= 2)
+
+
+def test_subdivide(rc, meshes):
+    obs = meshes[1]
+    s1 = obs.subdivide(1)
+    assert s1.n_t == 4 * obs.n_t
+    # one new vertex per distinct edge: between 3T/2 (closed manifold, every edge shared) and 3T
+    assert obs.n_v + 3 * obs.n_t // 2 <= s1.n_v <= obs.n_v + 3 * obs.n_t
+    assert np.array_equal(s1.aabb(), obs.aabb())
+    assert obs.subdivide(0).counts() == obs.counts()
+    assert obs.subdivide(2).n_t == 16 * obs.n_t   # BASELINE config 5, "16x-subdivided"
+
+
+def test_sharding_partition():
+    from robocheck_b200 import sharding as sh
+    for n in (0, 1, 31, 32, 33, 1000, 100000, 1_000_000):
+        for world in (1, 2, 4, 8):
+            seen = 0
+            for r in range(world):
+                lo, hi, per = sh.shard_bounds(n, world, r)
+                assert per % 32 == 0 and lo == min(n, r * per) and 0 <= hi - lo <= per
+                seen += hi - lo
+            assert seen == n
+    flags = (np.arange(77) % 3 == 0).astype(np.uint8)
+    w = sh.pack_bitmask(flags, 3)
+    assert w.dtype == np.uint32 and len(w) == 3
+    assert np.array_equal(sh.unpack_bitmask(w, 77), flags)
+    assert (int(w[0]) >> 3) & 1 == 1 and (int(w[0]) >> 4) & 1 == 0
