@@ -74,14 +74,14 @@ GatheredTris gather(const std::vector<float> &x, const std::vector<float> &y,
     return g;
 }
 
-int upload_obstacle(rc_ctx *ctx, const GatheredTris &g, float4 **a, float4 **b, float4 **c, float4 **d)
+int upload_obstacle(rc_ctx *ctx, const GatheredTris &g, float4 **a, float4 **b, float4 **c, float **d)
 {
     float4 *ra = nullptr, *rb = nullptr, *rcv = nullptr;
     const size_t n = g.a.size();
     cudaError_t e;
     if ((e = upload(ctx, &ra, g.a)) || (e = upload(ctx, &rb, g.b)) || (e = upload(ctx, &rcv, g.c)) ||
         (e = dev_alloc(ctx, a, n)) || (e = dev_alloc(ctx, b, n)) || (e = dev_alloc(ctx, c, n)) ||
-        (e = dev_alloc(ctx, d, n)))
+        (e = dev_alloc(ctx, d, (n + 3) & ~(size_t)3)))
         return check_cuda(ctx, e, "obstacle upload");
     if ((e = launch_obstacle_planes(ra, rb, rcv, *a, *b, *c, *d, (int)n, ctx->own_stream)))
         return check_cuda(ctx, e, "obstacle planes");
@@ -211,6 +211,11 @@ int rc_create(rc_ctx **out, const float *rob_x, const float *rob_y, const float 
                 lo[2] = std::min(lo[2], (double)rob_z[v]); hi[2] = std::max(hi[2], (double)rob_z[v]);
             }
             for (int k = 0; k < 3; k++) t.rob_center[k] = (float)(0.5 * (lo[k] + hi[k]));
+            for (int k = 0; k < 3; k++) {
+                t.rob_box_c[k] = t.rob_center[k];
+                const double e = std::max(hi[k] - (double)t.rob_center[k], (double)t.rob_center[k] - lo[k]);
+                t.rob_box_e[k] = (float)(e * (1.0 + 1e-6)) + 1e-4f;
+            }
             double r2 = 0;
             for (int v = 0; v < n_rob_v; v++) {
                 const double dx = rob_x[v] - t.rob_center[0], dy = rob_y[v] - t.rob_center[1],

@@ -24,8 +24,7 @@
 
 namespace rc {
 
-constexpr int kCulledWarps = 16;
-constexpr int kCulledThreads = kCulledWarps * 32;
+constexpr int kCulledWarpsDefault = 24;  // warps per CTA (one CTA per SM); 16/20/24 instantiated
 constexpr int kStackCap = 1024;  // node pairs per warp; overflow falls back to the exhaustive sweep
 constexpr int kLeafQCap = 64;
 constexpr int kTailQCap = 160;   // pairs that passed both plane tests, finished 32 at a time
@@ -37,6 +36,8 @@ struct CulledArgs {
     const float4 *rob_bvh, *obs_bvh;
     int n_rob_nodes, n_obs_nodes;
     float sph_x, sph_y, sph_z, sph_r;
+    float box_cx, box_cy, box_cz, box_ex, box_ey, box_ez;  // robot local AABB (centre, half extent)
+    int probe_stride;                                      // probe vertices: lane * stride
 };
 
 __device__ __forceinline__ bool boxes_overlap(const Mat34 &m, const float4 r0, const float4 r1,
@@ -67,7 +68,7 @@ __device__ __forceinline__ bool boxes_overlap(const Mat34 &m, const float4 r0, c
 __device__ __noinline__ bool narrow_exhaustive(const Mat34 m, const float4 *s_rob_v,
                                                const uint2 *s_rob_t, int n_rob_t,
                                                const float4 *s_obs_a, const float4 *s_obs_b,
-                                               const float4 *s_obs_c, const float4 *s_obs_d,
+                                               const float4 *s_obs_c, const float *s_obs_d,
                                                int n_obs_t, int lane)
 {
     bool hit = false;
@@ -84,7 +85,7 @@ __device__ __noinline__ bool narrow_exhaustive(const Mat34 m, const float4 *s_ro
         for (int k = 0; k < n_obs_t; k++) {
             const float4 oa = s_obs_a[k], ob = s_obs_b[k], oc = s_obs_c[k];
             const Tri o = {oa.x, oa.y, oa.z, ob.x, ob.y, ob.z, oc.x, oc.y, oc.z};
-            const Plane po = {oa.w, ob.w, oc.w, s_obs_d[k].x};
+            const Plane po = {oa.w, ob.w, oc.w, s_obs_d[k]};
             if (active && pair_hits(r, pr, o, po)) hit = true;
         }
         hit = __any_sync(kFull, hit);
@@ -92,8 +93,8 @@ __device__ __noinline__ bool narrow_exhaustive(const Mat34 m, const float4 *s_ro
     return hit;
 }
 
-template <bool STATS>
-__global__ void __launch_bounds__(kCulledThreads, 1) check_culled_kernel(const CulledArgs a)
+template <bool STATS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const CulledArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const CheckArgs &c = a.c;
@@ -104,8 +105,8 @@ __global__ void __launch_bounds__(kCulledThreads, 1) check_culled_kernel(const C
     float4 *s_obs_a = s_obs_bvh + 2 * a.n_obs_nodes;
     float4 *s_obs_b = s_obs_a + c.n_obs_t;
     float4 *s_obs_c = s_obs_b + c.n_obs_t;
-    float4 *s_obs_d = s_obs_c + c.n_obs_t;
-    uint2 *s_rob_t = reinterpret_cast<uint2 *>(s_obs_d + c.n_obs_t);
+    float *s_obs_d = reinterpret_cast<float *>(s_obs_c + c.n_obs_t);
+    uint2 *s_rob_t = reinterpret_cast<uint2 *>(s_obs_d + pad4(c.n_obs_t));
     uint32_t *s_work = reinterpret_cast<uint32_t *>(s_rob_t + c.n_rob_t + (c.n_rob_t & 1));
 
     if (threadIdx.x == 0) {
@@ -117,14 +118,15 @@ __global__ void __launch_bounds__(kCulledThreads, 1) check_culled_kernel(const C
         const uint32_t bv = c.n_rob_v_pad * 16u, bo = c.n_obs_t * 16u,
                        bt = (c.n_rob_t + (c.n_rob_t & 1)) * 8u;
         const uint32_t brn = a.n_rob_nodes * 32u, bon = a.n_obs_nodes * 32u;
-        mbar_expect_tx(bar, bv + 4u * bo + bt + brn + bon);
+        const uint32_t bd = pad4(c.n_obs_t) * 4u;
+        mbar_expect_tx(bar, bv + 3u * bo + bd + bt + brn + bon);
         tma_load_1d(s_rob_v, c.rob_v, bv, bar);
         tma_load_1d(s_rob_bvh, a.rob_bvh, brn, bar);
         tma_load_1d(s_obs_bvh, a.obs_bvh, bon, bar);
         tma_load_1d(s_obs_a, c.obs_a, bo, bar);
         tma_load_1d(s_obs_b, c.obs_b, bo, bar);
         tma_load_1d(s_obs_c, c.obs_c, bo, bar);
-        tma_load_1d(s_obs_d, c.obs_d, bo, bar);
+        tma_load_1d(s_obs_d, c.obs_d, bd, bar);
         tma_load_1d(s_rob_t, c.rob_t, bt, bar);
     }
     mbar_wait(bar, 0);
@@ -165,15 +167,52 @@ __global__ void __launch_bounds__(kCulledThreads, 1) check_culled_kernel(const C
                 }
             }
 
-            // A: exact AABB and broad-phase flag
-            float box[6];
-            warp_aabb(m, s_rob_v, c.n_rob_v_pad, lane, box);
-            if (broad_valid(box[0], box[1], box[2], box[3], box[4], box[5], c.obs_box.x_min,
-                            c.obs_box.y_min, c.obs_box.z_min, c.obs_box.x_max, c.obs_box.y_max,
-                            c.obs_box.z_max)) {
-                publish(c, i, true, lane);
-                if (STATS) st_broad++;
-                continue;
+            // A: exact broad-phase flag.  Two shortcuts decide it without the full vertex sweep:
+            //  - the world AABB of the robot's local bounding box contains the exact vertex AABB;
+            //    if it clears the obstacle AABB with margin the configuration is valid;
+            //  - if ANY exactly-transformed robot vertex lies inside the obstacle AABB, the two
+            //    AABBs overlap on every axis (robot.min <= v <= obstacle.max, obstacle.min <= v <=
+            //    robot.max), so the broad phase cannot clear it.
+            // Otherwise the lanes transform all vertices and reduce the exact AABB.
+            {
+                const float cx = fmaf(m.r02, a.box_cz, fmaf(m.r01, a.box_cy, fmaf(m.r00, a.box_cx, m.tx)));
+                const float cy = fmaf(m.r12, a.box_cz, fmaf(m.r11, a.box_cy, fmaf(m.r10, a.box_cx, m.ty)));
+                const float cz = fmaf(m.r22, a.box_cz, fmaf(m.r21, a.box_cy, fmaf(m.r20, a.box_cx, m.tz)));
+                const float ex = fmaf(fabsf(m.r02), a.box_ez, fmaf(fabsf(m.r01), a.box_ey, fabsf(m.r00) * a.box_ex));
+                const float ey = fmaf(fabsf(m.r12), a.box_ez, fmaf(fabsf(m.r11), a.box_ey, fabsf(m.r10) * a.box_ex));
+                const float ez = fmaf(fabsf(m.r22), a.box_ez, fmaf(fabsf(m.r21), a.box_ey, fabsf(m.r20) * a.box_ex));
+                const float gx = ex + 0.01f + 4e-6f * (fabsf(cx) + ex);
+                const float gy = ey + 0.01f + 4e-6f * (fabsf(cy) + ey);
+                const float gz = ez + 0.01f + 4e-6f * (fabsf(cz) + ez);
+                const bool clear = cx - gx > c.obs_box.x_max || cx + gx < c.obs_box.x_min ||
+                                   cy - gy > c.obs_box.y_max || cy + gy < c.obs_box.y_min ||
+                                   cz - gz > c.obs_box.z_max || cz + gz < c.obs_box.z_min;
+                if (clear) {
+                    publish(c, i, true, lane);
+                    if (STATS) st_sphere++;
+                    continue;
+                }
+            }
+            bool certain_overlap;
+            {
+                const float4 p = s_rob_v[lane * a.probe_stride];
+                float x, y, z;
+                xform(m, p.x, p.y, p.z, x, y, z);
+                const bool inside = c.obs_box.x_min <= x && x <= c.obs_box.x_max &&
+                                    c.obs_box.y_min <= y && y <= c.obs_box.y_max &&
+                                    c.obs_box.z_min <= z && z <= c.obs_box.z_max;
+                certain_overlap = __any_sync(kFull, inside);
+            }
+            if (!certain_overlap) {
+                float box[6];
+                warp_aabb(m, s_rob_v, c.n_rob_v_pad, lane, box);
+                if (broad_valid(box[0], box[1], box[2], box[3], box[4], box[5], c.obs_box.x_min,
+                                c.obs_box.y_min, c.obs_box.z_min, c.obs_box.x_max, c.obs_box.y_max,
+                                c.obs_box.z_max)) {
+                    publish(c, i, true, lane);
+                    if (STATS) st_broad++;
+                    continue;
+                }
             }
 
             // B + C + D
@@ -198,7 +237,7 @@ __global__ void __launch_bounds__(kCulledThreads, 1) check_culled_kernel(const C
                     const Plane pr = plane_of(r);
                     const float4 oa = s_obs_a[k], ob = s_obs_b[k], oc = s_obs_c[k];
                     const Tri o = {oa.x, oa.y, oa.z, ob.x, ob.y, ob.z, oc.x, oc.y, oc.z};
-                    const Plane po = {oa.w, ob.w, oc.w, s_obs_d[k].x};
+                    const Plane po = {oa.w, ob.w, oc.w, s_obs_d[k]};
                     const float dO0 = sdist(pr, o.ax, o.ay, o.az), dO1 = sdist(pr, o.bx, o.by, o.bz),
                                 dO2 = sdist(pr, o.cx, o.cy, o.cz);
                     const float dR0 = sdist(po, r.ax, r.ay, r.az), dR1 = sdist(po, r.bx, r.by, r.bz),
@@ -238,7 +277,7 @@ __global__ void __launch_bounds__(kCulledThreads, 1) check_culled_kernel(const C
                                     straddles(sdist(pr, oa.x, oa.y, oa.z), sdist(pr, ob.x, ob.y, ob.z),
                                               sdist(pr, oc.x, oc.y, oc.z));
                         if (pass) {
-                            const Plane po = {oa.w, ob.w, oc.w, s_obs_d[k].x};
+                            const Plane po = {oa.w, ob.w, oc.w, s_obs_d[k]};
                             pass = straddles(sdist(po, r.ax, r.ay, r.az), sdist(po, r.bx, r.by, r.bz),
                                              sdist(po, r.cx, r.cy, r.cz));
                         }
@@ -317,12 +356,12 @@ __global__ void __launch_bounds__(kCulledThreads, 1) check_culled_kernel(const C
     }
 }
 
-static size_t culled_smem_bytes(const DeviceTables &t)
+static size_t culled_smem_bytes(const DeviceTables &t, int warps)
 {
     size_t b = 16 + (size_t)t.n_rob_v_pad * 16 + (size_t)t.n_rob_nodes * 32 +
-               (size_t)t.n_obs_nodes * 32 + (size_t)t.n_obs_t * 64 +
+               (size_t)t.n_obs_nodes * 32 + (size_t)t.n_obs_t * 48 + (size_t)pad4(t.n_obs_t) * 4 +
                (size_t)(t.n_rob_t + (t.n_rob_t & 1)) * 8;
-    b += (size_t)kCulledWarps * kWarpWork * 4;
+    b += (size_t)warps * kWarpWork * 4;
     return b;
 }
 
@@ -331,10 +370,12 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
                                 cudaStream_t stream)
 {
     const DeviceTables &t = ctx->t;
-    const size_t smem = culled_smem_bytes(t);
-    if (smem > (size_t)ctx->max_smem_optin || t.n_rob_nodes > 65535 || t.n_obs_nodes > 65535 ||
-        t.n_rob_v > 65535)
-        return cudaErrorInvalidConfiguration;
+    int warps = kCulledWarpsDefault;
+    if (const char *env = getenv("RC_CULLED_WARPS")) warps = atoi(env);  // tuning knob
+    if (warps != 16 && warps != 20 && warps != 24) warps = kCulledWarpsDefault;
+    // fewer warps per CTA when the tables leave less room for the per-warp work areas
+    while (warps > 16 && culled_smem_bytes(t, warps) > (size_t)ctx->max_smem_optin) warps -= 4;
+    const size_t smem = culled_smem_bytes(t, warps);
     CulledArgs a;
     a.c.rob_v = t.rob_v; a.c.rob_t = t.rob_t_sorted;
     a.c.obs_a = t.obs_a_sorted; a.c.obs_b = t.obs_b_sorted; a.c.obs_c = t.obs_c_sorted;
@@ -347,13 +388,18 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
     a.n_rob_nodes = t.n_rob_nodes; a.n_obs_nodes = t.n_obs_nodes;
     a.sph_x = t.rob_center[0]; a.sph_y = t.rob_center[1]; a.sph_z = t.rob_center[2];
     a.sph_r = t.rob_radius;
+    a.box_cx = t.rob_box_c[0]; a.box_cy = t.rob_box_c[1]; a.box_cz = t.rob_box_c[2];
+    a.box_ex = t.rob_box_e[0]; a.box_ey = t.rob_box_e[1]; a.box_ez = t.rob_box_e[2];
+    a.probe_stride = max(1, t.n_rob_v / 32);
     const int grid = ctx->sm_count;
-    const long warps = (long)grid * kCulledWarps;
-    a.c.chunk = (int)max(1L, min(16L, n / (warps * 8)));
-    auto kern = want_stats ? check_culled_kernel<true> : check_culled_kernel<false>;
+    a.c.chunk = (int)max(1L, min(16L, n / ((long)grid * warps * 8)));
+    void (*kern)(const CulledArgs) = nullptr;
+    if (warps == 16) kern = want_stats ? check_culled_kernel<true, 16> : check_culled_kernel<false, 16>;
+    else if (warps == 20) kern = want_stats ? check_culled_kernel<true, 20> : check_culled_kernel<false, 20>;
+    else kern = want_stats ? check_culled_kernel<true, 24> : check_culled_kernel<false, 24>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<grid, kCulledThreads, smem, stream>>>(a);
+    kern<<<grid, warps * 32, smem, stream>>>(a);
     return cudaGetLastError();
 }
 

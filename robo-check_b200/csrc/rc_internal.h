@@ -21,19 +21,20 @@ struct DeviceTables {
     float4 *obs_a = nullptr;    // [n_obs_t]  (p1.x, p1.y, p1.z, N.x)
     float4 *obs_b = nullptr;    // [n_obs_t]  (p2.x, p2.y, p2.z, N.y)
     float4 *obs_c = nullptr;    // [n_obs_t]  (p3.x, p3.y, p3.z, N.z)
-    float4 *obs_d = nullptr;    // [n_obs_t]  (s = N.p1, 0, 0, 0)
+    float *obs_d = nullptr;     // [n_obs_t↑4] s = N.p1 (the reference's d is -s)
     // BVHs for the culled path (see bvh.h): two float4 per node
     float4 *rob_bvh = nullptr;  // [2 * n_rob_nodes]
     float4 *obs_bvh = nullptr;  // [2 * n_obs_nodes]
     uint2 *rob_t_sorted = nullptr;   // robot triangles in BVH leaf order
-    float4 *obs_a_sorted = nullptr, *obs_b_sorted = nullptr, *obs_c_sorted = nullptr,
-           *obs_d_sorted = nullptr;  // obstacle triangles in BVH leaf order
+    float4 *obs_a_sorted = nullptr, *obs_b_sorted = nullptr, *obs_c_sorted = nullptr;
+    float *obs_d_sorted = nullptr;   // obstacle triangles in BVH leaf order
     int n_rob_v = 0, n_rob_t = 0, n_obs_v = 0, n_obs_t = 0;
     int n_rob_nodes = 0, n_obs_nodes = 0;
     int n_rob_v_pad = 0;        // n_rob_v rounded up to 32 (padding repeats vertex 0)
     rc_aabb obs_box;
     float rob_center[3];        // bounding sphere of the robot in its local frame
     float rob_radius;
+    float rob_box_c[3], rob_box_e[3];  // robot local AABB: centre and half extent (rounded up)
 };
 
 }  // namespace rc
@@ -104,7 +105,7 @@ cudaError_t launch_broad(long n, const rc_aabb *d_robots, const rc_aabb *d_obsta
 cudaError_t launch_narrow_soa(const rc_ctx *ctx, const float *d_x, const float *d_y,
                               const float *d_z, long n, uint8_t *d_valid, cudaStream_t stream);
 cudaError_t launch_obstacle_planes(const float4 *a, const float4 *b, const float4 *c, float4 *a_out,
-                                   float4 *b_out, float4 *c_out, float4 *d_out, int n,
+                                   float4 *b_out, float4 *c_out, float *d_out, int n,
                                    cudaStream_t stream);
 
 }  // namespace rc

@@ -9,6 +9,7 @@
 //   check_culled_kernel  same result, BVH-culled (rc_culled.cuh).
 //   stage kernels        the un-fused stage API (transform / AABB / broad / narrow).
 #include <float.h>
+#include <stdlib.h>
 
 #include "rc_device.cuh"
 #include "rc_internal.h"
@@ -18,12 +19,13 @@ namespace rc {
 constexpr int kWarpsPerCta = 8;
 constexpr int kThreads = kWarpsPerCta * 32;
 constexpr unsigned kFull = 0xffffffffu;
+__host__ __device__ constexpr int pad4(int n) { return (n + 3) & ~3; }
 
 // ------------------------------------------------------------------------------------------
 // Obstacle planes: configuration independent, computed once per context with the same
 // arithmetic the reference re-executes per pair (compute_plane_sep, narrow-phase.cu:629).
 __global__ void obstacle_planes_kernel(const float4 *a, const float4 *b, const float4 *c,
-                                       float4 *a_out, float4 *b_out, float4 *c_out, float4 *d_out,
+                                       float4 *a_out, float4 *b_out, float4 *c_out, float *d_out,
                                        int n)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -34,11 +36,11 @@ __global__ void obstacle_planes_kernel(const float4 *a, const float4 *b, const f
     a_out[k] = make_float4(A.x, A.y, A.z, p.nx);
     b_out[k] = make_float4(B.x, B.y, B.z, p.ny);
     c_out[k] = make_float4(C.x, C.y, C.z, p.nz);
-    d_out[k] = make_float4(p.s, 0.f, 0.f, 0.f);
+    d_out[k] = p.s;
 }
 
 cudaError_t launch_obstacle_planes(const float4 *a, const float4 *b, const float4 *c, float4 *a_out,
-                                   float4 *b_out, float4 *c_out, float4 *d_out, int n,
+                                   float4 *b_out, float4 *c_out, float *d_out, int n,
                                    cudaStream_t stream)
 {
     if (n <= 0) return cudaSuccess;
@@ -91,7 +93,8 @@ __device__ __forceinline__ void warp_aabb(const Mat34 &m, const float4 *__restri
 struct CheckArgs {
     const float4 *rob_v;   // [n_rob_v_pad]
     const uint2 *rob_t;    // [n_rob_t]
-    const float4 *obs_a, *obs_b, *obs_c, *obs_d;  // [n_obs_t]
+    const float4 *obs_a, *obs_b, *obs_c;  // [n_obs_t]
+    const float *obs_d;                   // [n_obs_t rounded up to 4]
     int n_rob_v_pad, n_rob_t, n_obs_t;
     rc_aabb obs_box;
     const rc_config *confs;
@@ -122,8 +125,8 @@ __global__ void __launch_bounds__(kThreads, 2) check_brute_kernel(const CheckArg
     float4 *s_obs_a = s_rob_v + a.n_rob_v_pad;
     float4 *s_obs_b = s_obs_a + a.n_obs_t;
     float4 *s_obs_c = s_obs_b + a.n_obs_t;
-    float4 *s_obs_d = s_obs_c + a.n_obs_t;
-    uint2 *s_rob_t = reinterpret_cast<uint2 *>(s_obs_d + a.n_obs_t);
+    float *s_obs_d = reinterpret_cast<float *>(s_obs_c + a.n_obs_t);
+    uint2 *s_rob_t = reinterpret_cast<uint2 *>(s_obs_d + pad4(a.n_obs_t));
 
     // Stage the mesh tables with TMA bulk copies (one elected thread issues them, everybody
     // waits on the mbarrier's transaction count).
@@ -135,12 +138,13 @@ __global__ void __launch_bounds__(kThreads, 2) check_brute_kernel(const CheckArg
     if (threadIdx.x == 0) {
         const uint32_t bv = a.n_rob_v_pad * 16u, bo = a.n_obs_t * 16u,
                        bt = (a.n_rob_t + (a.n_rob_t & 1)) * 8u;
-        mbar_expect_tx(bar, bv + 4u * bo + bt);
+        const uint32_t bd = pad4(a.n_obs_t) * 4u;
+        mbar_expect_tx(bar, bv + 3u * bo + bd + bt);
         tma_load_1d(s_rob_v, a.rob_v, bv, bar);
         tma_load_1d(s_obs_a, a.obs_a, bo, bar);
         tma_load_1d(s_obs_b, a.obs_b, bo, bar);
         tma_load_1d(s_obs_c, a.obs_c, bo, bar);
-        tma_load_1d(s_obs_d, a.obs_d, bo, bar);
+        tma_load_1d(s_obs_d, a.obs_d, bd, bar);
         tma_load_1d(s_rob_t, a.rob_t, bt, bar);
     }
     mbar_wait(bar, 0);
@@ -181,7 +185,7 @@ __global__ void __launch_bounds__(kThreads, 2) check_brute_kernel(const CheckArg
                 auto finish = [&](int k) {
                     const float4 oa = s_obs_a[k], ob = s_obs_b[k], oc = s_obs_c[k];
                     const Tri o = {oa.x, oa.y, oa.z, ob.x, ob.y, ob.z, oc.x, oc.y, oc.z};
-                    const Plane po = {oa.w, ob.w, oc.w, s_obs_d[k].x};
+                    const Plane po = {oa.w, ob.w, oc.w, s_obs_d[k]};
                     const float dR0 = sdist(po, r.ax, r.ay, r.az), dR1 = sdist(po, r.bx, r.by, r.bz),
                                 dR2 = sdist(po, r.cx, r.cy, r.cz);
                     if (straddles(dR0, dR1, dR2)) {
@@ -240,7 +244,7 @@ namespace rc {
 
 static size_t brute_smem_bytes(const DeviceTables &t)
 {
-    return 16 + (size_t)t.n_rob_v_pad * 16 + (size_t)t.n_obs_t * 64 +
+    return 16 + (size_t)t.n_rob_v_pad * 16 + (size_t)t.n_obs_t * 48 + (size_t)pad4(t.n_obs_t) * 4 +
            (size_t)(t.n_rob_t + (t.n_rob_t & 1)) * 8;
 }
 

@@ -278,8 +278,8 @@ __global__ void __launch_bounds__(kThreads, 2) narrow_soa_kernel(const CheckArgs
     float4 *s_obs_a = reinterpret_cast<float4 *>(smem_raw + 16);
     float4 *s_obs_b = s_obs_a + a.n_obs_t;
     float4 *s_obs_c = s_obs_b + a.n_obs_t;
-    float4 *s_obs_d = s_obs_c + a.n_obs_t;
-    uint2 *s_rob_t = reinterpret_cast<uint2 *>(s_obs_d + a.n_obs_t);
+    float *s_obs_d = reinterpret_cast<float *>(s_obs_c + a.n_obs_t);
+    uint2 *s_rob_t = reinterpret_cast<uint2 *>(s_obs_d + pad4(a.n_obs_t));
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         mbar_fence_init();
@@ -287,11 +287,12 @@ __global__ void __launch_bounds__(kThreads, 2) narrow_soa_kernel(const CheckArgs
     __syncthreads();
     if (threadIdx.x == 0) {
         const uint32_t bo = a.n_obs_t * 16u, bt = (a.n_rob_t + (a.n_rob_t & 1)) * 8u;
-        mbar_expect_tx(bar, 4u * bo + bt);
+        const uint32_t bd = pad4(a.n_obs_t) * 4u;
+        mbar_expect_tx(bar, 3u * bo + bd + bt);
         tma_load_1d(s_obs_a, a.obs_a, bo, bar);
         tma_load_1d(s_obs_b, a.obs_b, bo, bar);
         tma_load_1d(s_obs_c, a.obs_c, bo, bar);
-        tma_load_1d(s_obs_d, a.obs_d, bo, bar);
+        tma_load_1d(s_obs_d, a.obs_d, bd, bar);
         tma_load_1d(s_rob_t, a.rob_t, bt, bar);
     }
     mbar_wait(bar, 0);
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(kThreads, 2) narrow_soa_kernel(const CheckArgs
             auto finish = [&](int k) {
                 const float4 oa = s_obs_a[k], ob = s_obs_b[k], oc = s_obs_c[k];
                 const Tri o = {oa.x, oa.y, oa.z, ob.x, ob.y, ob.z, oc.x, oc.y, oc.z};
-                const Plane po = {oa.w, ob.w, oc.w, s_obs_d[k].x};
+                const Plane po = {oa.w, ob.w, oc.w, s_obs_d[k]};
                 const float dR0 = sdist(po, r.ax, r.ay, r.az), dR1 = sdist(po, r.bx, r.by, r.bz),
                             dR2 = sdist(po, r.cx, r.cy, r.cz);
                 if (straddles(dR0, dR1, dR2)) {
@@ -359,7 +360,8 @@ cudaError_t launch_narrow_soa(const rc_ctx *ctx, const float *d_x, const float *
     a.obs_box = t.obs_box;
     a.confs = nullptr; a.n = n; a.valid = d_valid; a.bitmask = nullptr;
     a.counters = ctx->d_counters; a.chunk = 1;
-    const size_t smem = 16 + (size_t)t.n_obs_t * 64 + (size_t)(t.n_rob_t + (t.n_rob_t & 1)) * 8;
+    const size_t smem = 16 + (size_t)t.n_obs_t * 48 + (size_t)pad4(t.n_obs_t) * 4 +
+                        (size_t)(t.n_rob_t + (t.n_rob_t & 1)) * 8;
     if (smem > (size_t)ctx->max_smem_optin) return cudaErrorInvalidConfiguration;
     e = cudaFuncSetAttribute(narrow_soa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
