@@ -122,6 +122,7 @@ int rc_narrow_phase_host(int n, int n_rob_t, int n_rob_v, int n_obs_t, int n_obs
 typedef struct {
     unsigned long long broad_cleared, sphere_cleared, narrow_valid, narrow_invalid;
     unsigned long long node_pairs, leaf_pairs, tri_pairs, tail_pairs, overflow, launches;
+    unsigned long long node_rounds, leaf_rounds, tail_rounds; /* warp steps of each phase */
 } rc_stats;
 /* Statistics of rc_check calls since the last reset; counting is off by default. */
 int rc_stats_enable(rc_ctx *ctx, int on);

@@ -38,7 +38,8 @@ class RoboCheckError(RuntimeError):
 class rc_stats(C.Structure):
     _fields_ = [(k, C.c_ulonglong) for k in (
         "broad_cleared", "sphere_cleared", "narrow_valid", "narrow_invalid", "node_pairs",
-        "leaf_pairs", "tri_pairs", "tail_pairs", "overflow", "launches")]
+        "leaf_pairs", "tri_pairs", "tail_pairs", "overflow", "launches", "node_rounds",
+        "leaf_rounds", "tail_rounds")]
 
 
 # every symbol include/robocheck.h declares: (name, restype, argtypes)

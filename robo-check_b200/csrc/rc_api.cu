@@ -188,7 +188,9 @@ int rc_create(rc_ctx **out, const float *rob_x, const float *rob_y, const float 
     cudaError_t e;
     do {
         if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) ||
-            (e = cudaEventCreate(&ctx->ev0)) || (e = cudaEventCreate(&ctx->ev1))) {
+            (e = cudaStreamCreateWithFlags(&ctx->own_stream2, cudaStreamNonBlocking)) ||
+            (e = cudaEventCreate(&ctx->ev0)) || (e = cudaEventCreate(&ctx->ev1)) ||
+            (e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming))) {
             rcode = check_cuda(ctx, e, "stream/event");
             break;
         }
@@ -250,6 +252,7 @@ int rc_create(rc_ctx **out, const float *rob_x, const float *rob_y, const float 
             (e = upload(ctx, &t.rob_t, rt, rt_pad)) || (e = upload(ctx, &t.rob_t_sorted, rts, rt_pad)) ||
             (e = upload(ctx, &t.rob_bvh, rbn)) || (e = upload(ctx, &t.obs_bvh, obn)) ||
             (e = dev_alloc(ctx, &ctx->d_counters, RC_NUM_COUNTERS)) ||
+            (e = dev_alloc(ctx, &ctx->d_queues, kHostChunks)) ||
             (e = dev_alloc(ctx, &ctx->d_obs_box, 1)) ||
             (e = cudaMemcpy(ctx->d_obs_box, &t.obs_box, sizeof(rc_aabb), cudaMemcpyHostToDevice))) {
             rcode = check_cuda(ctx, e, "table upload");
@@ -295,6 +298,8 @@ void rc_destroy(rc_ctx *ctx)
     if (ctx->d_stage_valid) cudaFree(ctx->d_stage_valid);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->own_stream2) cudaStreamDestroy(ctx->own_stream2);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -324,7 +329,7 @@ int rc_check(rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_valid, ui
     if (n == 0) return RC_OK;
     cudaSetDevice(ctx->device);
     cudaError_t e = launch_check(ctx, d_confs, n, d_valid, d_bitmask, mode, ctx->stats_on,
-                                 stream_of(ctx, stream));
+                                 stream_of(ctx, stream), nullptr);
     if (e == cudaErrorInvalidConfiguration)
         return set_error(ctx, RC_ERR_UNSUPPORTED, "mesh tables do not fit in shared memory");
     ctx->launches++;
@@ -352,14 +357,18 @@ int rc_check_host(rc_ctx *ctx, const rc_config *h_confs, long n, uint8_t *h_vali
         std::memcpy(ctx->h_pinned_confs, h_confs, (size_t)n * sizeof(rc_config));
         src = ctx->h_pinned_confs;
     }
+    uint8_t *dst = out_pinned ? h_valid : ctx->h_pinned_valid;
     if ((e = cudaMemcpyAsync(ctx->d_stage_confs, src, (size_t)n * sizeof(rc_config),
                              cudaMemcpyHostToDevice, s)))
         return check_cuda(ctx, e, "H2D configurations");
     cudaEventRecord(ctx->ev0, s);
-    rcode = rc_check(ctx, ctx->d_stage_confs, n, ctx->d_stage_valid, nullptr, mode, s);
-    if (rcode != RC_OK) return rcode;
+    e = launch_check(ctx, ctx->d_stage_confs, n, ctx->d_stage_valid, nullptr, mode, ctx->stats_on, s,
+                     ctx->d_queues);
+    if (e == cudaErrorInvalidConfiguration)
+        return set_error(ctx, RC_ERR_UNSUPPORTED, "mesh tables do not fit in shared memory");
+    if (e) return check_cuda(ctx, e, "rc_check_host launch");
+    ctx->launches++;
     cudaEventRecord(ctx->ev1, s);
-    uint8_t *dst = out_pinned ? h_valid : ctx->h_pinned_valid;
     if ((e = cudaMemcpyAsync(dst, ctx->d_stage_valid, (size_t)n, cudaMemcpyDeviceToHost, s)) ||
         (e = cudaStreamSynchronize(s)))
         return check_cuda(ctx, e, "D2H flags");
@@ -530,6 +539,8 @@ int rc_stats_read(rc_ctx *ctx, rc_stats *out, int reset)
     out->node_pairs = h[CNT_NODE_PAIRS]; out->leaf_pairs = h[CNT_LEAF_PAIRS];
     out->tri_pairs = h[CNT_TRI_PAIRS]; out->tail_pairs = h[CNT_TAIL_PAIRS];
     out->overflow = h[CNT_OVERFLOW]; out->launches = ctx->launches;
+    out->node_rounds = h[CNT_NODE_ROUNDS]; out->leaf_rounds = h[CNT_LEAF_ROUNDS];
+    out->tail_rounds = h[CNT_TAIL_ROUNDS];
     if (reset) {
         ctx->launches = 0;
         if ((e = cudaMemset(ctx->d_counters, 0, sizeof h))) return check_cuda(ctx, e, "rc_stats reset");

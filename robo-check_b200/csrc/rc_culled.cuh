@@ -38,6 +38,8 @@ struct CulledArgs {
     float sph_x, sph_y, sph_z, sph_r;
     float box_cx, box_cy, box_cz, box_ex, box_ey, box_ez;  // robot local AABB (centre, half extent)
     int probe_stride;                                      // probe vertices: lane * stride
+    long tail_begin;                                       // configurations left when chunks shrink to 1
+    int tail_thresh, leaf_thresh;                          // queue fill levels that trigger a round
 };
 
 __device__ __forceinline__ bool boxes_overlap(const Mat34 &m, const float4 r0, const float4 r1,
@@ -63,8 +65,8 @@ __device__ __forceinline__ bool boxes_overlap(const Mat34 &m, const float4 r0, c
     return !sep;
 }
 
-// Exhaustive sweep for one configuration (used when the pair stack overflows): lane = robot
-// triangle, obstacle triangles broadcast.  Returns true when a hitting pair exists.
+// Exhaustive sweep for one configuration, used only when the pair stack overflows (never
+// observed); kept small on purpose: lane = robot triangle, obstacle triangles broadcast.
 __device__ __noinline__ bool narrow_exhaustive(const Mat34 m, const float4 *s_rob_v,
                                                const uint2 *s_rob_t, int n_rob_t,
                                                const float4 *s_obs_a, const float4 *s_obs_b,
@@ -73,9 +75,7 @@ __device__ __noinline__ bool narrow_exhaustive(const Mat34 m, const float4 *s_ro
 {
     bool hit = false;
     for (int jb = 0; jb < n_rob_t && !hit; jb += 32) {
-        const int j = jb + lane;
-        const bool active = j < n_rob_t;
-        const uint2 ti = s_rob_t[active ? j : n_rob_t - 1];
+        const uint2 ti = s_rob_t[min(jb + lane, n_rob_t - 1)];
         const float4 A = s_rob_v[ti.x & 0xffffu], B = s_rob_v[ti.x >> 16], C = s_rob_v[ti.y];
         Tri r;
         xform(m, A.x, A.y, A.z, r.ax, r.ay, r.az);
@@ -86,7 +86,7 @@ __device__ __noinline__ bool narrow_exhaustive(const Mat34 m, const float4 *s_ro
             const float4 oa = s_obs_a[k], ob = s_obs_b[k], oc = s_obs_c[k];
             const Tri o = {oa.x, oa.y, oa.z, ob.x, ob.y, ob.z, oc.x, oc.y, oc.z};
             const Plane po = {oa.w, ob.w, oc.w, s_obs_d[k]};
-            if (active && pair_hits(r, pr, o, po)) hit = true;
+            if (pair_hits(r, pr, o, po)) hit = true;
         }
         hit = __any_sync(kFull, hit);
     }
@@ -137,14 +137,19 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
     uint32_t *leafq = stack + kStackCap;
     uint32_t *tailq = leafq + kLeafQCap;
     unsigned long long st_broad = 0, st_sphere = 0, st_valid = 0, st_invalid = 0, st_nodes = 0,
-                       st_leaves = 0, st_tris = 0, st_over = 0, st_tails = 0;
+                       st_leaves = 0, st_tris = 0, st_over = 0, st_tails = 0, st_nr = 0, st_lr = 0, st_tr = 0;
 
+    // Guided self-scheduling: chunks of c.chunk configurations while plenty of work is left,
+    // single configurations near the end so that no warp is left holding a long chunk.
+    long seen = 0;
     for (;;) {
+        const int take = (seen + a.tail_begin < c.n) ? c.chunk : 1;
         long base = 0;
-        if (lane == 0) base = (long)atomicAdd(c.counters + CNT_QUEUE, (unsigned long long)c.chunk);
+        if (lane == 0) base = (long)atomicAdd(c.queue, (unsigned long long)take);
         base = __shfl_sync(kFull, base, 0);
         if (base >= c.n) break;
-        const long end = min(base + (long)c.chunk, c.n);
+        seen = base;
+        const long end = min(base + (long)take, c.n);
         for (long i = base; i < end; i++) {
             const Mat34 m = load_matrix(c.confs, i);
 
@@ -221,7 +226,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
             if (lane == 0) stack[0] = 0u;  // (root, root)
             __syncwarp();
             while (sp > 0 || lq > 0 || tq > 0) {
-                if (tq >= 32 || (sp == 0 && lq == 0)) {
+                if (tq >= a.tail_thresh || (sp == 0 && lq == 0)) {
                     // ---- D: finish up to 32 queued pairs, one per lane
                     const int cnt = min(tq, 32);
                     tq -= cnt;
@@ -243,12 +248,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
                     const float dR0 = sdist(po, r.ax, r.ay, r.az), dR1 = sdist(po, r.bx, r.by, r.bz),
                                 dR2 = sdist(po, r.cx, r.cy, r.cz);
                     const bool h = act && pair_tail(r, pr, dR0, dR1, dR2, o, po, dO0, dO1, dO2);
-                    if (STATS) st_tails += cnt;
+                    if (STATS) { st_tails += cnt; st_tr++; }
                     if (__any_sync(kFull, h)) { hit = true; break; }
                     __syncwarp();
                     continue;
                 }
-                if (lq >= 8 || sp == 0) {
+                if (lq >= a.leaf_thresh || sp == 0) {
                     // ---- C: up to eight leaf pairs, lane = (slot, robot triangle of the leaf)
                     const int cnt = min(lq, 8);
                     lq -= cnt;
@@ -285,7 +290,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
                         if (pass) tailq[tq + __popc(mp & lt)] = (j << 16) | (uint32_t)k;
                         tq += __popc(mp);
                     }
-                    if (STATS) { st_leaves += cnt; st_tris += (act ? ocount : 0); }
+                    if (STATS) { st_leaves += cnt; st_tris += (act ? ocount : 0); st_lr++; }
                     __syncwarp();
                     continue;
                 }
@@ -301,7 +306,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
                 const uint32_t ra = __float_as_uint(r0.w), rb = __float_as_uint(r1.w);
                 const uint32_t oa = __float_as_uint(o0.w), ob = __float_as_uint(o1.w);
                 const bool la = (ra & 0x80000000u) != 0, lb = (oa & 0x80000000u) != 0;
-                if (STATS) st_nodes += cnt;
+                if (STATS) { st_nodes += cnt; st_nr++; }
                 __syncwarp();  // everybody has read its entry before the slots are reused
                 const bool ll = ov && la && lb;
                 const unsigned mll = __ballot_sync(kFull, ll);
@@ -352,6 +357,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
             atomicAdd(c.counters + CNT_TRI_PAIRS, st_tris);
             atomicAdd(c.counters + CNT_TAIL_PAIRS, st_tails);
             atomicAdd(c.counters + CNT_OVERFLOW, st_over);
+            atomicAdd(c.counters + CNT_NODE_ROUNDS, st_nr);
+            atomicAdd(c.counters + CNT_LEAF_ROUNDS, st_lr);
+            atomicAdd(c.counters + CNT_TAIL_ROUNDS, st_tr);
         }
     }
 }
@@ -367,7 +375,7 @@ static size_t culled_smem_bytes(const DeviceTables &t, int warps)
 
 cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, long n,
                                 uint8_t *d_valid, uint32_t *d_bitmask, int want_stats,
-                                cudaStream_t stream)
+                                cudaStream_t stream, unsigned long long *queue)
 {
     const DeviceTables &t = ctx->t;
     int warps = kCulledWarpsDefault;
@@ -383,7 +391,7 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
     a.c.n_rob_v_pad = t.n_rob_v_pad; a.c.n_rob_t = t.n_rob_t; a.c.n_obs_t = t.n_obs_t;
     a.c.obs_box = t.obs_box;
     a.c.confs = d_confs; a.c.n = n; a.c.valid = d_valid; a.c.bitmask = d_bitmask;
-    a.c.counters = ctx->d_counters;
+    a.c.counters = ctx->d_counters; a.c.queue = queue;
     a.rob_bvh = t.rob_bvh; a.obs_bvh = t.obs_bvh;
     a.n_rob_nodes = t.n_rob_nodes; a.n_obs_nodes = t.n_obs_nodes;
     a.sph_x = t.rob_center[0]; a.sph_y = t.rob_center[1]; a.sph_z = t.rob_center[2];
@@ -392,7 +400,13 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
     a.box_ex = t.rob_box_e[0]; a.box_ey = t.rob_box_e[1]; a.box_ez = t.rob_box_e[2];
     a.probe_stride = max(1, t.n_rob_v / 32);
     const int grid = ctx->sm_count;
-    a.c.chunk = (int)max(1L, min(16L, n / ((long)grid * warps * 8)));
+    // small chunks: the per-configuration cost varies 1:8 (cleared / full sweep / colliding)
+    a.c.chunk = (int)max(1L, min(16L, n / ((long)grid * warps * 32)));
+    a.tail_begin = (long)grid * warps * 4;
+    a.tail_thresh = 32; a.leaf_thresh = 8;
+    if (const char *env = getenv("RC_TAIL_THRESH")) a.tail_thresh = max(1, min(32, atoi(env)));
+    if (const char *env = getenv("RC_LEAF_THRESH")) a.leaf_thresh = max(1, min(8, atoi(env)));
+    if (const char *env = getenv("RC_CHUNK")) a.c.chunk = max(1, min(16, atoi(env)));
     void (*kern)(const CulledArgs) = nullptr;
     if (warps == 16) kern = want_stats ? check_culled_kernel<true, 16> : check_culled_kernel<false, 16>;
     else if (warps == 20) kern = want_stats ? check_culled_kernel<true, 20> : check_culled_kernel<false, 20>;

@@ -57,7 +57,9 @@ struct rc_ctx {
     rc_config *h_pinned_confs = nullptr;
     uint8_t *h_pinned_valid = nullptr;
     long stage_capacity = 0;
-    cudaStream_t own_stream = nullptr;
+    cudaStream_t own_stream = nullptr, own_stream2 = nullptr;
+    cudaEvent_t ev_join = nullptr;
+    unsigned long long *d_queues = nullptr;    // [kHostChunks] work-queue counters of rc_check_host
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_kernel_ms = 0.f;
     std::string last_error;
@@ -78,18 +80,24 @@ enum Counter {
     CNT_TAIL_PAIRS,
     CNT_OVERFLOW,
     CNT_LAUNCHES,
+    CNT_NODE_ROUNDS,
+    CNT_LEAF_ROUNDS,
+    CNT_TAIL_ROUNDS,
     RC_NUM_COUNTERS = 16
 };
+constexpr int kHostChunks = 8;
 
 int set_error(rc_ctx *ctx, int code, const std::string &msg);
 int check_cuda(rc_ctx *ctx, cudaError_t e, const char *what);
 
 // kernels.cu launchers (all asynchronous on `stream`)
+// `queue` = the work-queue counter of this launch (concurrent launches need distinct ones)
 cudaError_t launch_check(const rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_valid,
-                         uint32_t *d_bitmask, int mode, int want_stats, cudaStream_t stream);
+                         uint32_t *d_bitmask, int mode, int want_stats, cudaStream_t stream,
+                         unsigned long long *queue);
 cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, long n,
                                 uint8_t *d_valid, uint32_t *d_bitmask, int want_stats,
-                                cudaStream_t stream);
+                                cudaStream_t stream, unsigned long long *queue);
 cudaError_t launch_fma_peak(float *d_out, int grid, int iters, cudaStream_t stream);
 cudaError_t launch_transform_soa(const rc_ctx *ctx, const rc_config *d_confs, long n, float *d_x,
                                  float *d_y, float *d_z, rc_aabb *d_aabb, uint8_t *d_valid,

@@ -101,7 +101,8 @@ struct CheckArgs {
     long n;
     uint8_t *valid;
     uint32_t *bitmask;
-    unsigned long long *counters;
+    unsigned long long *counters;  // statistics
+    unsigned long long *queue;     // work-queue counter of this launch
     int chunk;
 };
 
@@ -111,6 +112,66 @@ __device__ __forceinline__ void publish(const CheckArgs &a, long i, bool valid, 
         if (a.valid) a.valid[i] = valid ? 1 : 0;
         if (a.bitmask && valid) atomicOr(a.bitmask + (i >> 5), 1u << (i & 31));
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// Exhaustive narrow phase of one configuration by one warp: every (robot triangle, obstacle
+// triangle) pair the reference decides (narrow-phase.cu:586-677).  A lane owns two robot
+// triangles per pass (j and j + 32), obstacle triangles are broadcast from shared memory with
+// 128-bit loads, so one pass costs 3 LDS for 64 first plane tests (18 flop each).  Lanes past
+// the end re-test the last triangle (a duplicate cannot change "some pair hits").  The later
+// stages run at most once per lane and triangle between two warp-wide flushes, so the rare path
+// executes with several lanes instead of one.  `load_tri(j)` yields the world-space triangle.
+template <class LoadTri>
+__device__ __forceinline__ bool exhaustive_sweep(LoadTri load_tri, int n_rob_t,
+                                                 const float4 *__restrict__ s_obs_a,
+                                                 const float4 *__restrict__ s_obs_b,
+                                                 const float4 *__restrict__ s_obs_c,
+                                                 const float *__restrict__ s_obs_d, int n_obs_t,
+                                                 int lane, unsigned long long &tails)
+{
+    bool hit = false;
+    for (int jb = 0; jb < n_rob_t && !hit; jb += 64) {
+        const Tri r0 = load_tri(min(jb + lane, n_rob_t - 1));
+        const Tri r1 = load_tri(min(jb + 32 + lane, n_rob_t - 1));
+        const Plane p0 = plane_of(r0), p1 = plane_of(r1);
+        int pend0 = -1, pend1 = -1;
+
+        auto finish = [&](const Tri &r, const Plane &pr, int k) {
+            const float4 oa = s_obs_a[k], ob = s_obs_b[k], oc = s_obs_c[k];
+            const Tri o = {oa.x, oa.y, oa.z, ob.x, ob.y, ob.z, oc.x, oc.y, oc.z};
+            const Plane po = {oa.w, ob.w, oc.w, s_obs_d[k]};
+            const float dR0 = sdist(po, r.ax, r.ay, r.az), dR1 = sdist(po, r.bx, r.by, r.bz),
+                        dR2 = sdist(po, r.cx, r.cy, r.cz);
+            if (straddles(dR0, dR1, dR2)) {
+                tails++;
+                const float dO0 = sdist(pr, o.ax, o.ay, o.az), dO1 = sdist(pr, o.bx, o.by, o.bz),
+                            dO2 = sdist(pr, o.cx, o.cy, o.cz);
+                if (pair_tail(r, pr, dR0, dR1, dR2, o, po, dO0, dO1, dO2)) hit = true;
+            }
+        };
+
+#pragma unroll 4
+        for (int k = 0; k < n_obs_t; k++) {
+            const float4 oa = s_obs_a[k], ob = s_obs_b[k], oc = s_obs_c[k];  // broadcast
+            const bool pass0 = straddles(sdist(p0, oa.x, oa.y, oa.z), sdist(p0, ob.x, ob.y, ob.z),
+                                         sdist(p0, oc.x, oc.y, oc.z));
+            const bool pass1 = straddles(sdist(p1, oa.x, oa.y, oa.z), sdist(p1, ob.x, ob.y, ob.z),
+                                         sdist(p1, oc.x, oc.y, oc.z));
+            if (__any_sync(kFull, (pass0 && pend0 >= 0) || (pass1 && pend1 >= 0))) {
+                if (pend0 >= 0) finish(r0, p0, pend0);
+                if (pend1 >= 0) finish(r1, p1, pend1);
+                pend0 = pend1 = -1;
+                if (__any_sync(kFull, hit)) break;
+            }
+            if (pass0) pend0 = k;
+            if (pass1) pend1 = k;
+        }
+        if (pend0 >= 0) finish(r0, p0, pend0);
+        if (pend1 >= 0) finish(r1, p1, pend1);
+        hit = __any_sync(kFull, hit);
+    }
+    return hit;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -154,7 +215,7 @@ __global__ void __launch_bounds__(kThreads, 2) check_brute_kernel(const CheckArg
 
     for (;;) {
         long base = 0;
-        if (lane == 0) base = (long)atomicAdd(a.counters + CNT_QUEUE, (unsigned long long)a.chunk);
+        if (lane == 0) base = (long)atomicAdd(a.queue, (unsigned long long)a.chunk);
         base = __shfl_sync(kFull, base, 0);
         if (base >= a.n) break;
         const long end = min(base + (long)a.chunk, a.n);
@@ -169,50 +230,17 @@ __global__ void __launch_bounds__(kThreads, 2) check_brute_kernel(const CheckArg
                 if (STATS) st_broad++;
                 continue;
             }
-            bool hit = false;
-            for (int jb = 0; jb < a.n_rob_t && !hit; jb += 32) {
-                const int j = jb + lane;
-                const bool active = j < a.n_rob_t;
-                const uint2 ti = s_rob_t[active ? j : a.n_rob_t - 1];
+            auto load_tri = [&](int j) {
+                const uint2 ti = s_rob_t[j];
                 const float4 A = s_rob_v[ti.x & 0xffffu], B = s_rob_v[ti.x >> 16], C = s_rob_v[ti.y];
                 Tri r;
                 xform(m, A.x, A.y, A.z, r.ax, r.ay, r.az);
                 xform(m, B.x, B.y, B.z, r.bx, r.by, r.bz);
                 xform(m, C.x, C.y, C.z, r.cx, r.cy, r.cz);
-                const Plane pr = plane_of(r);
-                int pend = -1;  // obstacle triangle that passed the first plane test, not yet finished
-
-                auto finish = [&](int k) {
-                    const float4 oa = s_obs_a[k], ob = s_obs_b[k], oc = s_obs_c[k];
-                    const Tri o = {oa.x, oa.y, oa.z, ob.x, ob.y, ob.z, oc.x, oc.y, oc.z};
-                    const Plane po = {oa.w, ob.w, oc.w, s_obs_d[k]};
-                    const float dR0 = sdist(po, r.ax, r.ay, r.az), dR1 = sdist(po, r.bx, r.by, r.bz),
-                                dR2 = sdist(po, r.cx, r.cy, r.cz);
-                    if (straddles(dR0, dR1, dR2)) {
-                        if (STATS) st_tail++;
-                        const float dO0 = sdist(pr, o.ax, o.ay, o.az), dO1 = sdist(pr, o.bx, o.by, o.bz),
-                                    dO2 = sdist(pr, o.cx, o.cy, o.cz);
-                        if (pair_tail(r, pr, dR0, dR1, dR2, o, po, dO0, dO1, dO2)) hit = true;
-                    }
-                };
-
-                for (int k = 0; k < a.n_obs_t; k++) {
-                    const float4 oa = s_obs_a[k], ob = s_obs_b[k], oc = s_obs_c[k];  // broadcast
-                    const float d0 = sdist(pr, oa.x, oa.y, oa.z), d1 = sdist(pr, ob.x, ob.y, ob.z),
-                                d2 = sdist(pr, oc.x, oc.y, oc.z);
-                    const bool pass = active && straddles(d0, d1, d2);
-                    // The rest of the test runs at most once per lane between two warp-wide
-                    // flushes, so the rare path executes with several lanes instead of one.
-                    if (__any_sync(kFull, pass && pend >= 0)) {
-                        if (pend >= 0) finish(pend);
-                        pend = -1;
-                        if (__any_sync(kFull, hit)) break;
-                    }
-                    if (pass) pend = k;
-                }
-                if (pend >= 0) finish(pend);
-                hit = __any_sync(kFull, hit);
-            }
+                return r;
+            };
+            const bool hit = exhaustive_sweep(load_tri, a.n_rob_t, s_obs_a, s_obs_b, s_obs_c, s_obs_d,
+                                              a.n_obs_t, lane, st_tail);
             publish(a, i, !hit, lane);
             if (STATS) { if (hit) st_invalid++; else st_valid++; }
         }
@@ -249,13 +277,14 @@ static size_t brute_smem_bytes(const DeviceTables &t)
 }
 
 cudaError_t launch_check(const rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_valid,
-                         uint32_t *d_bitmask, int mode, int want_stats, cudaStream_t stream)
+                         uint32_t *d_bitmask, int mode, int want_stats, cudaStream_t stream,
+                         unsigned long long *queue)
 {
+    if (!queue) queue = ctx->d_counters + CNT_QUEUE;
     const DeviceTables &t = ctx->t;
     cudaError_t e;
     if (n <= 0) return cudaSuccess;
-    if ((e = cudaMemsetAsync(ctx->d_counters + CNT_QUEUE, 0, sizeof(unsigned long long), stream)) !=
-        cudaSuccess)
+    if ((e = cudaMemsetAsync(queue, 0, sizeof(unsigned long long), stream)) != cudaSuccess)
         return e;
     if (d_bitmask &&
         (e = cudaMemsetAsync(d_bitmask, 0, (size_t)((n + 31) / 32) * 4, stream)) != cudaSuccess)
@@ -268,7 +297,7 @@ cudaError_t launch_check(const rc_ctx *ctx, const rc_config *d_confs, long n, ui
         a.n_rob_v_pad = t.n_rob_v_pad; a.n_rob_t = t.n_rob_t; a.n_obs_t = t.n_obs_t;
         a.obs_box = t.obs_box;
         a.confs = d_confs; a.n = n; a.valid = d_valid; a.bitmask = d_bitmask;
-        a.counters = ctx->d_counters;
+        a.counters = ctx->d_counters; a.queue = queue;
         const size_t smem = brute_smem_bytes(t);
         if (smem > (size_t)ctx->max_smem_optin) return cudaErrorInvalidConfiguration;
         const int ctas_per_sm = (2 * smem + 2048 <= (size_t)ctx->max_smem_optin) ? 2 : 1;
@@ -282,7 +311,7 @@ cudaError_t launch_check(const rc_ctx *ctx, const rc_config *d_confs, long n, ui
         kern<<<grid, kThreads, smem, stream>>>(a);
         return cudaGetLastError();
     }
-    return launch_check_culled(ctx, d_confs, n, d_valid, d_bitmask, want_stats, stream);
+    return launch_check_culled(ctx, d_confs, n, d_valid, d_bitmask, want_stats, stream, queue);
 }
 
 }  // namespace rc

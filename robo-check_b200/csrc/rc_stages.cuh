@@ -299,49 +299,21 @@ __global__ void __launch_bounds__(kThreads, 2) narrow_soa_kernel(const CheckArgs
     const int lane = threadIdx.x & 31;
     for (;;) {
         long i = 0;
-        if (lane == 0) i = (long)atomicAdd(a.counters + CNT_QUEUE, 1ull);
+        if (lane == 0) i = (long)atomicAdd(a.queue, 1ull);
         i = __shfl_sync(kFull, i, 0);
         if (i >= a.n) break;
         if (a.valid[i]) continue;
         const float *x = px + (size_t)i * n_rob_v, *y = py + (size_t)i * n_rob_v,
                     *z = pz + (size_t)i * n_rob_v;
-        bool hit = false;
-        for (int jb = 0; jb < a.n_rob_t && !hit; jb += 32) {
-            const int j = jb + lane;
-            const bool active = j < a.n_rob_t;
-            const uint2 ti = s_rob_t[active ? j : a.n_rob_t - 1];
+        auto load_tri = [&](int j) {
+            const uint2 ti = s_rob_t[j];
             const int va = ti.x & 0xffffu, vb = ti.x >> 16, vc = ti.y;
-            const Tri r = {__ldg(x + va), __ldg(y + va), __ldg(z + va), __ldg(x + vb), __ldg(y + vb),
-                           __ldg(z + vb), __ldg(x + vc), __ldg(y + vc), __ldg(z + vc)};
-            const Plane pr = plane_of(r);
-            int pend = -1;
-            auto finish = [&](int k) {
-                const float4 oa = s_obs_a[k], ob = s_obs_b[k], oc = s_obs_c[k];
-                const Tri o = {oa.x, oa.y, oa.z, ob.x, ob.y, ob.z, oc.x, oc.y, oc.z};
-                const Plane po = {oa.w, ob.w, oc.w, s_obs_d[k]};
-                const float dR0 = sdist(po, r.ax, r.ay, r.az), dR1 = sdist(po, r.bx, r.by, r.bz),
-                            dR2 = sdist(po, r.cx, r.cy, r.cz);
-                if (straddles(dR0, dR1, dR2)) {
-                    const float dO0 = sdist(pr, o.ax, o.ay, o.az), dO1 = sdist(pr, o.bx, o.by, o.bz),
-                                dO2 = sdist(pr, o.cx, o.cy, o.cz);
-                    if (pair_tail(r, pr, dR0, dR1, dR2, o, po, dO0, dO1, dO2)) hit = true;
-                }
-            };
-            for (int k = 0; k < a.n_obs_t; k++) {
-                const float4 oa = s_obs_a[k], ob = s_obs_b[k], oc = s_obs_c[k];
-                const float d0 = sdist(pr, oa.x, oa.y, oa.z), d1 = sdist(pr, ob.x, ob.y, ob.z),
-                            d2 = sdist(pr, oc.x, oc.y, oc.z);
-                const bool pass = active && straddles(d0, d1, d2);
-                if (__any_sync(kFull, pass && pend >= 0)) {
-                    if (pend >= 0) finish(pend);
-                    pend = -1;
-                    if (__any_sync(kFull, hit)) break;
-                }
-                if (pass) pend = k;
-            }
-            if (pend >= 0) finish(pend);
-            hit = __any_sync(kFull, hit);
-        }
+            return Tri{__ldg(x + va), __ldg(y + va), __ldg(z + va), __ldg(x + vb), __ldg(y + vb),
+                       __ldg(z + vb), __ldg(x + vc), __ldg(y + vc), __ldg(z + vc)};
+        };
+        unsigned long long tails = 0;
+        const bool hit = exhaustive_sweep(load_tri, a.n_rob_t, s_obs_a, s_obs_b, s_obs_c, s_obs_d,
+                                          a.n_obs_t, lane, tails);
         if (lane == 0) a.valid[i] = hit ? 0 : 1;
     }
 }
@@ -359,7 +331,7 @@ cudaError_t launch_narrow_soa(const rc_ctx *ctx, const float *d_x, const float *
     a.n_rob_v_pad = t.n_rob_v_pad; a.n_rob_t = t.n_rob_t; a.n_obs_t = t.n_obs_t;
     a.obs_box = t.obs_box;
     a.confs = nullptr; a.n = n; a.valid = d_valid; a.bitmask = nullptr;
-    a.counters = ctx->d_counters; a.chunk = 1;
+    a.counters = ctx->d_counters; a.queue = ctx->d_counters + CNT_QUEUE; a.chunk = 1;
     const size_t smem = 16 + (size_t)t.n_obs_t * 48 + (size_t)pad4(t.n_obs_t) * 4 +
                         (size_t)(t.n_rob_t + (t.n_rob_t & 1)) * 8;
     if (smem > (size_t)ctx->max_smem_optin) return cudaErrorInvalidConfiguration;

@@ -1,0 +1,59 @@
+"""N>1 path on real GPUs: two ranks (torchrun-style env, NCCL), configurations sharded, the kernel
+writes the bitmask words into its slot of the gather buffer, one all-gather.  Skipped with fewer
+than two GPUs (the CPU/gloo twin is tests/test_dist_gloo.py)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import robocheck_b200 as rc
+    from robocheck_b200 import sharding as sh
+    ctx = rc.Context(device=rank)
+    confs = np.concatenate([rc.createAlphaBotConfigurations(n // 2, True, 41),
+                            rc.createAlphaBotConfigurations(n - n // 2, False, 42)])
+
+    def check_local(shard, mask_words):
+        if len(shard):
+            d = torch.from_numpy(np.ascontiguousarray(shard)).cuda()
+            ctx.check(d, len(shard), None, mask_words, rc.RC_MODE_CULLED, torch.cuda.current_stream())
+
+    flags = sh.check_sharded(check_local, confs, dist, device=torch.device("cuda", rank))
+    single = ctx.check_host(confs)
+    if rank == 0:
+        q.put(bool(np.array_equal(flags, single)) and len(flags) == n)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_sharded_check():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 50001, q)) for r in range(2)]
+    [p.start() for p in procs]
+    ok = q.get(timeout=300)
+    [p.join(timeout=60) for p in procs]
+    assert ok and all(p.exitcode == 0 for p in procs)
