@@ -241,6 +241,15 @@ int rc_create(rc_ctx **out, const float *rob_x, const float *rob_y, const float 
         const Bvh rb = build_bvh(rob_x, rob_y, rob_z, rob_v1, rob_v2, rob_v3, n_rob_t, kBoxMargin);
         const Bvh ob = build_bvh(obs_x, obs_y, obs_z, obs_v1, obs_v2, obs_v3, n_obs_t, kBoxMargin);
         t.n_rob_nodes = rb.n_nodes; t.n_obs_nodes = ob.n_nodes;
+        for (int d = 0; d < 4; d++) {
+            const std::vector<int> cr = rb.cut(d), co = ob.cut(d);
+            t.n_seed_r[d] = (int)std::min<size_t>(cr.size(), 8);
+            t.n_seed_o[d] = (int)std::min<size_t>(co.size(), 8);
+            for (int q = 0; q < 8; q++) {
+                t.seed_r[d][q] = (uint32_t)(q < (int)cr.size() ? cr[q] : 0);
+                t.seed_o[d][q] = (uint32_t)(q < (int)co.size() ? co[q] : 0);
+            }
+        }
         std::vector<uint2> rts((size_t)n_rob_t);
         for (int p = 0; p < n_rob_t; p++) rts[p] = rt[rb.order[p]];
         std::vector<float4> rbn((size_t)rb.n_nodes * 2), obn((size_t)ob.n_nodes * 2);

@@ -28,7 +28,7 @@ constexpr int kCulledWarpsDefault = 24;  // warps per CTA (one CTA per SM); 16/2
 constexpr int kStackCap = 1024;  // node pairs per warp; overflow falls back to the exhaustive sweep
 constexpr int kLeafQCap = 64;
 constexpr int kTailQCap = 160;   // pairs that passed both plane tests, finished 32 at a time
-constexpr int kWarpWork = kStackCap + kLeafQCap + kTailQCap;
+constexpr int kStackCapGlobal = 1536;  // obstacle tables in global memory: deeper trees
 constexpr int kLeafTrisDev = 4;  // must match rc::kLeafTris of the host builder (rc_bvh.h)
 
 struct CulledArgs {
@@ -39,6 +39,8 @@ struct CulledArgs {
     float box_cx, box_cy, box_cz, box_ex, box_ey, box_ez;  // robot local AABB (centre, half extent)
     int probe_stride;                                      // probe vertices: lane * stride
     long tail_begin;                                       // configurations left when chunks shrink to 1
+    uint32_t seed_r[8], seed_o[8];                   // traversal starts from this cut of both trees
+    int n_seed_r, n_seed_o;
     int tail_thresh, leaf_thresh;                          // queue fill levels that trigger a round
 };
 
@@ -93,21 +95,37 @@ __device__ __noinline__ bool narrow_exhaustive(const Mat34 m, const float4 *s_ro
     return hit;
 }
 
-template <bool STATS, int WARPS>
+// GOBS = obstacle tables (BVH + triangles) stay in global memory (L2-resident) instead of being
+// staged into shared memory: meshes of any size (BASELINE config 5, the subdivided obstacle).
+// Pair encodings then use 11 bits for the robot side and 21 bits for the obstacle side.
+template <bool STATS, int WARPS, bool GOBS>
 __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const CulledArgs a)
 {
+    constexpr int SH = GOBS ? 21 : 16;
+    constexpr uint32_t LOW = (1u << SH) - 1u;
+    constexpr int kStack = GOBS ? kStackCapGlobal : kStackCap;
+    constexpr int kWarpWork = kStack + kLeafQCap + kTailQCap;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const CheckArgs &c = a.c;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
     float4 *s_rob_v = reinterpret_cast<float4 *>(smem_raw + 16);
     float4 *s_rob_bvh = s_rob_v + c.n_rob_v_pad;
     float4 *s_obs_bvh = s_rob_bvh + 2 * a.n_rob_nodes;
-    float4 *s_obs_a = s_obs_bvh + 2 * a.n_obs_nodes;
-    float4 *s_obs_b = s_obs_a + c.n_obs_t;
-    float4 *s_obs_c = s_obs_b + c.n_obs_t;
-    float *s_obs_d = reinterpret_cast<float *>(s_obs_c + c.n_obs_t);
-    uint2 *s_rob_t = reinterpret_cast<uint2 *>(s_obs_d + pad4(c.n_obs_t));
+    float4 *s_obs_a = s_obs_bvh + (GOBS ? 0 : 2 * a.n_obs_nodes);
+    float4 *s_obs_b = s_obs_a + (GOBS ? 0 : c.n_obs_t);
+    float4 *s_obs_c = s_obs_b + (GOBS ? 0 : c.n_obs_t);
+    float *s_obs_d = reinterpret_cast<float *>(s_obs_c + (GOBS ? 0 : c.n_obs_t));
+    uint2 *s_rob_t = reinterpret_cast<uint2 *>(s_obs_d + (GOBS ? 0 : pad4(c.n_obs_t)));
     uint32_t *s_work = reinterpret_cast<uint32_t *>(s_rob_t + c.n_rob_t + (c.n_rob_t & 1));
+    // obstacle accessors: shared memory, or the read-only global path
+    auto obs_node = [&](int nb, int half) -> float4 {
+        if constexpr (GOBS) return __ldg(a.obs_bvh + 2 * nb + half);
+        else return s_obs_bvh[2 * nb + half];
+    };
+    auto obs_A = [&](int k) -> float4 { if constexpr (GOBS) return __ldg(c.obs_a + k); else return s_obs_a[k]; };
+    auto obs_B = [&](int k) -> float4 { if constexpr (GOBS) return __ldg(c.obs_b + k); else return s_obs_b[k]; };
+    auto obs_C = [&](int k) -> float4 { if constexpr (GOBS) return __ldg(c.obs_c + k); else return s_obs_c[k]; };
+    auto obs_D = [&](int k) -> float { if constexpr (GOBS) return __ldg(c.obs_d + k); else return s_obs_d[k]; };
 
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
@@ -119,22 +137,24 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
                        bt = (c.n_rob_t + (c.n_rob_t & 1)) * 8u;
         const uint32_t brn = a.n_rob_nodes * 32u, bon = a.n_obs_nodes * 32u;
         const uint32_t bd = pad4(c.n_obs_t) * 4u;
-        mbar_expect_tx(bar, bv + 3u * bo + bd + bt + brn + bon);
+        mbar_expect_tx(bar, bv + bt + brn + (GOBS ? 0u : 3u * bo + bd + bon));
         tma_load_1d(s_rob_v, c.rob_v, bv, bar);
         tma_load_1d(s_rob_bvh, a.rob_bvh, brn, bar);
-        tma_load_1d(s_obs_bvh, a.obs_bvh, bon, bar);
-        tma_load_1d(s_obs_a, c.obs_a, bo, bar);
-        tma_load_1d(s_obs_b, c.obs_b, bo, bar);
-        tma_load_1d(s_obs_c, c.obs_c, bo, bar);
-        tma_load_1d(s_obs_d, c.obs_d, bd, bar);
         tma_load_1d(s_rob_t, c.rob_t, bt, bar);
+        if (!GOBS) {
+            tma_load_1d(s_obs_bvh, a.obs_bvh, bon, bar);
+            tma_load_1d(s_obs_a, c.obs_a, bo, bar);
+            tma_load_1d(s_obs_b, c.obs_b, bo, bar);
+            tma_load_1d(s_obs_c, c.obs_c, bo, bar);
+            tma_load_1d(s_obs_d, c.obs_d, bd, bar);
+        }
     }
     mbar_wait(bar, 0);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
     uint32_t *stack = s_work + warp * kWarpWork;
-    uint32_t *leafq = stack + kStackCap;
+    uint32_t *leafq = stack + kStack;
     uint32_t *tailq = leafq + kLeafQCap;
     unsigned long long st_broad = 0, st_sphere = 0, st_valid = 0, st_invalid = 0, st_nodes = 0,
                        st_leaves = 0, st_tris = 0, st_over = 0, st_tails = 0, st_nr = 0, st_lr = 0, st_tr = 0;
@@ -221,9 +241,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
             }
 
             // B + C + D
-            int sp = 1, lq = 0, tq = 0;
+            // the descent starts from a cut through both trees instead of (root, root): the top
+            // levels almost always overlap here and would cost steps with a handful of lanes
+            int sp = a.n_seed_r * a.n_seed_o, lq = 0, tq = 0;
             bool hit = false, overflow = false;
-            if (lane == 0) stack[0] = 0u;  // (root, root)
+            for (int q = lane; q < sp; q += 32)
+                stack[q] = (a.seed_r[q / a.n_seed_o] << SH) | a.seed_o[q % a.n_seed_o];
             __syncwarp();
             while (sp > 0 || lq > 0 || tq > 0) {
                 if (tq >= a.tail_thresh || (sp == 0 && lq == 0)) {
@@ -232,17 +255,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
                     tq -= cnt;
                     const bool act = lane < cnt;
                     const uint32_t e = tailq[tq + (act ? lane : 0)];
-                    const uint2 ti = s_rob_t[e >> 16];
-                    const int k = e & 0xffffu;
+                    const uint2 ti = s_rob_t[e >> SH];
+                    const int k = (int)(e & LOW);
                     const float4 A = s_rob_v[ti.x & 0xffffu], B = s_rob_v[ti.x >> 16], C = s_rob_v[ti.y];
                     Tri r;
                     xform(m, A.x, A.y, A.z, r.ax, r.ay, r.az);
                     xform(m, B.x, B.y, B.z, r.bx, r.by, r.bz);
                     xform(m, C.x, C.y, C.z, r.cx, r.cy, r.cz);
                     const Plane pr = plane_of(r);
-                    const float4 oa = s_obs_a[k], ob = s_obs_b[k], oc = s_obs_c[k];
+                    const float4 oa = obs_A(k), ob = obs_B(k), oc = obs_C(k);
                     const Tri o = {oa.x, oa.y, oa.z, ob.x, ob.y, ob.z, oc.x, oc.y, oc.z};
-                    const Plane po = {oa.w, ob.w, oc.w, s_obs_d[k]};
+                    const Plane po = {oa.w, ob.w, oc.w, obs_D(k)};
                     const float dO0 = sdist(pr, o.ax, o.ay, o.az), dO1 = sdist(pr, o.bx, o.by, o.bz),
                                 dO2 = sdist(pr, o.cx, o.cy, o.cz);
                     const float dR0 = sdist(po, r.ax, r.ay, r.az), dR1 = sdist(po, r.bx, r.by, r.bz),
@@ -260,11 +283,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
                     const int slot = lane >> 2, ri = lane & 3;
                     bool act = slot < cnt;
                     const uint32_t e = leafq[lq + (act ? slot : 0)];
-                    const int na = e >> 16, nb = e & 0xffffu;
+                    const int na = (int)(e >> SH), nb = (int)(e & LOW);
                     const uint32_t rfirst = __float_as_uint(s_rob_bvh[2 * na].w) & 0x7fffffffu;
                     const int rcount = (int)__float_as_uint(s_rob_bvh[2 * na + 1].w);
-                    const uint32_t ofirst = __float_as_uint(s_obs_bvh[2 * nb].w) & 0x7fffffffu;
-                    const int ocount = (int)__float_as_uint(s_obs_bvh[2 * nb + 1].w);
+                    const uint32_t ofirst = __float_as_uint(obs_node(nb, 0).w) & 0x7fffffffu;
+                    const int ocount = (int)__float_as_uint(obs_node(nb, 1).w);
                     act = act && ri < rcount;
                     const uint32_t j = rfirst + (act ? ri : 0);
                     const uint2 ti = s_rob_t[j];
@@ -277,17 +300,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
 #pragma unroll
                     for (int q = 0; q < kLeafTrisDev; q++) {
                         const int k = ofirst + min(q, ocount - 1);
-                        const float4 oa = s_obs_a[k], ob = s_obs_b[k], oc = s_obs_c[k];
+                        const float4 oa = obs_A(k), ob = obs_B(k), oc = obs_C(k);
                         bool pass = act && q < ocount &&
                                     straddles(sdist(pr, oa.x, oa.y, oa.z), sdist(pr, ob.x, ob.y, ob.z),
                                               sdist(pr, oc.x, oc.y, oc.z));
                         if (pass) {
-                            const Plane po = {oa.w, ob.w, oc.w, s_obs_d[k]};
+                            const Plane po = {oa.w, ob.w, oc.w, obs_D(k)};
                             pass = straddles(sdist(po, r.ax, r.ay, r.az), sdist(po, r.bx, r.by, r.bz),
                                              sdist(po, r.cx, r.cy, r.cz));
                         }
                         const unsigned mp = __ballot_sync(kFull, pass);
-                        if (pass) tailq[tq + __popc(mp & lt)] = (j << 16) | (uint32_t)k;
+                        if (pass) tailq[tq + __popc(mp & lt)] = (j << SH) | (uint32_t)k;
                         tq += __popc(mp);
                     }
                     if (STATS) { st_leaves += cnt; st_tris += (act ? ocount : 0); st_lr++; }
@@ -299,9 +322,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
                 sp -= cnt;
                 const bool act = lane < cnt;
                 const uint32_t e = stack[sp + (act ? lane : 0)];
-                const int na = e >> 16, nb = e & 0xffffu;
+                const int na = (int)(e >> SH), nb = (int)(e & LOW);
                 const float4 r0 = s_rob_bvh[2 * na], r1 = s_rob_bvh[2 * na + 1];
-                const float4 o0 = s_obs_bvh[2 * nb], o1 = s_obs_bvh[2 * nb + 1];
+                const float4 o0 = obs_node(nb, 0), o1 = obs_node(nb, 1);
                 const bool ov = act && boxes_overlap(m, r0, r1, o0, o1);
                 const uint32_t ra = __float_as_uint(r0.w), rb = __float_as_uint(r1.w);
                 const uint32_t oa = __float_as_uint(o0.w), ob = __float_as_uint(o1.w);
@@ -315,29 +338,33 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
                 const bool two = ov && (la != lb), four = ov && !la && !lb;
                 const unsigned m2 = __ballot_sync(kFull, two), m4 = __ballot_sync(kFull, four);
                 const int total = 2 * __popc(m2) + 4 * __popc(m4);
-                if (sp + total > kStackCap) { overflow = true; break; }
+                if (sp + total > kStack) { overflow = true; break; }
                 const int off = sp + 2 * __popc(m2 & lt) + 4 * __popc(m4 & lt);
                 if (two) {
                     if (la) {  // robot node is a leaf: descend the obstacle node
-                        stack[off] = ((uint32_t)na << 16) | oa;
-                        stack[off + 1] = ((uint32_t)na << 16) | ob;
+                        stack[off] = ((uint32_t)na << SH) | oa;
+                        stack[off + 1] = ((uint32_t)na << SH) | ob;
                     } else {
-                        stack[off] = (ra << 16) | (uint32_t)nb;
-                        stack[off + 1] = (rb << 16) | (uint32_t)nb;
+                        stack[off] = (ra << SH) | (uint32_t)nb;
+                        stack[off + 1] = (rb << SH) | (uint32_t)nb;
                     }
                 } else if (four) {
-                    stack[off] = (ra << 16) | oa;
-                    stack[off + 1] = (ra << 16) | ob;
-                    stack[off + 2] = (rb << 16) | oa;
-                    stack[off + 3] = (rb << 16) | ob;
+                    stack[off] = (ra << SH) | oa;
+                    stack[off + 1] = (ra << SH) | ob;
+                    stack[off + 2] = (rb << SH) | oa;
+                    stack[off + 3] = (rb << SH) | ob;
                 }
                 sp += total;
                 __syncwarp();
             }
             if (overflow) {
                 if (STATS) st_over++;
-                hit = narrow_exhaustive(m, s_rob_v, s_rob_t, c.n_rob_t, s_obs_a, s_obs_b, s_obs_c,
-                                        s_obs_d, c.n_obs_t, lane);
+                if constexpr (GOBS)
+                    hit = narrow_exhaustive(m, s_rob_v, s_rob_t, c.n_rob_t, c.obs_a, c.obs_b, c.obs_c,
+                                            c.obs_d, c.n_obs_t, lane);
+                else
+                    hit = narrow_exhaustive(m, s_rob_v, s_rob_t, c.n_rob_t, s_obs_a, s_obs_b, s_obs_c,
+                                            s_obs_d, c.n_obs_t, lane);
             }
             __syncwarp();
             publish(c, i, !hit, lane);
@@ -364,13 +391,22 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
     }
 }
 
-static size_t culled_smem_bytes(const DeviceTables &t, int warps)
+static size_t culled_smem_bytes(const DeviceTables &t, int warps, bool gobs)
 {
     size_t b = 16 + (size_t)t.n_rob_v_pad * 16 + (size_t)t.n_rob_nodes * 32 +
-               (size_t)t.n_obs_nodes * 32 + (size_t)t.n_obs_t * 48 + (size_t)pad4(t.n_obs_t) * 4 +
                (size_t)(t.n_rob_t + (t.n_rob_t & 1)) * 8;
-    b += (size_t)warps * kWarpWork * 4;
+    if (!gobs)
+        b += (size_t)t.n_obs_nodes * 32 + (size_t)t.n_obs_t * 48 + (size_t)pad4(t.n_obs_t) * 4;
+    b += (size_t)warps * ((gobs ? kStackCapGlobal : kStackCap) + kLeafQCap + kTailQCap) * 4;
     return b;
+}
+
+template <bool GOBS>
+static void (*pick_culled(int warps, int want_stats))(const CulledArgs)
+{
+    if (warps == 16) return want_stats ? check_culled_kernel<true, 16, GOBS> : check_culled_kernel<false, 16, GOBS>;
+    if (warps == 20) return want_stats ? check_culled_kernel<true, 20, GOBS> : check_culled_kernel<false, 20, GOBS>;
+    return want_stats ? check_culled_kernel<true, 24, GOBS> : check_culled_kernel<false, 24, GOBS>;
 }
 
 cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, long n,
@@ -381,9 +417,18 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
     int warps = kCulledWarpsDefault;
     if (const char *env = getenv("RC_CULLED_WARPS")) warps = atoi(env);  // tuning knob
     if (warps != 16 && warps != 20 && warps != 24) warps = kCulledWarpsDefault;
-    // fewer warps per CTA when the tables leave less room for the per-warp work areas
-    while (warps > 16 && culled_smem_bytes(t, warps) > (size_t)ctx->max_smem_optin) warps -= 4;
-    const size_t smem = culled_smem_bytes(t, warps);
+    // Obstacle tables go to shared memory when everything fits with at least 16 warps per CTA;
+    // otherwise they stay in global memory (any obstacle size, robot tables must still fit).
+    bool gobs = getenv("RC_FORCE_GLOBAL_OBSTACLE") != nullptr;
+    if (!gobs && (culled_smem_bytes(t, 16, false) > (size_t)ctx->max_smem_optin ||
+                  t.n_obs_nodes > 65535 || t.n_rob_nodes > 65535))
+        gobs = true;
+    while (warps > 16 && culled_smem_bytes(t, warps, gobs) > (size_t)ctx->max_smem_optin) warps -= 4;
+    const size_t smem = culled_smem_bytes(t, warps, gobs);
+    if (smem > (size_t)ctx->max_smem_optin || t.n_rob_v > 65535) return cudaErrorInvalidConfiguration;
+    if (gobs && (t.n_rob_nodes >= (1 << 11) || t.n_rob_t >= (1 << 11) || t.n_obs_nodes >= (1 << 21) ||
+                 t.n_obs_t >= (1 << 21)))
+        return cudaErrorInvalidConfiguration;
     CulledArgs a;
     a.c.rob_v = t.rob_v; a.c.rob_t = t.rob_t_sorted;
     a.c.obs_a = t.obs_a_sorted; a.c.obs_b = t.obs_b_sorted; a.c.obs_c = t.obs_c_sorted;
@@ -404,13 +449,14 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
     a.c.chunk = (int)max(1L, min(16L, n / ((long)grid * warps * 32)));
     a.tail_begin = (long)grid * warps * 4;
     a.tail_thresh = 32; a.leaf_thresh = 8;
+    int sd = 2;
+    if (const char *env = getenv("RC_SEED_DEPTH")) sd = max(0, min(3, atoi(env)));
+    a.n_seed_r = t.n_seed_r[sd]; a.n_seed_o = t.n_seed_o[sd];
+    for (int q = 0; q < 8; q++) { a.seed_r[q] = t.seed_r[sd][q]; a.seed_o[q] = t.seed_o[sd][q]; }
     if (const char *env = getenv("RC_TAIL_THRESH")) a.tail_thresh = max(1, min(32, atoi(env)));
     if (const char *env = getenv("RC_LEAF_THRESH")) a.leaf_thresh = max(1, min(8, atoi(env)));
     if (const char *env = getenv("RC_CHUNK")) a.c.chunk = max(1, min(16, atoi(env)));
-    void (*kern)(const CulledArgs) = nullptr;
-    if (warps == 16) kern = want_stats ? check_culled_kernel<true, 16> : check_culled_kernel<false, 16>;
-    else if (warps == 20) kern = want_stats ? check_culled_kernel<true, 20> : check_culled_kernel<false, 20>;
-    else kern = want_stats ? check_culled_kernel<true, 24> : check_culled_kernel<false, 24>;
+    void (*kern)(const CulledArgs) = gobs ? pick_culled<true>(warps, want_stats) : pick_culled<false>(warps, want_stats);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, warps * 32, smem, stream>>>(a);

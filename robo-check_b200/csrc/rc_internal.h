@@ -34,7 +34,10 @@ struct DeviceTables {
     rc_aabb obs_box;
     float rob_center[3];        // bounding sphere of the robot in its local frame
     float rob_radius;
-    float rob_box_c[3], rob_box_e[3];  // robot local AABB: centre and half extent (rounded up)
+    float rob_box_c[3], rob_box_e[3];
+    // traversal seeds: node cuts at depth 0..3 of both trees (<= 8 nodes each)
+    uint32_t seed_r[4][8], seed_o[4][8];
+    int n_seed_r[4], n_seed_o[4];  // robot local AABB: centre and half extent (rounded up)
 };
 
 }  // namespace rc

@@ -5,6 +5,7 @@
 #include <cfloat>
 #include <cstring>
 #include <numeric>
+#include <utility>
 
 namespace rc {
 namespace {
@@ -76,6 +77,27 @@ struct Builder {
 };
 
 }  // namespace
+
+std::vector<int> Bvh::cut(int d) const
+{
+    std::vector<int> out;
+    if (n_nodes == 0) return out;
+    std::vector<std::pair<int, int>> todo{{0, 0}};
+    while (!todo.empty()) {
+        const auto [node, depth_now] = todo.back();
+        todo.pop_back();
+        uint32_t l0, l1;
+        std::memcpy(&l0, &nodes[(size_t)node * 8 + 3], 4);
+        std::memcpy(&l1, &nodes[(size_t)node * 8 + 7], 4);
+        if ((l0 & kLeafFlag) || depth_now == d) {
+            out.push_back(node);
+        } else {
+            todo.push_back({(int)l1, depth_now + 1});
+            todo.push_back({(int)l0, depth_now + 1});
+        }
+    }
+    return out;
+}
 
 Bvh build_bvh(const float *x, const float *y, const float *z, const int *v1, const int *v2,
               const int *v3, int n_t, float margin)

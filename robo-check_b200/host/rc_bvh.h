@@ -19,6 +19,8 @@ struct Bvh {
     std::vector<int> order;            // order[p] = original triangle index at leaf position p
     int n_nodes = 0;
     int depth = 0;
+    // nodes at depth `d` (plus leaves above it): a cut through the tree, used to seed traversals
+    std::vector<int> cut(int d) const;
 };
 
 Bvh build_bvh(const float *x, const float *y, const float *z, const int *v1, const int *v2,

@@ -231,3 +231,37 @@ def test_vertices_match_reference_gpu_kernel(rc, ctx, po, omeshes):
     assert np.array_equal(ox.view(np.uint32), rx.view(np.uint32))
     assert np.array_equal(oy.view(np.uint32), ry.view(np.uint32))
     assert np.array_equal(oz.view(np.uint32), rz.view(np.uint32))
+
+
+# ---- obstacle tables in global memory (meshes that do not fit in shared memory) ----------------
+def test_global_obstacle_mode_same_flags(rc, meshes, mixed_confs, mixed_oracle, monkeypatch):
+    """The same alpha1.0 check with the obstacle BVH/triangles read from global memory."""
+    monkeypatch.setenv("RC_FORCE_GLOBAL_OBSTACLE", "1")
+    c = rc.Context(meshes[0], meshes[1], device=0)
+    try:
+        got, bits = run_check(c, mixed_confs, rc.RC_MODE_CULLED, bitmask=True)
+    finally:
+        c.close()
+    assert np.array_equal(got, mixed_oracle) and np.array_equal(bits, mixed_oracle)
+
+
+@pytest.mark.parametrize("levels,n", [(1, 400), (2, 160)])
+def test_subdivided_obstacle_matches_oracle(rc, po, meshes, levels, n):
+    """BASELINE config 5 in small: robot vs the midpoint-subdivided obstacle (4,032 / 16,128
+    triangles).  The reference cannot run this (its meshes live in 64 KB of __constant__ memory),
+    so the checker is the CPU oracle, which takes any mesh size."""
+    rob, obs = meshes[0], meshes[1].subdivide(levels)
+    assert obs.n_t == 1008 * 4 ** levels
+    confs = rc.createAlphaBotConfigurations(n, True, 700 + levels)
+    want = po.check(po.OracleMesh(*rob.arrays()), po.OracleMesh(*obs.arrays()), confs, po.VARIANT_GPU)
+    c = rc.Context(rob, obs, device=0)
+    try:
+        got = run_check(c, confs, rc.RC_MODE_CULLED)
+        c.stats_enable(True)
+        c.stats(reset=True)
+        run_check(c, confs, rc.RC_MODE_CULLED)
+        assert c.stats()["overflow"] == 0
+    finally:
+        c.close()
+    assert np.array_equal(got, want)
+    assert 0 < int(want.sum()) < n
