@@ -16,7 +16,7 @@
 
 namespace rc {
 
-constexpr int kWarpsPerCta = 8;
+constexpr int kWarpsPerCta = 12;  // x 2 CTAs per SM = 24 warps (<= 85 registers)
 constexpr int kThreads = kWarpsPerCta * 32;
 constexpr unsigned kFull = 0xffffffffu;
 __host__ __device__ constexpr int pad4(int n) { return (n + 3) & ~3; }

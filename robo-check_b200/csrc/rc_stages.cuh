@@ -105,34 +105,60 @@ cudaError_t launch_transform_soa(const rc_ctx *ctx, const rc_config *d_confs, lo
 
 // ---- genTransformedCopies (transformation/transform.cu:65-97) ------------------------------
 // AoS output [conf][vertex] of 12-byte records.  The reference writes it with a stride of a
-// whole configuration between lanes; here a warp transposes 32 vertices through shared memory
-// and writes 3 x 128 contiguous bytes.
+// whole configuration between lanes.  Here a warp transforms 128 vertices per step (4 per lane),
+// interleaves x/y/z through a 1.5 KB shared tile and writes the 1,536 contiguous bytes with
+// 128-bit stores; rows are 16-byte aligned when n_v % 4 == 0, otherwise the scalar tail path runs.
 __global__ void __launch_bounds__(kStageThreads) transform_aos_kernel(
     const rc_vec3 *__restrict__ base, int n_v, const rc_config *__restrict__ confs, long n,
     rc_vec3 *__restrict__ out)
 {
-    __shared__ float tile[kStageWarps][96];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int n_v_pad = (n_v + 127) / 128 * 128;
+    float *sx = reinterpret_cast<float *>(smem_raw);
+    float *sy = sx + n_v_pad;
+    float *sz = sy + n_v_pad;
+    float *tiles = sz + n_v_pad;  // [kStageWarps][384]
+    for (int v = threadIdx.x; v < n_v_pad; v += blockDim.x) {
+        const int sv = v < n_v ? v : 0;
+        sx[v] = base[sv].x; sy[v] = base[sv].y; sz[v] = base[sv].z;
+    }
+    __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float *tile = tiles + w * 384;
     const long warp = (long)blockIdx.x * kStageWarps + w;
     const long n_warps = (long)gridDim.x * kStageWarps;
-    const float *bf = reinterpret_cast<const float *>(base);
     float *of = reinterpret_cast<float *>(out);
+    const bool vec = (n_v % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     for (long i = warp; i < n; i += n_warps) {
         const Mat34 m = load_matrix(confs, i);
-        for (int v0 = 0; v0 < n_v; v0 += 32) {
-            const int cnt = min(32, n_v - v0);
-            // coalesced read of 3*cnt floats, transposed through the tile
-            for (int e = lane; e < 3 * cnt; e += 32) tile[w][e] = __ldg(bf + 3 * (size_t)v0 + e);
+        float *row = of + 3 * (size_t)i * n_v;
+        for (int v0 = 0; v0 < n_v; v0 += 128) {
+            const int v = v0 + 4 * lane;
+            const float4 X = *reinterpret_cast<const float4 *>(sx + v);
+            const float4 Y = *reinterpret_cast<const float4 *>(sy + v);
+            const float4 Z = *reinterpret_cast<const float4 *>(sz + v);
+            float o[12];
+            xform(m, X.x, Y.x, Z.x, o[0], o[1], o[2]);
+            xform(m, X.y, Y.y, Z.y, o[3], o[4], o[5]);
+            xform(m, X.z, Y.z, Z.z, o[6], o[7], o[8]);
+            xform(m, X.w, Y.w, Z.w, o[9], o[10], o[11]);
+            // lane l owns floats [12 l, 12 l + 12) of the 384-float tile
+            float4 *tl = reinterpret_cast<float4 *>(tile + 12 * lane);
+            tl[0] = make_float4(o[0], o[1], o[2], o[3]);
+            tl[1] = make_float4(o[4], o[5], o[6], o[7]);
+            tl[2] = make_float4(o[8], o[9], o[10], o[11]);
             __syncwarp();
-            float x = 0.f, y = 0.f, z = 0.f;
-            if (lane < cnt) xform(m, tile[w][3 * lane], tile[w][3 * lane + 1], tile[w][3 * lane + 2], x, y, z);
-            __syncwarp();
-            if (lane < cnt) {
-                tile[w][3 * lane] = x; tile[w][3 * lane + 1] = y; tile[w][3 * lane + 2] = z;
+            const int cnt = 3 * min(128, n_v - v0);  // floats of this step
+            float *dst = row + 3 * (size_t)v0;
+            if (vec) {
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    const int f = 4 * (lane + 32 * q);
+                    if (f < cnt) __stcs(reinterpret_cast<float4 *>(dst + f), *reinterpret_cast<const float4 *>(tile + f));
+                }
+            } else {
+                for (int f = lane; f < cnt; f += 32) dst[f] = tile[f];
             }
-            __syncwarp();
-            float *dst = of + 3 * ((size_t)i * n_v + v0);
-            for (int e = lane; e < 3 * cnt; e += 32) dst[e] = tile[w][e];
             __syncwarp();
         }
     }
@@ -144,13 +170,21 @@ cudaError_t launch_transform_aos(const rc_ctx *ctx, const rc_config *d_confs, lo
     if (n <= 0 || n_v <= 0) return cudaSuccess;
     const long want = (n + kStageWarps - 1) / kStageWarps;
     const int grid = (int)min(want, (long)ctx->sm_count * 8);
-    transform_aos_kernel<<<grid, kStageThreads, 0, stream>>>(d_base, n_v, d_confs, n, d_out);
+    const size_t smem = (size_t)((n_v + 127) / 128 * 128) * 12 + (size_t)kStageWarps * 384 * 4;
+    if (smem > (size_t)ctx->max_smem_optin) return cudaErrorInvalidConfiguration;
+    cudaError_t e = cudaFuncSetAttribute(transform_aos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return e;
+    transform_aos_kernel<<<grid, kStageThreads, smem, stream>>>(d_base, n_v, d_confs, n, d_out);
     return cudaGetLastError();
 }
 
 // ---- generateAABBPrimitiveKernel (generate-AABB.cu:7-35) ----------------------------------
-// min/max per configuration over AoS vertices; one warp per configuration reads the 3*n_v floats
-// of the row contiguously, each lane keeping the running min/max of the component it lands on.
+// min/max per configuration over AoS vertices.  One warp per configuration streams the 3*n_v
+// floats of the row with 128-bit loads.  Float f of the row is component f % 3; lane l reads the
+// float4 number q = l + 32*it, whose first float is component q % 3 = (l + 2*it) % 3, so with the
+// loop unrolled by three every (iteration class r, slot s) pair has a fixed component per lane:
+// 12 running min/max pairs, folded into x/y/z once at the end.
 __global__ void __launch_bounds__(kStageThreads) aabb_aos_kernel(const rc_vec3 *__restrict__ verts,
                                                                  unsigned n_v, unsigned n,
                                                                  rc_aabb *__restrict__ out)
@@ -159,28 +193,50 @@ __global__ void __launch_bounds__(kStageThreads) aabb_aos_kernel(const rc_vec3 *
     const size_t warp = (size_t)blockIdx.x * kStageWarps + (threadIdx.x >> 5);
     const size_t n_warps = (size_t)gridDim.x * kStageWarps;
     const float *f = reinterpret_cast<const float *>(verts);
+    const unsigned total = 3 * n_v;
+    const bool vec = (total % 4 == 0) && ((reinterpret_cast<uintptr_t>(verts) & 15) == 0);
     for (size_t i = warp; i < n; i += n_warps) {
+        const float *row = f + (size_t)total * i;
         float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-        const float *row = f + 3 * i * n_v;
-        const unsigned total = 3 * n_v;
-        // 96 = lcm(32, 3): within a block of 96 floats lane l sees components (l, l+32, l+64) % 3
-        const int c0 = lane % 3, c1 = (lane + 32) % 3, c2 = (lane + 64) % 3;
-        for (unsigned e = lane; e < total; e += 96) {
-            const float a = __ldcs(row + e);
-            if (c0 == 0) { lo[0] = fminf(lo[0], a); hi[0] = fmaxf(hi[0], a); }
-            else if (c0 == 1) { lo[1] = fminf(lo[1], a); hi[1] = fmaxf(hi[1], a); }
-            else { lo[2] = fminf(lo[2], a); hi[2] = fmaxf(hi[2], a); }
-            if (e + 32 < total) {
-                const float b = __ldcs(row + e + 32);
-                if (c1 == 0) { lo[0] = fminf(lo[0], b); hi[0] = fmaxf(hi[0], b); }
-                else if (c1 == 1) { lo[1] = fminf(lo[1], b); hi[1] = fmaxf(hi[1], b); }
-                else { lo[2] = fminf(lo[2], b); hi[2] = fmaxf(hi[2], b); }
+        if (vec) {
+            float slo[3][4], shi[3][4];
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) { slo[r][q] = FLT_MAX; shi[r][q] = -FLT_MAX; }
+            const unsigned nq = total / 4;
+            const float4 *row4 = reinterpret_cast<const float4 *>(row);
+            for (unsigned q0 = lane; q0 < nq; q0 += 96) {
+#pragma unroll
+                for (int r = 0; r < 3; r++) {
+                    const unsigned q = q0 + 32 * r;
+                    if (q < nq) {
+                        const float4 v = __ldcs(row4 + q);
+                        slo[r][0] = fminf(slo[r][0], v.x); shi[r][0] = fmaxf(shi[r][0], v.x);
+                        slo[r][1] = fminf(slo[r][1], v.y); shi[r][1] = fmaxf(shi[r][1], v.y);
+                        slo[r][2] = fminf(slo[r][2], v.z); shi[r][2] = fmaxf(shi[r][2], v.z);
+                        slo[r][3] = fminf(slo[r][3], v.w); shi[r][3] = fmaxf(shi[r][3], v.w);
+                    }
+                }
             }
-            if (e + 64 < total) {
-                const float c = __ldcs(row + e + 64);
-                if (c2 == 0) { lo[0] = fminf(lo[0], c); hi[0] = fmaxf(hi[0], c); }
-                else if (c2 == 1) { lo[1] = fminf(lo[1], c); hi[1] = fmaxf(hi[1], c); }
-                else { lo[2] = fminf(lo[2], c); hi[2] = fmaxf(hi[2], c); }
+            // fold: slot (r, s) of this lane holds component (lane + 2 r + s) % 3
+            const int l3 = lane % 3;
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int cmp = (l3 + 2 * r + q) % 3;
+#pragma unroll
+                    for (int k = 0; k < 3; k++)
+                        if (cmp == k) { lo[k] = fminf(lo[k], slo[r][q]); hi[k] = fmaxf(hi[k], shi[r][q]); }
+                }
+        } else {
+            for (unsigned e = lane; e < total; e += 32) {
+                const float a = __ldcs(row + e);
+                const int cmp = e % 3;
+#pragma unroll
+                for (int k = 0; k < 3; k++)
+                    if (cmp == k) { lo[k] = fminf(lo[k], a); hi[k] = fmaxf(hi[k], a); }
             }
         }
         const float lx = warp_min(lo[0]), ly = warp_min(lo[1]), lz = warp_min(lo[2]);

@@ -265,3 +265,30 @@ def test_subdivided_obstacle_matches_oracle(rc, po, meshes, levels, n):
         c.close()
     assert np.array_equal(got, want)
     assert 0 < int(want.sum()) < n
+
+
+@pytest.mark.parametrize("n_v,n", [(6, 2), (7, 37), (64, 33), (100, 5), (792, 9)])
+def test_aabb_and_transform_stages_odd_sizes(rc, ctx, po, n_v, n):
+    """generate-AABB/test-generate-AABB.cu:83-114 style: exact equality against a serial min/max,
+    on sizes that exercise the scalar (unaligned) and the 128-bit paths of the stage kernels."""
+    torch = _torch()
+    rng = np.random.default_rng(n_v * 1000 + n)
+    verts = rng.uniform(-50, 50, size=(n, n_v, 3)).astype(np.float32)
+    want = np.concatenate([verts.min(1), verts.max(1)], axis=1)
+    d = torch.from_numpy(verts).cuda()
+    out = torch.zeros(n * 6, dtype=torch.float32, device="cuda")
+    ctx.generate_aabb(d, n_v, n, out, torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy().reshape(n, 6), want)
+    assert np.array_equal(ctx.generate_aabb_host(verts, n_v, n), want)
+    # genTransformedCopies with a caller-supplied base mesh of n_v vertices
+    base = verts[0].copy()
+    confs = rc.createAlphaBotConfigurations(n, True, 9)
+    d_base = torch.from_numpy(base).cuda()
+    d_confs = torch.from_numpy(confs).cuda()
+    d_out = torch.zeros(n * n_v * 3, dtype=torch.float32, device="cuda")
+    ctx.transform_aos(d_confs, n, d_out, d_base=d_base, n_v=n_v, stream=torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    ox, oy, oz = po.transform(confs, base[:, 0], base[:, 1], base[:, 2])
+    got = d_out.cpu().numpy().reshape(n, n_v, 3)
+    assert np.array_equal(got[..., 0], ox) and np.array_equal(got[..., 1], oy) and np.array_equal(got[..., 2], oz)
