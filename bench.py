@@ -200,7 +200,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3) if args.warmup else 0):
+    for _ in range(max(args.warmup, 3)):  # never fewer than three warm-up steps
         step()
     barrier()
     sampler = ClockSampler(local)

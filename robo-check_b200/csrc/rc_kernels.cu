@@ -135,8 +135,8 @@ __device__ __forceinline__ bool exhaustive_sweep(LoadTri load_tri, int n_rob_t,
         const Tri r0 = load_tri(min(jb + lane, n_rob_t - 1));
         const Tri r1 = load_tri(min(jb + 32 + lane, n_rob_t - 1));
         const Plane p0 = plane_of(r0), p1 = plane_of(r1);
-        int pend0 = -1, pend1 = -1;
 
+        // second plane test and the rest for one (robot triangle, obstacle triangle k)
         auto finish = [&](const Tri &r, const Plane &pr, int k) {
             const float4 oa = s_obs_a[k], ob = s_obs_b[k], oc = s_obs_c[k];
             const Tri o = {oa.x, oa.y, oa.z, ob.x, ob.y, ob.z, oc.x, oc.y, oc.z};
@@ -151,24 +151,40 @@ __device__ __forceinline__ bool exhaustive_sweep(LoadTri load_tri, int n_rob_t,
             }
         };
 
+        // Obstacle triangles in blocks of 32: the first plane test of every pair sets a bit, the
+        // (rare, ~5 %) survivors of a block are finished together afterwards, one per lane and
+        // step, so the hot loop has no vote and the long path runs with many lanes.
+        for (int kb = 0; kb < n_obs_t; kb += 32) {
+            uint32_t m0 = 0, m1 = 0;
+            const int kn = min(32, n_obs_t - kb);
 #pragma unroll 4
-        for (int k = 0; k < n_obs_t; k++) {
-            const float4 oa = s_obs_a[k], ob = s_obs_b[k], oc = s_obs_c[k];  // broadcast
-            const bool pass0 = straddles(sdist(p0, oa.x, oa.y, oa.z), sdist(p0, ob.x, ob.y, ob.z),
-                                         sdist(p0, oc.x, oc.y, oc.z));
-            const bool pass1 = straddles(sdist(p1, oa.x, oa.y, oa.z), sdist(p1, ob.x, ob.y, ob.z),
-                                         sdist(p1, oc.x, oc.y, oc.z));
-            if (__any_sync(kFull, (pass0 && pend0 >= 0) || (pass1 && pend1 >= 0))) {
-                if (pend0 >= 0) finish(r0, p0, pend0);
-                if (pend1 >= 0) finish(r1, p1, pend1);
-                pend0 = pend1 = -1;
-                if (__any_sync(kFull, hit)) break;
+            for (int q = 0; q < kn; q++) {
+                const int k = kb + q;
+                const float4 oa = s_obs_a[k], ob = s_obs_b[k], oc = s_obs_c[k];  // broadcast
+                const bool pass0 = straddles(sdist(p0, oa.x, oa.y, oa.z), sdist(p0, ob.x, ob.y, ob.z),
+                                             sdist(p0, oc.x, oc.y, oc.z));
+                const bool pass1 = straddles(sdist(p1, oa.x, oa.y, oa.z), sdist(p1, ob.x, ob.y, ob.z),
+                                             sdist(p1, oc.x, oc.y, oc.z));
+                m0 |= (uint32_t)pass0 << q;
+                m1 |= (uint32_t)pass1 << q;
             }
-            if (pass0) pend0 = k;
-            if (pass1) pend1 = k;
+            while (__any_sync(kFull, (m0 | m1) != 0u)) {
+                if (m0 | m1) {
+                    // one code path for both triangles of the lane (selects instead of branches)
+                    const bool first = m0 != 0u;
+                    const uint32_t mm = first ? m0 : m1;
+                    const int q = __ffs(mm) - 1;
+                    if (first) m0 &= m0 - 1; else m1 &= m1 - 1;
+                    const Tri r = {first ? r0.ax : r1.ax, first ? r0.ay : r1.ay, first ? r0.az : r1.az,
+                                   first ? r0.bx : r1.bx, first ? r0.by : r1.by, first ? r0.bz : r1.bz,
+                                   first ? r0.cx : r1.cx, first ? r0.cy : r1.cy, first ? r0.cz : r1.cz};
+                    const Plane pr = {first ? p0.nx : p1.nx, first ? p0.ny : p1.ny,
+                                      first ? p0.nz : p1.nz, first ? p0.s : p1.s};
+                    finish(r, pr, kb + q);
+                }
+            }
+            if (__any_sync(kFull, hit)) break;
         }
-        if (pend0 >= 0) finish(r0, p0, pend0);
-        if (pend1 >= 0) finish(r1, p1, pend1);
         hit = __any_sync(kFull, hit);
     }
     return hit;
