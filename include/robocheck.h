@@ -118,6 +118,31 @@ int rc_narrow_phase_host(int n, int n_rob_t, int n_rob_v, int n_obs_t, int n_obs
                          const rc_tri *rob_trs, const rc_vec3 *rob_pts, const rc_tri *obs_trs,
                          const rc_vec3 *obs_pts, uint8_t *valid, int device);
 
+/* test/MegaKernel.hu:6-7 MegaKernel<<<>>> argument list on device pointers.  The obstacle AABB and
+ * the per-triangle obstacle AABBs (generateTriAABBs, test/MegaKernel.cu:31-35) are accepted for
+ * call-site compatibility and ignored: the context owns its own culling structures.  Like the
+ * reference kernel this entry point only ever writes `false`: the caller pre-fills valid_confs
+ * with true (MegaKernel.cu:448-452). */
+int rc_megakernel(rc_ctx *ctx, const rc_config *d_configs, const rc_aabb *d_obs_aabb,
+                  const rc_aabb *d_obs_tri_aabbs, uint8_t *d_valid_confs, int num_configs, void *stream);
+/* generateTriAABBs (test/MegaKernel.cu:20-35): per-triangle AABBs of the context's obstacle, host
+ * array of n_obs_t entries. */
+int rc_obstacle_tri_aabbs(const rc_ctx *ctx, rc_aabb *h_out);
+
+/* ---- planner loop helpers ----------------------------------------------------
+ * Configurations generated on the device (no H2D copy; the reference spends a fixed 45-50 ms per
+ * call on preparation, report 4.8): counter-based generator, uniform in the given box and in
+ * [-pi, pi) for the angles like generateConfs (Utils_rai.cu:322-348) -- but NOT the mt19937 stream
+ * of rc_conf_generate. */
+int rc_conf_generate_device(rc_ctx *ctx, rc_config *d_out, long n, float x_min, float x_max,
+                            float y_min, float y_max, float z_min, float z_max, uint64_t seed,
+                            void *stream);
+/* Order-preserving compaction: indices i < n whose flag equals `want` (1 = valid), ascending, and
+ * their count.  Flags come from d_bitmask if it is not NULL, else from d_valid.  d_indices needs
+ * room for n entries; d_count is one device word.  Asynchronous. */
+int rc_compact(rc_ctx *ctx, const uint8_t *d_valid, const uint32_t *d_bitmask, long n, int want,
+               uint32_t *d_indices, unsigned long long *d_count, void *stream);
+
 /* ---- measurement ------------------------------------------------------------------------- */
 typedef struct {
     unsigned long long broad_cleared, sphere_cleared, narrow_valid, narrow_invalid;

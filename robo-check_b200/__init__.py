@@ -64,6 +64,10 @@ ABI = [
     ("rc_broad_fused", _i, [_vp, _vp, _l, _vp, _vp, _vp, _vp, _vp, _vp]),
     ("rc_narrow_phase", _i, [_vp, _vp, _vp, _vp, _l, _vp, _vp]),
     ("rc_narrow_phase_host", _i, [_i] * 5 + [_vp] * 5 + [_i]),
+    ("rc_megakernel", _i, [_vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    ("rc_obstacle_tri_aabbs", _i, [_vp, _vp]),
+    ("rc_conf_generate_device", _i, [_vp, _vp, _l] + [_f] * 6 + [C.c_uint64, _vp]),
+    ("rc_compact", _i, [_vp, _vp, _vp, _l, _i, _vp, _vp, _vp]),
     ("rc_stats_enable", _i, [_vp, _i]),
     ("rc_stats_read", _i, [_vp, C.POINTER(rc_stats), _i]),
     ("rc_last_kernel_ms", _f, [_vp]),
@@ -375,6 +379,24 @@ class Context:
     def narrow_phase(self, d_x, d_y, d_z, n, d_valid, stream=None):
         _check(_lib.rc_narrow_phase(self._h, _ptr(d_x), _ptr(d_y), _ptr(d_z), int(n), _ptr(d_valid),
                                     _stream_ptr(stream)), self._h)
+
+    def megakernel(self, d_configs, d_valid_confs, n, d_obs_aabb=None, d_obs_tri_aabbs=None, stream=None):
+        """test/MegaKernel.hu:6 argument list (obstacle AABB arguments are accepted and ignored)."""
+        _check(_lib.rc_megakernel(self._h, _ptr(d_configs), _ptr(d_obs_aabb), _ptr(d_obs_tri_aabbs),
+                                  _ptr(d_valid_confs), int(n), _stream_ptr(stream)), self._h)
+
+    def obstacle_tri_aabbs(self):
+        out = np.zeros((self.n_obs_t, 6), np.float32)
+        _check(_lib.rc_obstacle_tri_aabbs(self._h, _ptr(out)), self._h)
+        return out
+
+    def generate_device(self, d_out, n, box, seed, stream=None):
+        _check(_lib.rc_conf_generate_device(self._h, _ptr(d_out), int(n), *[float(v) for v in box],
+                                            int(seed), _stream_ptr(stream)), self._h)
+
+    def compact(self, n, d_indices, d_count, d_valid=None, d_bitmask=None, want=1, stream=None):
+        _check(_lib.rc_compact(self._h, _ptr(d_valid), _ptr(d_bitmask), int(n), int(want),
+                               _ptr(d_indices), _ptr(d_count), _stream_ptr(stream)), self._h)
 
     # measurement -----------------------------------------------------------------------------------
     def stats_enable(self, on=True):

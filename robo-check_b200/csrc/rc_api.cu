@@ -305,6 +305,7 @@ void rc_destroy(rc_ctx *ctx)
     if (ctx->h_pinned_valid) cudaFreeHost(ctx->h_pinned_valid);
     if (ctx->d_stage_confs) cudaFree(ctx->d_stage_confs);
     if (ctx->d_stage_valid) cudaFree(ctx->d_stage_valid);
+    if (ctx->d_block_counts) cudaFree(ctx->d_block_counts);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -523,6 +524,67 @@ int rc_narrow_phase_host(int n, int n_rob_t, int n_rob_v, int n_obs_t, int n_obs
     cudaFree(dx); cudaFree(dy); cudaFree(dz); cudaFree(dv);
     rc_destroy(ctx);
     return rcode;
+}
+
+int rc_megakernel(rc_ctx *ctx, const rc_config *d_configs, const rc_aabb *, const rc_aabb *,
+                  uint8_t *d_valid_confs, int num_configs, void *stream)
+{
+    // writes every flag; on a buffer pre-filled with true that equals "only ever writes false"
+    return rc_check(ctx, d_configs, num_configs, d_valid_confs, nullptr, RC_MODE_CULLED, stream);
+}
+
+int rc_obstacle_tri_aabbs(const rc_ctx *ctx, rc_aabb *h_out)
+{
+    if (!ctx || !h_out) return RC_ERR_INVALID;
+    for (int t = 0; t < ctx->t.n_obs_t; t++) {
+        const int idx[3] = {ctx->obs_v1[t], ctx->obs_v2[t], ctx->obs_v3[t]};
+        rc_aabb b = {FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+        for (int k = 0; k < 3; k++) {
+            b.x_min = std::min(b.x_min, ctx->obs_x[idx[k]]); b.x_max = std::max(b.x_max, ctx->obs_x[idx[k]]);
+            b.y_min = std::min(b.y_min, ctx->obs_y[idx[k]]); b.y_max = std::max(b.y_max, ctx->obs_y[idx[k]]);
+            b.z_min = std::min(b.z_min, ctx->obs_z[idx[k]]); b.z_max = std::max(b.z_max, ctx->obs_z[idx[k]]);
+        }
+        h_out[t] = b;
+    }
+    return RC_OK;
+}
+
+int rc_conf_generate_device(rc_ctx *ctx, rc_config *d_out, long n, float x_min, float x_max,
+                            float y_min, float y_max, float z_min, float z_max, uint64_t seed,
+                            void *stream)
+{
+    if (!ctx || n < 0 || (n > 0 && !d_out)) return RC_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    const float box[6] = {x_min, x_max, y_min, y_max, z_min, z_max};
+    ctx->launches++;
+    return check_cuda(ctx, launch_conf_generate(d_out, n, box, seed, stream_of(ctx, stream)),
+                      "rc_conf_generate_device");
+}
+
+int rc_compact(rc_ctx *ctx, const uint8_t *d_valid, const uint32_t *d_bitmask, long n, int want,
+               uint32_t *d_indices, unsigned long long *d_count, void *stream)
+{
+    if (!ctx || n < 0 || n > 0xffffffffL || !d_count || (n > 0 && (!d_indices || (!d_valid && !d_bitmask))))
+        return RC_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    if (n == 0)
+        return check_cuda(ctx, cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), stream_of(ctx, stream)),
+                          "rc_compact");
+    const long n_blocks = (n + 4095) / 4096;
+    if (n_blocks > ctx->block_counts_cap) {
+        // grown on demand; the old buffer may still be in use by an earlier asynchronous call
+        cudaDeviceSynchronize();
+        if (ctx->d_block_counts) cudaFree(ctx->d_block_counts);
+        ctx->d_block_counts = nullptr;
+        ctx->block_counts_cap = 0;
+        cudaError_t e = cudaMalloc(&ctx->d_block_counts, (size_t)std::max(n_blocks, 1024L) * 4);
+        if (e) return check_cuda(ctx, e, "rc_compact scratch");
+        ctx->block_counts_cap = std::max(n_blocks, 1024L);
+    }
+    ctx->launches += 3;
+    return check_cuda(ctx, launch_compact(d_valid, d_bitmask, n, want ? 1 : 0, d_indices, d_count,
+                                          ctx->d_block_counts, stream_of(ctx, stream)),
+                      "rc_compact");
 }
 
 // ---- measurement --------------------------------------------------------------------------

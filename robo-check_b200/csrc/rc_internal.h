@@ -62,6 +62,8 @@ struct rc_ctx {
     long stage_capacity = 0;
     cudaStream_t own_stream = nullptr, own_stream2 = nullptr;
     cudaEvent_t ev_join = nullptr;
+    uint32_t *d_block_counts = nullptr;        // scratch of rc_compact, grown on demand
+    long block_counts_cap = 0;
     unsigned long long *d_queues = nullptr;    // [kHostChunks] work-queue counters of rc_check_host
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_kernel_ms = 0.f;
@@ -102,6 +104,11 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
                                 uint8_t *d_valid, uint32_t *d_bitmask, int want_stats,
                                 cudaStream_t stream, unsigned long long *queue);
 cudaError_t launch_fma_peak(float *d_out, int grid, int iters, cudaStream_t stream);
+cudaError_t launch_conf_generate(rc_config *d_out, long n, const float box[6], uint64_t seed,
+                                 cudaStream_t stream);
+cudaError_t launch_compact(const uint8_t *d_valid, const uint32_t *d_mask, long n, int want,
+                           uint32_t *d_indices, unsigned long long *d_count, uint32_t *d_block_counts,
+                           cudaStream_t stream);
 cudaError_t launch_transform_soa(const rc_ctx *ctx, const rc_config *d_confs, long n, float *d_x,
                                  float *d_y, float *d_z, rc_aabb *d_aabb, uint8_t *d_valid,
                                  cudaStream_t stream);

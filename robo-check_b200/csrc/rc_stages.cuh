@@ -399,6 +399,160 @@ cudaError_t launch_narrow_soa(const rc_ctx *ctx, const float *d_x, const float *
     return cudaGetLastError();
 }
 
+// ---- planner loop helpers -----------------------------------------------------------------
+__device__ __forceinline__ uint64_t mix64(uint64_t z)
+{  // splitmix64 finaliser
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(256) conf_generate_kernel(rc_config *out, long n, float x0, float x1,
+                                                            float y0, float y1, float z0, float z1,
+                                                            uint64_t seed)
+{
+    const float lo[6] = {x0, y0, z0, -3.14159265358979f, -3.14159265358979f, -3.14159265358979f};
+    const float hi[6] = {x1, y1, z1, 3.14159265358979f, 3.14159265358979f, 3.14159265358979f};
+    float *f = reinterpret_cast<float *>(out);
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < 6 * n; e += (long)gridDim.x * blockDim.x) {
+        const int k = (int)(e % 6);
+        const uint64_t h = mix64(seed * 0x9E3779B97F4A7C15ull + (uint64_t)e + 1);
+        const float u = (float)(h >> 40) * (1.0f / 16777216.0f);  // [0, 1)
+        f[e] = fmaf(u, hi[k] - lo[k], lo[k]);
+    }
+}
+
+cudaError_t launch_conf_generate(rc_config *d_out, long n, const float box[6], uint64_t seed,
+                                 cudaStream_t stream)
+{
+    if (n <= 0) return cudaSuccess;
+    const int grid = (int)min((6 * n + 255) / 256, 148L * 16);
+    conf_generate_kernel<<<grid, 256, 0, stream>>>(d_out, n, box[0], box[1], box[2], box[3], box[4], box[5], seed);
+    return cudaGetLastError();
+}
+
+// Compaction: 4096 flags (128 words) per block.
+constexpr int kCompactWords = 128;
+
+__device__ __forceinline__ uint32_t flag_word(const uint8_t *valid, const uint32_t *mask, long n, long w,
+                                              int want)
+{
+    uint32_t bits = 0;
+    const long base = w * 32;
+    if (base >= n) return 0;
+    if (mask) {
+        bits = mask[w];
+    } else {
+        const int cnt = (int)min(32L, n - base);
+        if (cnt == 32 && (reinterpret_cast<uintptr_t>(valid + base) & 15) == 0) {
+            const uint4 a = *reinterpret_cast<const uint4 *>(valid + base);
+            const uint4 b = *reinterpret_cast<const uint4 *>(valid + base + 16);
+            const uint32_t wds[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+#pragma unroll
+                for (int r = 0; r < 4; r++) bits |= (uint32_t)(((wds[q] >> (8 * r)) & 0xffu) != 0) << (4 * q + r);
+        } else {
+            for (int q = 0; q < cnt; q++) bits |= (uint32_t)(valid[base + q] != 0) << q;
+        }
+    }
+    if (!want) bits = ~bits;
+    const long left = n - base;
+    if (left < 32) bits &= (1u << left) - 1u;
+    return bits;
+}
+
+__global__ void __launch_bounds__(kCompactWords) compact_count_kernel(const uint8_t *valid,
+                                                                      const uint32_t *mask, long n,
+                                                                      int want, uint32_t *block_counts)
+{
+    __shared__ uint32_t s[kCompactWords / 32];
+    const long w = (long)blockIdx.x * kCompactWords + threadIdx.x;
+    uint32_t c = __popc(flag_word(valid, mask, n, w, want));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(kFull, c, o);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = s[0] + s[1] + s[2] + s[3];
+}
+
+__global__ void __launch_bounds__(1024) compact_scan_kernel(uint32_t *block_counts, long n_blocks,
+                                                            unsigned long long *total)
+{  // exclusive scan in place, one block, sequential over chunks of 1024
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (long b0 = 0; b0 < n_blocks; b0 += 1024) {
+        const long b = b0 + threadIdx.x;
+        const uint32_t v = b < n_blocks ? block_counts[b] : 0;
+        unsigned long long x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long y = __shfl_up_sync(kFull, x, o);
+            if ((threadIdx.x & 31) >= o) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            unsigned long long wv = s_warp[threadIdx.x];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long y = __shfl_up_sync(kFull, wv, o);
+                if (threadIdx.x >= o) wv += y;
+            }
+            s_warp[threadIdx.x] = wv;
+        }
+        __syncthreads();
+        const unsigned long long before = s_carry + (threadIdx.x >= 32 ? s_warp[(threadIdx.x >> 5) - 1] : 0);
+        if (b < n_blocks) block_counts[b] = (uint32_t)(before + x - v);
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = before + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = s_carry;
+}
+
+__global__ void __launch_bounds__(kCompactWords) compact_scatter_kernel(const uint8_t *valid,
+                                                                        const uint32_t *mask, long n,
+                                                                        int want,
+                                                                        const uint32_t *block_offsets,
+                                                                        uint32_t *indices)
+{
+    __shared__ uint32_t s[kCompactWords / 32];
+    const long w = (long)blockIdx.x * kCompactWords + threadIdx.x;
+    uint32_t bits = flag_word(valid, mask, n, w, want);
+    const uint32_t c = __popc(bits);
+    uint32_t x = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(kFull, x, o);
+        if ((threadIdx.x & 31) >= o) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) s[threadIdx.x >> 5] = x;
+    __syncthreads();
+    uint32_t off = block_offsets[blockIdx.x] + x - c;
+    for (int q = 0; q < (int)(threadIdx.x >> 5); q++) off += s[q];
+    while (bits) {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        indices[off++] = (uint32_t)(w * 32 + b);
+    }
+}
+
+cudaError_t launch_compact(const uint8_t *d_valid, const uint32_t *d_mask, long n, int want,
+                           uint32_t *d_indices, unsigned long long *d_count, uint32_t *d_block_counts,
+                           cudaStream_t stream)
+{
+    const long n_blocks = (n + 32L * kCompactWords - 1) / (32L * kCompactWords);
+    if (n_blocks == 0) return cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), stream);
+    compact_count_kernel<<<(unsigned)n_blocks, kCompactWords, 0, stream>>>(d_valid, d_mask, n, want, d_block_counts);
+    compact_scan_kernel<<<1, 1024, 0, stream>>>(d_block_counts, n_blocks, d_count);
+    compact_scatter_kernel<<<(unsigned)n_blocks, kCompactWords, 0, stream>>>(d_valid, d_mask, n, want,
+                                                                            d_block_counts, d_indices);
+    return cudaGetLastError();
+}
+
 // ---- FP32 FMA peak ------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) fma_peak_kernel(float *out, int iters)
 {

@@ -3,6 +3,8 @@
 reference's own kernels compiled for sm_100a (oracle/_ref/libref.so) on the same inputs.
 Integer/flag work: bit-exact.  Transformed vertices: bit-exact vs the reference kernel and the
 oracle (tolerance stated by north_star is 1e-6 relative; we assert equality)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -292,3 +294,90 @@ def test_aabb_and_transform_stages_odd_sizes(rc, ctx, po, n_v, n):
     ox, oy, oz = po.transform(confs, base[:, 0], base[:, 1], base[:, 2])
     got = d_out.cpu().numpy().reshape(n, n_v, 3)
     assert np.array_equal(got[..., 0], ox) and np.array_equal(got[..., 1], oy) and np.array_equal(got[..., 2], oz)
+
+
+# ---- MegaKernel-signature entry, planner-loop helpers ------------------------------------------
+def test_megakernel_signature_and_tri_aabbs(rc, ctx, meshes, mixed_confs, mixed_oracle):
+    torch = _torch()
+    n = len(mixed_confs)
+    d_confs = torch.from_numpy(mixed_confs).cuda()
+    d_valid = torch.ones(n, dtype=torch.uint8, device="cuda")   # pre-filled true, MegaKernel.cu:448-452
+    tri_boxes = ctx.obstacle_tri_aabbs()
+    d_tri = torch.from_numpy(tri_boxes).cuda()
+    d_obs = torch.from_numpy(ctx.obstacle_aabb()).cuda()
+    ctx.megakernel(d_confs, d_valid, n, d_obs, d_tri, torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    assert np.array_equal(d_valid.cpu().numpy(), mixed_oracle)
+    # generateTriAABBs: min/max of the three vertices of every obstacle triangle
+    x, y, z, v1, v2, v3 = meshes[1].arrays()
+    P = np.stack([x, y, z], 1)
+    T = np.stack([P[v1], P[v2], P[v3]], 1)
+    assert np.array_equal(tri_boxes, np.concatenate([T.min(1), T.max(1)], 1))
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 4096, 4097, 100003])
+def test_compaction(rc, ctx, n):
+    torch = _torch()
+    rng = np.random.default_rng(n)
+    flags = (rng.random(n) < 0.37).astype(np.uint8)
+    from robocheck_b200 import sharding as sh
+    words = sh.pack_bitmask(flags, (n + 31) // 32 + 1)
+    d_flags = torch.from_numpy(flags).cuda()
+    d_words = torch.from_numpy(words.view(np.int32)).cuda()
+    for want in (1, 0):
+        truth = np.nonzero(flags == want)[0].astype(np.uint32)
+        for use_mask in (False, True):
+            d_idx = torch.full((max(n, 1),), -1, dtype=torch.int32, device="cuda")
+            d_cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+            ctx.compact(n, d_idx, d_cnt, d_valid=None if use_mask else d_flags,
+                        d_bitmask=d_words if use_mask else None, want=want,
+                        stream=torch.cuda.current_stream())
+            torch.cuda.synchronize()
+            cnt = int(d_cnt.item())
+            assert cnt == len(truth)
+            assert np.array_equal(d_idx.cpu().numpy()[:cnt].view(np.uint32), truth)
+
+
+def test_device_generator_and_planner_loop(rc, ctx, po, omeshes):
+    """generate on the device -> check -> compact the valid ones; flags of the generated
+    configurations are checked against the CPU oracle."""
+    torch = _torch()
+    n = 3000
+    rng_box = [-0.3, 0.3, -0.2, 0.2, -0.1, 0.1]
+    d_confs = torch.zeros(n * 6, dtype=torch.float32, device="cuda")
+    s = torch.cuda.current_stream()
+    ctx.generate_device(d_confs, n, rng_box, 1234, s)
+    d_valid = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    d_mask = torch.zeros((n + 31) // 32, dtype=torch.int32, device="cuda")
+    ctx.check(d_confs, n, d_valid, d_mask, rc.RC_MODE_CULLED, s)
+    d_idx = torch.zeros(n, dtype=torch.int32, device="cuda")
+    d_cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    ctx.compact(n, d_idx, d_cnt, d_bitmask=d_mask, stream=s)
+    torch.cuda.synchronize()
+    confs = d_confs.cpu().numpy().reshape(n, 6)
+    assert np.all(confs[:, 0] >= -0.3) and np.all(confs[:, 0] < 0.3) and np.all(np.abs(confs[:, 3:]) <= np.pi)
+    assert confs[:, 0].std() > 0.1 and abs(confs[:, 4].mean()) < 0.2          # looks uniform
+    d2 = torch.zeros(n * 6, dtype=torch.float32, device="cuda")
+    ctx.generate_device(d2, n, rng_box, 1234, s); torch.cuda.synchronize()
+    assert torch.equal(d2, d_confs)                                            # reproducible
+    want = po.check(omeshes[0], omeshes[1], confs, po.VARIANT_GPU)
+    assert np.array_equal(d_valid.cpu().numpy(), want)
+    cnt = int(d_cnt.item())
+    assert np.array_equal(d_idx.cpu().numpy()[:cnt], np.nonzero(want)[0])
+
+
+def test_cpp_harness_end_to_end(rc, golden, tmp_path):
+    """robocheck_cli = the reference's full-integration-test main() written against the reference's
+    own signatures (include/robocheck_compat.hpp): must reproduce every tag of the shipped sets."""
+    import subprocess
+    cli = os.path.join(rc.REPO_ROOT, "robo-check_b200", "robocheck_cli")
+    for key, n_valid in (("easy_confs10k", 9997), ("hard_confs10k", 7328)):
+        g = golden[key]
+        conf = str(tmp_path / (key + ".conf"))
+        rc.writeConfigurationToFileTagged(g["confs"], g["tags"], conf)
+        back, tags = rc.readConfigurationFromFileTagged(conf)
+        assert np.array_equal(back, g["confs"]) and np.array_equal(tags, g["tags"])  # 6-digit text is exact here
+        out = subprocess.run([cli, conf, os.path.join(rc.ASSET_DIR, "robot.g"),
+                              os.path.join(rc.ASSET_DIR, "obstacle.g")], capture_output=True, text=True)
+        assert out.returncode == 0, out.stdout + out.stderr
+        assert f"{n_valid} valid" in out.stdout and "0 disagreements" in out.stdout
