@@ -1,0 +1,20 @@
+#!/bin/bash
+# Round-end evidence, run on the GPU box through gpurun (one ncu tool per call):
+#   bash profiles/collect.sh launches   -> plain bench run, then the ncu launch list of the same command
+#   bash profiles/collect.sh full       -> plain driver run, then ncu --set full of every kernel of the path
+set -e
+mkdir -p gpurun_out
+case "$1" in
+launches)
+  python bench.py --steps 3 --warmup 3 --no-extras > gpurun_out/bench_plain.json 2> gpurun_out/bench_plain.err &&
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+      --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 3 --no-extras > gpurun_out/ncu_launches.log 2>&1
+  ;;
+full)
+  python profiles/prof_driver.py all > gpurun_out/plain.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on \
+      -k regex:"check_culled|check_brute|transform_soa|transform_aos|aabb_|narrow_soa|broad_kernel" -c 14 \
+      -o gpurun_out/prof_full python profiles/prof_driver.py all > gpurun_out/ncu_full.log 2>&1
+  ;;
+esac
+tail -n 3 gpurun_out/*.log

@@ -29,6 +29,11 @@ if which in ("all", "stage"):
     d_box = torch.empty(n * 6, dtype=torch.float32, device="cuda")
     for _ in range(reps):
         ctx.broad_fused(d_confs, n, dx, dy, dz, d_box, d_valid, s)
+    aos = torch.empty(n * nv * 3, dtype=torch.float32, device="cuda")
+    ctx.transform_aos(d_confs, n, aos, stream=s)
+    ctx.generate_aabb(aos, nv, n, d_box, s)
+    ctx.generate_aabb_soa(dx, dy, dz, nv, n, d_box, s)
+    ctx.broad_phase(n, d_box, d_valid, stream=s)
     ctx.narrow_phase(dx, dy, dz, 8192, d_valid, s)
 torch.cuda.synchronize()
 print("ok", int(d_valid.sum()))

@@ -1,0 +1,41 @@
+#!/usr/bin/env python
+"""ncu report -> markdown summary (one table per distinct kernel, last captured launch of each).
+usage: summarize.py <report.ncu-rep> <title>"""
+import csv
+import io
+import subprocess
+import sys
+
+rep, title = sys.argv[1], sys.argv[2]
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+hdr, units = rows[0], rows[1]
+WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "launch__shared_mem_per_block_dynamic", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_sector_hit_rate.pct", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"]
+STALL = [h for h in hdr if "pcsamp_warps_issue_stalled" in h and "not_issued" not in h]
+print(f"# {title}\n")
+print("`ncu --set full --clock-control none --import-source on`, run after the same command exited 0 "
+      "without ncu (profiles/collect.sh full).  Times under ncu are cold-cache and serialised.\n")
+last = {}
+for r in rows[2:]:
+    last[r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "")] = r
+for name, r in last.items():
+    print(f"## `{name}`\n\n| metric | value | unit |\n|---|---|---|")
+    for w in WANT:
+        if w in hdr:
+            i = hdr.index(w)
+            print(f"| {w} | {r[i]} | {units[i]} |")
+    st = [(h, float(r[hdr.index(h)] or 0)) for h in STALL]
+    tot = sum(v for _, v in st) or 1
+    top = sorted(st, key=lambda kv: -kv[1])[:5]
+    print("| top stall reasons (pc sampling) | " +
+          ", ".join(f"{h.split('stalled_')[1]} {100 * v / tot:.0f}%" for h, v in top) + " | |\n")
