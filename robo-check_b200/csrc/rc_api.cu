@@ -3,6 +3,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -169,6 +170,15 @@ int rc_create(rc_ctx **out, const float *rob_x, const float *rob_y, const float 
     rc_ctx *ctx = new (std::nothrow) rc_ctx();
     if (!ctx) return RC_ERR_NOMEM;
     ctx->device = device;
+    {
+        auto knob = [](const char *name, int dflt) { const char *e = getenv(name); return e ? atoi(e) : dflt; };
+        ctx->knob_warps = knob("RC_CULLED_WARPS", 0);
+        ctx->knob_seed_depth = knob("RC_SEED_DEPTH", -1);
+        ctx->knob_tail = knob("RC_TAIL_THRESH", 0);
+        ctx->knob_leaf = knob("RC_LEAF_THRESH", 0);
+        ctx->knob_chunk = knob("RC_CHUNK", 0);
+        ctx->knob_global_obstacle = getenv("RC_FORCE_GLOBAL_OBSTACLE") != nullptr;
+    }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     ctx->rob_x.assign(rob_x, rob_x + n_rob_v); ctx->rob_y.assign(rob_y, rob_y + n_rob_v);

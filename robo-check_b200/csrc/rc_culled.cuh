@@ -414,12 +414,11 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
                                 cudaStream_t stream, unsigned long long *queue)
 {
     const DeviceTables &t = ctx->t;
-    int warps = kCulledWarpsDefault;
-    if (const char *env = getenv("RC_CULLED_WARPS")) warps = atoi(env);  // tuning knob
+    int warps = ctx->knob_warps;
     if (warps != 16 && warps != 20 && warps != 24) warps = kCulledWarpsDefault;
     // Obstacle tables go to shared memory when everything fits with at least 16 warps per CTA;
     // otherwise they stay in global memory (any obstacle size, robot tables must still fit).
-    bool gobs = getenv("RC_FORCE_GLOBAL_OBSTACLE") != nullptr;
+    bool gobs = ctx->knob_global_obstacle;
     if (!gobs && (culled_smem_bytes(t, 16, false) > (size_t)ctx->max_smem_optin ||
                   t.n_obs_nodes > 65535 || t.n_rob_nodes > 65535))
         gobs = true;
@@ -449,13 +448,12 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
     a.c.chunk = (int)max(1L, min(16L, n / ((long)grid * warps * 32)));
     a.tail_begin = (long)grid * warps * 4;
     a.tail_thresh = 32; a.leaf_thresh = 8;
-    int sd = 2;
-    if (const char *env = getenv("RC_SEED_DEPTH")) sd = max(0, min(3, atoi(env)));
+    const int sd = ctx->knob_seed_depth < 0 ? 2 : min(3, ctx->knob_seed_depth);
     a.n_seed_r = t.n_seed_r[sd]; a.n_seed_o = t.n_seed_o[sd];
     for (int q = 0; q < 8; q++) { a.seed_r[q] = t.seed_r[sd][q]; a.seed_o[q] = t.seed_o[sd][q]; }
-    if (const char *env = getenv("RC_TAIL_THRESH")) a.tail_thresh = max(1, min(32, atoi(env)));
-    if (const char *env = getenv("RC_LEAF_THRESH")) a.leaf_thresh = max(1, min(8, atoi(env)));
-    if (const char *env = getenv("RC_CHUNK")) a.c.chunk = max(1, min(16, atoi(env)));
+    if (ctx->knob_tail > 0) a.tail_thresh = min(32, ctx->knob_tail);
+    if (ctx->knob_leaf > 0) a.leaf_thresh = min(8, ctx->knob_leaf);
+    if (ctx->knob_chunk > 0) a.c.chunk = min(16, ctx->knob_chunk);
     void (*kern)(const CulledArgs) = gobs ? pick_culled<true>(warps, want_stats) : pick_culled<false>(warps, want_stats);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

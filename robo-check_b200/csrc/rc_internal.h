@@ -67,6 +67,10 @@ struct rc_ctx {
     unsigned long long *d_queues = nullptr;    // [kHostChunks] work-queue counters of rc_check_host
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_kernel_ms = 0.f;
+    // tuning knobs, read from the environment once at rc_create (RC_CULLED_WARPS, RC_SEED_DEPTH,
+    // RC_TAIL_THRESH, RC_LEAF_THRESH, RC_CHUNK, RC_FORCE_GLOBAL_OBSTACLE); 0 / -1 = default
+    int knob_warps = 0, knob_seed_depth = -1, knob_tail = 0, knob_leaf = 0, knob_chunk = 0;
+    bool knob_global_obstacle = false;
     std::string last_error;
     std::vector<void *> allocations;
 };
