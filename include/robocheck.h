@@ -143,6 +143,17 @@ int rc_conf_generate_device(rc_ctx *ctx, rc_config *d_out, long n, float x_min, 
 int rc_compact(rc_ctx *ctx, const uint8_t *d_valid, const uint32_t *d_bitmask, long n, int want,
                uint32_t *d_indices, unsigned long long *d_count, void *stream);
 
+/* ---- sphere-approximated robot (BASELINE config 3) -----------------------------
+ * The reference has no such path (test/CPU-Sphere-Test.cpp:8-18 only collides two unit spheres
+ * with FCL), so the semantics are this library's: the robot is a set of spheres (x, y, z, r) in
+ * its local frame; a configuration is valid iff no sphere, moved by the configuration, comes
+ * within its radius of an obstacle triangle.  xyzr == NULL installs the default set: the smallest
+ * enclosing sphere of every robot triangle. */
+int rc_set_robot_spheres(rc_ctx *ctx, const float *xyzr, int n);
+int rc_robot_spheres(const rc_ctx *ctx, float *xyzr_out, int *n); /* xyzr_out may be NULL */
+int rc_check_spheres(rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_valid,
+                     uint32_t *d_bitmask, void *stream);
+
 /* ---- measurement ------------------------------------------------------------------------- */
 typedef struct {
     unsigned long long broad_cleared, sphere_cleared, narrow_valid, narrow_invalid;

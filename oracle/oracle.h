@@ -49,6 +49,10 @@ int rco_check(const rco_mesh *rob, const rco_mesh *obs, const rco_config *confs,
 int rco_narrow(const rco_mesh *rob, const rco_mesh *obs, const float *px, const float *py,
                const float *pz, long n, int variant, uint8_t *valid);
 
+float rco_point_tri_dist2(const float p[3], const float t[9]);
+int rco_check_spheres(const float *spheres, int n_s, const rco_mesh *obs, const rco_config *confs,
+                      long n, int nthreads, uint8_t *valid);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,6 +38,7 @@ def lib():
         _lib = C.CDLL(ORACLE_SO)
         _lib.rco_project.restype = C.c_float
         _lib.rco_param.restype = C.c_float
+        _lib.rco_point_tri_dist2.restype = C.c_float
     return _lib
 
 
@@ -115,6 +116,21 @@ def pair_hits(r9, o9, variant=VARIANT_GPU):
     cop = C.c_int()
     h = lib().rco_pair_hits(_p(_f(r9)), _p(_f(o9)), variant, C.byref(cop))
     return int(h), int(cop.value)
+
+
+def check_spheres(spheres, obs, confs, nthreads=None):
+    """Sphere-approximated robot (this repo's own definition, see oracle.c): uint8 flags."""
+    spheres = _f(spheres).reshape(-1, 4)
+    confs = _f(confs).reshape(-1, 6)
+    valid = np.zeros(len(confs), np.uint8)
+    rc = lib().rco_check_spheres(_p(spheres), len(spheres), C.byref(obs.c), _p(confs),
+                                 C.c_long(len(confs)), nthreads or os.cpu_count() or 1, _p(valid))
+    assert rc == 0
+    return valid
+
+
+def point_tri_dist2(p, tri9):
+    return float(lib().rco_point_tri_dist2(_p(_f(p)), _p(_f(tri9))))
 
 
 # ---- the compiled reference ------------------------------------------------------------------

@@ -68,6 +68,9 @@ ABI = [
     ("rc_obstacle_tri_aabbs", _i, [_vp, _vp]),
     ("rc_conf_generate_device", _i, [_vp, _vp, _l] + [_f] * 6 + [C.c_uint64, _vp]),
     ("rc_compact", _i, [_vp, _vp, _vp, _l, _i, _vp, _vp, _vp]),
+    ("rc_set_robot_spheres", _i, [_vp, _vp, _i]),
+    ("rc_robot_spheres", _i, [_vp, _vp, C.POINTER(_i)]),
+    ("rc_check_spheres", _i, [_vp, _vp, _l, _vp, _vp, _vp]),
     ("rc_stats_enable", _i, [_vp, _i]),
     ("rc_stats_read", _i, [_vp, C.POINTER(rc_stats), _i]),
     ("rc_last_kernel_ms", _f, [_vp]),
@@ -397,6 +400,26 @@ class Context:
     def compact(self, n, d_indices, d_count, d_valid=None, d_bitmask=None, want=1, stream=None):
         _check(_lib.rc_compact(self._h, _ptr(d_valid), _ptr(d_bitmask), int(n), int(want),
                                _ptr(d_indices), _ptr(d_count), _stream_ptr(stream)), self._h)
+
+    # sphere-approximated robot ---------------------------------------------------------------------
+    def set_robot_spheres(self, xyzr=None):
+        if xyzr is None:
+            _check(_lib.rc_set_robot_spheres(self._h, None, 0), self._h)
+        else:
+            xyzr = np.ascontiguousarray(xyzr, dtype=np.float32).reshape(-1, 4)
+            _check(_lib.rc_set_robot_spheres(self._h, _ptr(xyzr), len(xyzr)), self._h)
+
+    def robot_spheres(self):
+        n = C.c_int()
+        _check(_lib.rc_robot_spheres(self._h, None, C.byref(n)), self._h)
+        out = np.zeros((n.value, 4), np.float32)
+        if n.value:
+            _check(_lib.rc_robot_spheres(self._h, _ptr(out), C.byref(n)), self._h)
+        return out
+
+    def check_spheres(self, d_confs, n, d_valid=None, d_bitmask=None, stream=None):
+        _check(_lib.rc_check_spheres(self._h, _ptr(d_confs), int(n), _ptr(d_valid), _ptr(d_bitmask),
+                                     _stream_ptr(stream)), self._h)
 
     # measurement -----------------------------------------------------------------------------------
     def stats_enable(self, on=True):

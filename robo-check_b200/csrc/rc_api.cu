@@ -597,6 +597,87 @@ int rc_compact(rc_ctx *ctx, const uint8_t *d_valid, const uint32_t *d_bitmask, l
                       "rc_compact");
 }
 
+int rc_set_robot_spheres(rc_ctx *ctx, const float *xyzr, int n)
+{
+    if (!ctx || (xyzr && n <= 0)) return RC_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    DeviceTables &t = ctx->t;
+    std::vector<float> s;
+    if (xyzr) {
+        s.assign(xyzr, xyzr + 4 * (size_t)n);
+        for (int k = 0; k < n; k++)
+            if (!(s[4 * k + 3] >= 0.f)) return RC_ERR_INVALID;
+    } else {
+        n = t.n_rob_t;
+        s.resize(4 * (size_t)n);
+        triangle_spheres(ctx->rob_x.data(), ctx->rob_y.data(), ctx->rob_z.data(), ctx->rob_v1.data(),
+                         ctx->rob_v2.data(), ctx->rob_v3.data(), n, s.data());
+    }
+    // tree over the spheres' boxes (robot frame), spheres stored in leaf order
+    std::vector<float> lo(3 * (size_t)n), hi(lo.size()), cen(lo.size());
+    double blo[3] = {1e300, 1e300, 1e300}, bhi[3] = {-1e300, -1e300, -1e300};
+    for (int k = 0; k < n; k++)
+        for (int q = 0; q < 3; q++) {
+            // box of the sphere, widened by an ulp-scale slack so that it really contains it
+            const float r = s[4 * k + 3] * (1.0f + 1e-6f) + 1e-6f;
+            lo[3 * (size_t)k + q] = s[4 * k + q] - r;
+            hi[3 * (size_t)k + q] = s[4 * k + q] + r;
+            cen[3 * (size_t)k + q] = s[4 * k + q];
+            blo[q] = std::min(blo[q], (double)lo[3 * (size_t)k + q]);
+            bhi[q] = std::max(bhi[q], (double)hi[3 * (size_t)k + q]);
+        }
+    const Bvh tree = build_bvh_boxes(lo.data(), hi.data(), cen.data(), n, kBoxMargin);
+    std::vector<float4> sorted((size_t)n), nodes((size_t)tree.n_nodes * 2);
+    for (int p = 0; p < n; p++) {
+        const int k = tree.order[p];
+        sorted[p] = make_float4(s[4 * k], s[4 * k + 1], s[4 * k + 2], s[4 * k + 3]);
+    }
+    std::memcpy(nodes.data(), tree.nodes.data(), tree.nodes.size() * sizeof(float));
+    double r2 = 0;
+    for (int q = 0; q < 3; q++) t.sph_bound[q] = (float)(0.5 * (blo[q] + bhi[q]));
+    for (int k = 0; k < n; k++) {
+        double d2 = 0;
+        for (int q = 0; q < 3; q++) d2 += ((double)s[4 * k + q] - t.sph_bound[q]) * ((double)s[4 * k + q] - t.sph_bound[q]);
+        r2 = std::max(r2, std::sqrt(d2) + (double)s[4 * k + 3]);
+    }
+    t.sph_bound[3] = (float)(r2 * (1.0 + 1e-6)) + 1e-4f;
+    cudaError_t e;
+    cudaDeviceSynchronize();  // an earlier asynchronous check may still read the old tables
+    if ((e = upload(ctx, &t.sph, sorted)) || (e = upload(ctx, &t.sph_bvh, nodes)))
+        return check_cuda(ctx, e, "sphere tables");
+    t.n_sph = n;
+    t.n_sph_nodes = tree.n_nodes;
+    ctx->spheres = s;
+    return RC_OK;
+}
+
+int rc_robot_spheres(const rc_ctx *ctx, float *xyzr_out, int *n)
+{
+    if (!ctx || !n) return RC_ERR_INVALID;
+    *n = (int)(ctx->spheres.size() / 4);
+    if (xyzr_out && !ctx->spheres.empty())
+        std::memcpy(xyzr_out, ctx->spheres.data(), ctx->spheres.size() * sizeof(float));
+    return RC_OK;
+}
+
+int rc_check_spheres(rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_valid,
+                     uint32_t *d_bitmask, void *stream)
+{
+    if (!ctx || n < 0 || (n > 0 && !d_confs) || (!d_valid && !d_bitmask)) return RC_ERR_INVALID;
+    if (n == 0) return RC_OK;
+    if (ctx->t.n_sph == 0) {
+        const int rcode = rc_set_robot_spheres(ctx, nullptr, 0);
+        if (rcode != RC_OK) return rcode;
+    }
+    cudaSetDevice(ctx->device);
+    cudaError_t e = launch_check_spheres(ctx, d_confs, n, d_valid, d_bitmask, ctx->stats_on,
+                                         stream_of(ctx, stream), nullptr);
+    if (e == cudaErrorInvalidConfiguration)
+        return set_error(ctx, RC_ERR_UNSUPPORTED, "sphere / obstacle tables do not fit");
+    ctx->launches++;
+    return check_cuda(ctx, e, "rc_check_spheres launch");
+}
+
 // ---- measurement --------------------------------------------------------------------------
 
 int rc_stats_enable(rc_ctx *ctx, int on)

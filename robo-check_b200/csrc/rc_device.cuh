@@ -289,3 +289,59 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
 }
 
 }  // namespace rc
+
+// ---- sphere-approximated robot (BASELINE config 3) ---------------------------------------------
+// Squared distance from point p to triangle (a, b, c): closest-point regions of Ericson,
+// "Real-Time Collision Detection" 5.1.5.  Every operation is individually rounded (no FMA), dot
+// products accumulate left to right, so a plain C restatement reproduces it bit for bit.
+namespace rc {
+__device__ __forceinline__ float dot3_rn(float ax, float ay, float az, float bx, float by, float bz)
+{
+    return __fadd_rn(__fadd_rn(__fmul_rn(ax, bx), __fmul_rn(ay, by)), __fmul_rn(az, bz));
+}
+
+__device__ __forceinline__ float point_tri_dist2(float px, float py, float pz, const Tri &t)
+{
+    const float abx = __fsub_rn(t.bx, t.ax), aby = __fsub_rn(t.by, t.ay), abz = __fsub_rn(t.bz, t.az);
+    const float acx = __fsub_rn(t.cx, t.ax), acy = __fsub_rn(t.cy, t.ay), acz = __fsub_rn(t.cz, t.az);
+    const float apx = __fsub_rn(px, t.ax), apy = __fsub_rn(py, t.ay), apz = __fsub_rn(pz, t.az);
+    const float d1 = dot3_rn(abx, aby, abz, apx, apy, apz), d2 = dot3_rn(acx, acy, acz, apx, apy, apz);
+    float qx, qy, qz;  // closest point
+    const float bpx = __fsub_rn(px, t.bx), bpy = __fsub_rn(py, t.by), bpz = __fsub_rn(pz, t.bz);
+    const float d3 = dot3_rn(abx, aby, abz, bpx, bpy, bpz), d4 = dot3_rn(acx, acy, acz, bpx, bpy, bpz);
+    const float cpx = __fsub_rn(px, t.cx), cpy = __fsub_rn(py, t.cy), cpz = __fsub_rn(pz, t.cz);
+    const float d5 = dot3_rn(abx, aby, abz, cpx, cpy, cpz), d6 = dot3_rn(acx, acy, acz, cpx, cpy, cpz);
+    const float vc = __fsub_rn(__fmul_rn(d1, d4), __fmul_rn(d3, d2));
+    const float vb = __fsub_rn(__fmul_rn(d5, d2), __fmul_rn(d1, d6));
+    const float va = __fsub_rn(__fmul_rn(d3, d6), __fmul_rn(d5, d4));
+    if (d1 <= 0.f && d2 <= 0.f) {
+        qx = t.ax; qy = t.ay; qz = t.az;
+    } else if (d3 >= 0.f && d4 <= d3) {
+        qx = t.bx; qy = t.by; qz = t.bz;
+    } else if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) {
+        const float v = __fdiv_rn(d1, __fsub_rn(d1, d3));
+        qx = __fadd_rn(t.ax, __fmul_rn(v, abx)); qy = __fadd_rn(t.ay, __fmul_rn(v, aby));
+        qz = __fadd_rn(t.az, __fmul_rn(v, abz));
+    } else if (d6 >= 0.f && d5 <= d6) {
+        qx = t.cx; qy = t.cy; qz = t.cz;
+    } else if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) {
+        const float w = __fdiv_rn(d2, __fsub_rn(d2, d6));
+        qx = __fadd_rn(t.ax, __fmul_rn(w, acx)); qy = __fadd_rn(t.ay, __fmul_rn(w, acy));
+        qz = __fadd_rn(t.az, __fmul_rn(w, acz));
+    } else if (va <= 0.f && __fsub_rn(d4, d3) >= 0.f && __fsub_rn(d5, d6) >= 0.f) {
+        const float e = __fsub_rn(d4, d3);
+        const float w = __fdiv_rn(e, __fadd_rn(e, __fsub_rn(d5, d6)));
+        qx = __fadd_rn(t.bx, __fmul_rn(w, __fsub_rn(t.cx, t.bx)));
+        qy = __fadd_rn(t.by, __fmul_rn(w, __fsub_rn(t.cy, t.by)));
+        qz = __fadd_rn(t.bz, __fmul_rn(w, __fsub_rn(t.cz, t.bz)));
+    } else {
+        const float denom = __fdiv_rn(1.0f, __fadd_rn(__fadd_rn(va, vb), vc));
+        const float v = __fmul_rn(vb, denom), w = __fmul_rn(vc, denom);
+        qx = __fadd_rn(__fadd_rn(t.ax, __fmul_rn(abx, v)), __fmul_rn(acx, w));
+        qy = __fadd_rn(__fadd_rn(t.ay, __fmul_rn(aby, v)), __fmul_rn(acy, w));
+        qz = __fadd_rn(__fadd_rn(t.az, __fmul_rn(abz, v)), __fmul_rn(acz, w));
+    }
+    const float ex = __fsub_rn(px, qx), ey = __fsub_rn(py, qy), ez = __fsub_rn(pz, qz);
+    return dot3_rn(ex, ey, ez, ex, ey, ez);
+}
+}  // namespace rc

@@ -28,6 +28,10 @@ struct DeviceTables {
     uint2 *rob_t_sorted = nullptr;   // robot triangles in BVH leaf order
     float4 *obs_a_sorted = nullptr, *obs_b_sorted = nullptr, *obs_c_sorted = nullptr;
     float *obs_d_sorted = nullptr;   // obstacle triangles in BVH leaf order
+    // sphere-approximated robot (optional, built on first use): spheres in sphere-tree leaf order
+    float4 *sph = nullptr, *sph_bvh = nullptr;
+    int n_sph = 0, n_sph_nodes = 0;
+    float sph_bound[4] = {0, 0, 0, 0};  // bounding sphere of the set, local frame
     int n_rob_v = 0, n_rob_t = 0, n_obs_v = 0, n_obs_t = 0;
     int n_rob_nodes = 0, n_obs_nodes = 0;
     int n_rob_v_pad = 0;        // n_rob_v rounded up to 32 (padding repeats vertex 0)
@@ -50,6 +54,7 @@ struct rc_ctx {
     // host copies (for rc_get_* and for rebuilding)
     std::vector<float> rob_x, rob_y, rob_z, obs_x, obs_y, obs_z;
     std::vector<int> rob_v1, rob_v2, rob_v3, obs_v1, obs_v2, obs_v3;
+    std::vector<float> spheres;                // robot sphere set as given / generated, n x 4
     // scratch owned by the context
     unsigned long long *d_counters = nullptr;  // [RC_NUM_COUNTERS] work queue + statistics
     rc_aabb *d_obs_box = nullptr;              // obstacle AABB on the device (broad-phase stage)
@@ -107,6 +112,9 @@ cudaError_t launch_check(const rc_ctx *ctx, const rc_config *d_confs, long n, ui
 cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, long n,
                                 uint8_t *d_valid, uint32_t *d_bitmask, int want_stats,
                                 cudaStream_t stream, unsigned long long *queue);
+cudaError_t launch_check_spheres(const rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_valid,
+                                 uint32_t *d_bitmask, int want_stats, cudaStream_t stream,
+                                 unsigned long long *queue);
 cudaError_t launch_fma_peak(float *d_out, int grid, int iters, cudaStream_t stream);
 cudaError_t launch_conf_generate(rc_config *d_out, long n, const float box[6], uint64_t seed,
                                  cudaStream_t stream);

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <cmath>
 #include <cstring>
 #include <numeric>
 #include <utility>
@@ -11,19 +12,16 @@ namespace rc {
 namespace {
 
 struct Builder {
-    const float *x, *y, *z;
-    const int *v1, *v2, *v3;
+    const float *plo, *phi;  // primitive boxes, 3 floats each
     float margin;
-    std::vector<float> cen;  // 3 per triangle
+    std::vector<float> cen;  // 3 per primitive
     Bvh out;
 
     void tri_bounds(int t, float lo[3], float hi[3]) const
     {
-        const int idx[3] = {v1[t], v2[t], v3[t]};
         for (int k = 0; k < 3; k++) {
-            lo[0] = std::min(lo[0], x[idx[k]]); hi[0] = std::max(hi[0], x[idx[k]]);
-            lo[1] = std::min(lo[1], y[idx[k]]); hi[1] = std::max(hi[1], y[idx[k]]);
-            lo[2] = std::min(lo[2], z[idx[k]]); hi[2] = std::max(hi[2], z[idx[k]]);
+            lo[k] = std::min(lo[k], plo[3 * (size_t)t + k]);
+            hi[k] = std::max(hi[k], phi[3 * (size_t)t + k]);
         }
     }
 
@@ -99,20 +97,87 @@ std::vector<int> Bvh::cut(int d) const
     return out;
 }
 
+Bvh build_bvh_boxes(const float *lo, const float *hi, const float *centre, int n, float margin)
+{
+    Builder b{lo, hi, margin, {}, {}};
+    b.cen.assign(centre, centre + 3 * (size_t)std::max(n, 0));
+    std::vector<int> prims((size_t)std::max(n, 0));
+    std::iota(prims.begin(), prims.end(), 0);
+    if (n > 0) b.build(prims.data(), n, 0);
+    return b.out;
+}
+
 Bvh build_bvh(const float *x, const float *y, const float *z, const int *v1, const int *v2,
               const int *v3, int n_t, float margin)
 {
-    Builder b{x, y, z, v1, v2, v3, margin, {}, {}};
-    b.cen.resize(3 * (size_t)std::max(n_t, 1));
+    std::vector<float> lo(3 * (size_t)std::max(n_t, 1)), hi(lo.size()), cen(lo.size());
     for (int t = 0; t < n_t; t++) {
-        b.cen[3 * (size_t)t + 0] = (x[v1[t]] + x[v2[t]] + x[v3[t]]) / 3.0f;
-        b.cen[3 * (size_t)t + 1] = (y[v1[t]] + y[v2[t]] + y[v3[t]]) / 3.0f;
-        b.cen[3 * (size_t)t + 2] = (z[v1[t]] + z[v2[t]] + z[v3[t]]) / 3.0f;
+        const int idx[3] = {v1[t], v2[t], v3[t]};
+        const float *c[3] = {x, y, z};
+        for (int k = 0; k < 3; k++) {
+            const float a = c[k][idx[0]], b2 = c[k][idx[1]], d = c[k][idx[2]];
+            lo[3 * (size_t)t + k] = std::min(a, std::min(b2, d));
+            hi[3 * (size_t)t + k] = std::max(a, std::max(b2, d));
+            cen[3 * (size_t)t + k] = (a + b2 + d) / 3.0f;
+        }
     }
-    std::vector<int> tris((size_t)n_t);
-    std::iota(tris.begin(), tris.end(), 0);
-    if (n_t > 0) b.build(tris.data(), n_t, 0);
-    return b.out;
+    return build_bvh_boxes(lo.data(), hi.data(), cen.data(), n_t, margin);
+}
+
+void triangle_spheres(const float *x, const float *y, const float *z, const int *v1, const int *v2,
+                      const int *v3, int n_t, float *out)
+{
+    for (int t = 0; t < n_t; t++) {
+        const double p[3][3] = {{x[v1[t]], y[v1[t]], z[v1[t]]}, {x[v2[t]], y[v2[t]], z[v2[t]]},
+                                {x[v3[t]], y[v3[t]], z[v3[t]]}};
+        auto d2 = [&](int i, int j) {
+            double s = 0;
+            for (int k = 0; k < 3; k++) s += (p[i][k] - p[j][k]) * (p[i][k] - p[j][k]);
+            return s;
+        };
+        // longest edge (i, j), opposite vertex k
+        int i = 0, j = 1, k = 2;
+        if (d2(1, 2) > d2(i, j)) { i = 1; j = 2; k = 0; }
+        if (d2(2, 0) > d2(i, j)) { i = 2; j = 0; k = 1; }
+        double c[3];
+        for (int q = 0; q < 3; q++) c[q] = 0.5 * (p[i][q] + p[j][q]);
+        double r2 = 0.25 * d2(i, j), dk = 0;
+        for (int q = 0; q < 3; q++) dk += (p[k][q] - c[q]) * (p[k][q] - c[q]);
+        if (dk > r2) {
+            // acute: circumcentre = a + (|ac|^2 (ab x ac) x ab + |ab|^2 ac x (ab x ac)) / (2 |ab x ac|^2)
+            double ab[3], ac[3], n[3], t1[3], t2[3];
+            for (int q = 0; q < 3; q++) { ab[q] = p[1][q] - p[0][q]; ac[q] = p[2][q] - p[0][q]; }
+            n[0] = ab[1] * ac[2] - ab[2] * ac[1]; n[1] = ab[2] * ac[0] - ab[0] * ac[2]; n[2] = ab[0] * ac[1] - ab[1] * ac[0];
+            t1[0] = n[1] * ab[2] - n[2] * ab[1]; t1[1] = n[2] * ab[0] - n[0] * ab[2]; t1[2] = n[0] * ab[1] - n[1] * ab[0];
+            t2[0] = ac[1] * n[2] - ac[2] * n[1]; t2[1] = ac[2] * n[0] - ac[0] * n[2]; t2[2] = ac[0] * n[1] - ac[1] * n[0];
+            const double ab2 = ab[0] * ab[0] + ab[1] * ab[1] + ab[2] * ab[2];
+            const double ac2 = ac[0] * ac[0] + ac[1] * ac[1] + ac[2] * ac[2];
+            const double nn = 2.0 * (n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+            if (nn > 0) {
+                r2 = 0;
+                for (int q = 0; q < 3; q++) c[q] = p[0][q] + (ac2 * t1[q] + ab2 * t2[q]) / nn;
+                for (int v = 0; v < 3; v++) {
+                    double dv = 0;
+                    for (int q = 0; q < 3; q++) dv += (p[v][q] - c[q]) * (p[v][q] - c[q]);
+                    r2 = std::max(r2, dv);
+                }
+            } else {
+                r2 = dk;
+            }
+        }
+        for (int q = 0; q < 3; q++) out[4 * (size_t)t + q] = (float)c[q];
+        // radius from the rounded centre, rounded up
+        double rr = 0;
+        for (int v = 0; v < 3; v++) {
+            double dv = 0;
+            for (int q = 0; q < 3; q++) {
+                const double e = p[v][q] - (double)out[4 * (size_t)t + q];
+                dv += e * e;
+            }
+            rr = std::max(rr, dv);
+        }
+        out[4 * (size_t)t + 3] = (float)(std::sqrt(rr) * (1.0 + 1e-6)) + 1e-6f;
+    }
 }
 
 }  // namespace rc

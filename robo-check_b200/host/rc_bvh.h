@@ -25,5 +25,12 @@ struct Bvh {
 
 Bvh build_bvh(const float *x, const float *y, const float *z, const int *v1, const int *v2,
               const int *v3, int n_t, float margin);
+// Same tree over arbitrary primitives given by their boxes (3 floats each) and sort keys.
+Bvh build_bvh_boxes(const float *lo, const float *hi, const float *centre, int n, float margin);
+
+// Bounding sphere of every triangle (smallest enclosing: mid-point of the longest edge if the
+// triangle is obtuse, circumsphere otherwise), radius rounded up.  out = n_t x (x, y, z, r).
+void triangle_spheres(const float *x, const float *y, const float *z, const int *v1, const int *v2,
+                      const int *v3, int n_t, float *out);
 
 }  // namespace rc

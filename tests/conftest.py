@@ -52,7 +52,7 @@ def golden():
     import numpy as np
     d = os.path.join(ROOT, "tests", "golden")
     return {k: np.load(os.path.join(d, k + ".npz")) for k in
-            ("easy_confs10k", "hard_confs10k", "refcpu_hard")}
+            ("easy_confs10k", "hard_confs10k", "refcpu_hard", "refgpu_hard")}
 
 
 @pytest.fixture(scope="session")

@@ -381,3 +381,42 @@ def test_cpp_harness_end_to_end(rc, golden, tmp_path):
                               os.path.join(rc.ASSET_DIR, "obstacle.g")], capture_output=True, text=True)
         assert out.returncode == 0, out.stdout + out.stderr
         assert f"{n_valid} valid" in out.stdout and "0 disagreements" in out.stdout
+
+
+# ---- sphere-approximated robot (BASELINE config 3; this repo's own definition) -----------------
+def test_sphere_robot_matches_oracle(rc, po, omeshes, meshes):
+    torch = _torch()
+    c = rc.Context(meshes[0], meshes[1], device=0)
+    try:
+        confs = np.concatenate([rc.createAlphaBotConfigurations(1500, True, 801),
+                                rc.createAlphaBotConfigurations(500, False, 802)]).astype(np.float32)
+        n = len(confs)
+        d_confs = torch.from_numpy(confs).cuda()
+        d_valid = torch.full((n,), 9, dtype=torch.uint8, device="cuda")
+        d_mask = torch.zeros((n + 31) // 32, dtype=torch.int32, device="cuda")
+        c.check_spheres(d_confs, n, d_valid, d_mask, torch.cuda.current_stream())
+        torch.cuda.synchronize()
+        spheres = c.robot_spheres()
+        assert spheres.shape == (1008, 4)          # default: one enclosing sphere per robot triangle
+        # every sphere really encloses its triangle
+        x, y, z, v1, v2, v3 = meshes[0].arrays()
+        P = np.stack([x, y, z], 1).astype(np.float64)
+        for tri in (v1, v2, v3):
+            assert np.all(np.linalg.norm(P[tri] - spheres[:, :3], axis=1) <= spheres[:, 3] * (1 + 1e-6))
+        want = po.check_spheres(spheres, omeshes[1], confs)
+        got = d_valid.cpu().numpy()
+        assert np.array_equal(got, want)
+        bits = np.unpackbits(d_mask.cpu().numpy().view(np.uint8), bitorder="little")[:n]
+        assert np.array_equal(bits, want)
+        # the spheres cover the robot surface: a configuration the spheres clear is also clear for
+        # the mesh (never the other way round)
+        mesh_flags = run_check(c, confs, rc.RC_MODE_CULLED)
+        assert np.all(got <= mesh_flags) and 0 < int(got.sum()) < int(mesh_flags.sum())
+        # a caller-supplied set: two spheres
+        c.set_robot_spheres(np.array([[10, 0, 5, 2.0], [40, 10, 8, 0.5]], np.float32))
+        c.check_spheres(d_confs, n, d_valid, None, torch.cuda.current_stream())
+        torch.cuda.synchronize()
+        want2 = po.check_spheres(c.robot_spheres(), omeshes[1], confs)
+        assert np.array_equal(d_valid.cpu().numpy(), want2) and int(want2.sum()) > int(want.sum())
+    finally:
+        c.close()
