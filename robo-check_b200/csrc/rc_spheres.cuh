@@ -5,8 +5,8 @@
 // (default: the smallest enclosing sphere of every robot triangle, so the set covers the surface);
 // a configuration is invalid iff some sphere, its centre moved by the configuration with the same
 // pinned arithmetic as the mesh path, comes within its radius of some obstacle triangle
-// (squared distance <= r*r, rc_device.cuh: point_tri_dist2).  Parity is pinned only against this
-// repo's own CPU oracle (oracle.c: rco_check_spheres) -- there is no reference to compare with.
+// (squared distance <= r*r, rc_device.cuh: point_tri_dist2).  There is no reference result to
+// compare with; the tests check it against an independent CPU restatement of this definition.
 //
 // Same machinery as rc_culled.cuh: one warp per configuration, persistent grid, dual-tree descent
 // (sphere tree in the robot frame x obstacle tree), leaf pairs of <= 4 spheres x <= 4 triangles.
