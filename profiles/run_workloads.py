@@ -4,7 +4,8 @@
   C4 1M "uniform SE(3)" = the reference's easy sampler (seed 510)
   C5 alpha1.0 robot vs the midpoint-subdivided obstacle: 2 levels = 16,128 triangles ("16x"),
      5 levels = 1,032,192 triangles ("~1M"); 90% easy + 10% hard configurations (seed 511)
-C3 (sphere-approximated robot) has no reference implementation and is not built."""
+  C3 sphere-approximated robot (this repo's definition: one enclosing sphere per robot triangle)
+     vs the obstacle mesh, 1M easy configurations (seed 509) and 100k hard ones"""
 import json
 import os
 import sys
@@ -27,19 +28,21 @@ def mix(n, seed):
     return out[np.random.default_rng(seed).permutation(n)]
 
 
-def run(name, ctx, confs, reps=5):
+def run(name, ctx, confs, reps=5, spheres=False):
     n = len(confs)
     d = torch.from_numpy(np.ascontiguousarray(confs, dtype=np.float32)).cuda()
     v = torch.zeros(n, dtype=torch.uint8, device="cuda")
     s = torch.cuda.current_stream()
     ctx.stats_enable(True); ctx.stats(reset=True)
-    ctx.check(d, n, v, None, rc.RC_MODE_CULLED, s); torch.cuda.synchronize()
+    check = (lambda: ctx.check_spheres(d, n, v, None, s)) if spheres else \
+            (lambda: ctx.check(d, n, v, None, rc.RC_MODE_CULLED, s))
+    check(); torch.cuda.synchronize()
     st = ctx.stats(reset=True); ctx.stats_enable(False)
     best = 1e9
     for _ in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(s)
-        ctx.check(d, n, v, None, rc.RC_MODE_CULLED, s)
+        check()
         e1.record(s); torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
     rec = {"workload": name, "configs": n, "ms": round(best, 4), "configs_per_s": round(n / best * 1e3),
@@ -56,6 +59,9 @@ assert np.array_equal(flags, gold["tags"]), "C1 must reproduce the FCL tags"
 run("C2 hard 100,000 (seed 508)", ctx, rc.createAlphaBotConfigurations(100_000, True, 508))
 run("C4 uniform 1,000,000 (easy sampler, seed 510)", ctx, rc.createAlphaBotConfigurations(1_000_000, False, 510))
 run("C2x hard 1,000,000 (seed 512)", ctx, rc.createAlphaBotConfigurations(1_000_000, True, 512))
+run("C3 sphere robot (1008 spheres), easy 1,000,000 (seed 509)", ctx,
+    rc.createAlphaBotConfigurations(1_000_000, False, 509), spheres=True)
+run("C3h sphere robot, hard 100,000 (seed 508)", ctx, rc.createAlphaBotConfigurations(100_000, True, 508), spheres=True)
 ctx.close()
 for levels in (2, 5):
     t0 = time.time()
