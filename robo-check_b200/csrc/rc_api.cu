@@ -177,6 +177,7 @@ int rc_create(rc_ctx **out, const float *rob_x, const float *rob_y, const float 
         ctx->knob_tail = knob("RC_TAIL_THRESH", 0);
         ctx->knob_leaf = knob("RC_LEAF_THRESH", 0);
         ctx->knob_chunk = knob("RC_CHUNK", 0);
+        ctx->knob_stack_cap = knob("RC_STACK_CAP", 0);
         ctx->knob_global_obstacle = getenv("RC_FORCE_GLOBAL_OBSTACLE") != nullptr;
     }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);

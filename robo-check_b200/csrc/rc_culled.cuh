@@ -41,7 +41,8 @@ struct CulledArgs {
     long tail_begin;                                       // configurations left when chunks shrink to 1
     uint32_t seed_r[8], seed_o[8];                   // traversal starts from this cut of both trees
     int n_seed_r, n_seed_o;
-    int tail_thresh, leaf_thresh;                          // queue fill levels that trigger a round
+    int tail_thresh, leaf_thresh;
+    int stack_cap;                                         // <= compiled capacity (smaller only in tests)                          // queue fill levels that trigger a round
 };
 
 __device__ __forceinline__ bool boxes_overlap(const Mat34 &m, const float4 r0, const float4 r1,
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
                 const bool two = ov && (la != lb), four = ov && !la && !lb;
                 const unsigned m2 = __ballot_sync(kFull, two), m4 = __ballot_sync(kFull, four);
                 const int total = 2 * __popc(m2) + 4 * __popc(m4);
-                if (sp + total > kStack) { overflow = true; break; }
+                if (sp + total > a.stack_cap) { overflow = true; break; }
                 const int off = sp + 2 * __popc(m2 & lt) + 4 * __popc(m4 & lt);
                 if (two) {
                     if (la) {  // robot node is a leaf: descend the obstacle node
@@ -451,6 +452,8 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
     const int sd = ctx->knob_seed_depth < 0 ? 2 : min(3, ctx->knob_seed_depth);
     a.n_seed_r = t.n_seed_r[sd]; a.n_seed_o = t.n_seed_o[sd];
     for (int q = 0; q < 8; q++) { a.seed_r[q] = t.seed_r[sd][q]; a.seed_o[q] = t.seed_o[sd][q]; }
+    a.stack_cap = gobs ? kStackCapGlobal : kStackCap;
+    if (ctx->knob_stack_cap > 0) a.stack_cap = max(64, min(a.stack_cap, ctx->knob_stack_cap));
     if (ctx->knob_tail > 0) a.tail_thresh = min(32, ctx->knob_tail);
     if (ctx->knob_leaf > 0) a.leaf_thresh = min(8, ctx->knob_leaf);
     if (ctx->knob_chunk > 0) a.c.chunk = min(16, ctx->knob_chunk);

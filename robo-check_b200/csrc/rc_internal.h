@@ -75,6 +75,7 @@ struct rc_ctx {
     // tuning knobs, read from the environment once at rc_create (RC_CULLED_WARPS, RC_SEED_DEPTH,
     // RC_TAIL_THRESH, RC_LEAF_THRESH, RC_CHUNK, RC_FORCE_GLOBAL_OBSTACLE); 0 / -1 = default
     int knob_warps = 0, knob_seed_depth = -1, knob_tail = 0, knob_leaf = 0, knob_chunk = 0;
+    int knob_stack_cap = 0;  // RC_STACK_CAP: shrink the pair stack to exercise the overflow fallback
     bool knob_global_obstacle = false;
     std::string last_error;
     std::vector<void *> allocations;

@@ -420,3 +420,19 @@ def test_sphere_robot_matches_oracle(rc, po, omeshes, meshes):
         assert np.array_equal(d_valid.cpu().numpy(), want2) and int(want2.sum()) > int(want.sum())
     finally:
         c.close()
+
+
+def test_stack_overflow_fallback(rc, meshes, mixed_confs, mixed_oracle, monkeypatch):
+    """The pair stack never overflows in practice; shrink it so that it does and check that the
+    exhaustive fallback takes over with the same flags."""
+    monkeypatch.setenv("RC_STACK_CAP", "64")
+    c = rc.Context(meshes[0], meshes[1], device=0)
+    try:
+        c.stats_enable(True)
+        c.stats(reset=True)
+        got = run_check(c, mixed_confs[:600], rc.RC_MODE_CULLED)
+        st = c.stats()
+    finally:
+        c.close()
+    assert st["overflow"] > 0
+    assert np.array_equal(got, mixed_oracle[:600])
