@@ -288,6 +288,26 @@ def main():
         "executed": {k: st[k] for k in ("node_pairs", "leaf_pairs", "tri_pairs", "overflow")},
         "mix": {k: st[k] for k in ("broad_cleared", "sphere_cleared", "narrow_valid", "narrow_invalid")},
     }
+    # hardware view of the same kernels from the committed ncu capture (not live; profiles/)
+    prof = {}
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_r01_metrics.json")))
+    except (OSError, ValueError):
+        pass
+
+    def hw_view(kernel):
+        p = prof.get(kernel)
+        if not p:
+            return None
+        return {"source": "profiles/ncu_r01_summary.md (ncu --set full, same kernel, not live)",
+                "issue_slots_busy_pct": p.get("issue_active_pct"), "fma_pipe_pct": p.get("fma_pipe_pct"),
+                "alu_pipe_pct": p.get("alu_pipe_pct"), "dram_throughput_pct": p.get("dram_throughput_pct"),
+                "lanes_per_instruction": p.get("lanes_per_instruction")}
+
+    if prof.get("check_culled_kernel"):
+        roofline["traffic"] = prof["check_culled_kernel"].get("dram_bytes")
+        roofline["traffic_unit"] = "bytes per launch (ncu dram__bytes_read+write, 100,000 configurations)"
+        roofline["hw"] = hw_view("check_culled_kernel")
     out = {
         "metric": "collision-checked configs/sec", "value": value, "unit": "configs/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -318,7 +338,7 @@ def main():
         out["roofline_brute"] = {
             "kernel": "check_brute_kernel", "bound": "fp32", "achieved": flop_b / tb / 1e12,
             "peak": fp32_peak, "unit": "TFLOP/s", "frac": flop_b / tb / 1e12 / fp32_peak,
-            "configs": nb, "ms": tb * 1e3, "configs_per_s": nb / tb}
+            "configs": nb, "ms": tb * 1e3, "configs_per_s": nb / tb, "hw": hw_view("check_brute_kernel")}
         # materialising transform+AABB+broad stage: HBM-bound, 9,553 B per configuration
         ns = min(n, 100_000)
         nv = ctx.n_rob_v
@@ -338,7 +358,9 @@ def main():
             "kernel": "transform_soa_kernel (broadPhaseFusedKernel_sep stage)", "bound": "hbm",
             "achieved": stage_bytes / t_stage / 1e9, "peak": hbm_peak, "unit": "GB/s",
             "frac": stage_bytes / t_stage / 1e9 / hbm_peak, "peak_source": hbm_src,
-            "configs": ns, "ms": t_stage * 1e3, "configs_per_s": ns / t_stage, "traffic": None}
+            "configs": ns, "ms": t_stage * 1e3, "configs_per_s": ns / t_stage,
+            "traffic": (prof.get("transform_soa_kernel") or {}).get("dram_bytes"),
+            "hw": hw_view("transform_soa_kernel")}
         del dx, dy, dz
         from oracle import pyoracle as po
         out["cpu_baseline"], _, _ = cpu_reference_throughput(rc, po, confs, seconds=12.0)

@@ -1,8 +1,10 @@
 #!/usr/bin/env python
-"""ncu report -> markdown summary (one table per distinct kernel, last captured launch of each).
-usage: summarize.py <report.ncu-rep> <title>"""
+"""ncu report -> markdown summary (one table per distinct kernel, last captured launch of each);
+with a third argument also a JSON file of the numbers bench.py quotes (DRAM traffic, pipe view).
+usage: summarize.py <report.ncu-rep> <title> [metrics.json]"""
 import csv
 import io
+import json
 import subprocess
 import sys
 
@@ -39,3 +41,30 @@ for name, r in last.items():
     top = sorted(st, key=lambda kv: -kv[1])[:5]
     print("| top stall reasons (pc sampling) | " +
           ", ".join(f"{h.split('stalled_')[1]} {100 * v / tot:.0f}%" for h, v in top) + " | |\n")
+
+if len(sys.argv) > 3:
+    def num(r, key):
+        try:
+            return float(r[hdr.index(key)])
+        except (ValueError, IndexError):
+            return None
+
+    def to_bytes(r, key):
+        v, u = num(r, key), units[hdr.index(key)].lower()
+        scale = {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
+        return None if v is None else v * scale
+
+    out = {}
+    for name, r in last.items():
+        out[name.split("<")[0].replace("rc::", "")] = {
+            "duration_ms_under_ncu": num(r, "gpu__time_duration.sum"),
+            "dram_bytes": (to_bytes(r, "dram__bytes_read.sum") or 0) + (to_bytes(r, "dram__bytes_write.sum") or 0),
+            "issue_active_pct": num(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+            "fma_pipe_pct": num(r, "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
+            "alu_pipe_pct": num(r, "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"),
+            "dram_throughput_pct": num(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+            "warp_instructions": num(r, "smsp__inst_executed.sum"),
+            "lanes_per_instruction": num(r, "smsp__thread_inst_executed_per_inst_executed.ratio"),
+            "registers": num(r, "launch__registers_per_thread"),
+        }
+    json.dump(out, open(sys.argv[3], "w"), indent=1)
