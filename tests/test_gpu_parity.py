@@ -436,3 +436,20 @@ def test_stack_overflow_fallback(rc, meshes, mixed_confs, mixed_oracle, monkeypa
         c.close()
     assert st["overflow"] > 0
     assert np.array_equal(got, mixed_oracle[:600])
+
+
+def test_million_configurations_bitmask_and_sample(rc, ctx, po, omeshes):
+    """Maximum-size style check (BASELINE config 4: 1M configurations of the reference's "easy"
+    sampler, ragged count): bytes and bitmask agree everywhere, the counts add up, and a random
+    sample of the flags -- all the interesting ones plus 1,500 others -- matches the CPU oracle."""
+    n = 1_000_003
+    confs = rc.createAlphaBotConfigurations(n, False, 510)
+    got, bits = run_check(ctx, confs, rc.RC_MODE_CULLED, bitmask=True)
+    assert np.array_equal(got, bits)
+    assert set(np.unique(got)) <= {0, 1}
+    rng = np.random.default_rng(1)
+    sample = np.unique(np.concatenate([np.nonzero(got == 0)[0][:500], rng.choice(n, 1500, replace=False),
+                                       [0, n - 1]]))
+    want = po.check(omeshes[0], omeshes[1], confs[sample], po.VARIANT_GPU)
+    assert np.array_equal(got[sample], want)
+    assert 0 < int((got == 0).sum()) < n // 100
