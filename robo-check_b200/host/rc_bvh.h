@@ -1,5 +1,5 @@
 // rc_bvh.h -- binary AABB tree over the triangles of one mesh, built once per context on the
-// host.  The reference has no acceleration structure in its live pipeline (its dead MegaKernel
+// host (surface-area heuristic, leaves of <= 4 triangles kept full).  The reference has no acceleration structure in its live pipeline (its dead MegaKernel
 // precomputes per-triangle obstacle AABBs, test/MegaKernel.cu:31-35); culling here must never
 // drop a pair the reference arithmetic would report, so every box is inflated by `margin`.
 #pragma once
