@@ -453,3 +453,43 @@ def test_million_configurations_bitmask_and_sample(rc, ctx, po, omeshes):
     want = po.check(omeshes[0], omeshes[1], confs[sample], po.VARIANT_GPU)
     assert np.array_equal(got[sample], want)
     assert 0 < int((got == 0).sum()) < n // 100
+
+
+@pytest.mark.parametrize("shape", ["tetra", "single", "strip7"])
+def test_tiny_meshes_all_paths(rc, po, shape):
+    """Degenerate sizes: one-leaf trees, fewer vertices than lanes, odd triangle counts."""
+    torch = _torch()
+    if shape == "tetra":
+        v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], np.float32) * 2
+        t = np.array([[0, 1, 2], [0, 1, 3], [0, 2, 3], [1, 2, 3]], np.int32)
+    elif shape == "single":
+        v = np.array([[0, 0, 0], [2, 0, 0.3], [0, 2, -0.2]], np.float32)
+        t = np.array([[0, 1, 2]], np.int32)
+    else:
+        v = np.array([[i * 0.7, (i % 2) * 1.1, 0.1 * i * i] for i in range(9)], np.float32)
+        t = np.array([[i, i + 1, i + 2] for i in range(7)], np.int32)
+    rob = rc.Mesh.from_arrays(v[:, 0], v[:, 1], v[:, 2], t[:, 0], t[:, 1], t[:, 2])
+    ov = v * np.float32(1.3) + np.float32([0.4, -0.2, 0.3])
+    obs = rc.Mesh.from_arrays(ov[:, 0], ov[:, 1], ov[:, 2], t[:, 0], t[:, 1], t[:, 2])
+    confs = rc.generateConfs(700, -2.5, 2.5, -2.5, 2.5, -2.5, 2.5, 77)
+    want = po.check(po.OracleMesh(*rob.arrays()), po.OracleMesh(*obs.arrays()), confs, po.VARIANT_GPU)
+    assert 0 < int(want.sum()) < len(want)
+    c = rc.Context(rob, obs, device=0)
+    try:
+        for mode in (rc.RC_MODE_CULLED, rc.RC_MODE_BRUTE):
+            got, bits = run_check(c, confs, mode, bitmask=True)
+            assert np.array_equal(got, want) and np.array_equal(bits, want)
+        n, nv = len(confs), rob.n_v
+        d_confs = torch.from_numpy(confs).cuda()
+        dx, dy, dz = (torch.zeros(n * nv, dtype=torch.float32, device="cuda") for _ in range(3))
+        d_valid = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        s = torch.cuda.current_stream()
+        c.broad_fused(d_confs, n, dx, dy, dz, None, d_valid, s)
+        c.narrow_phase(dx, dy, dz, n, d_valid, s)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_valid.cpu().numpy(), want)
+        c.check_spheres(d_confs, n, d_valid, None, s)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_valid.cpu().numpy(), po.check_spheres(c.robot_spheres(), po.OracleMesh(*obs.arrays()), confs))
+    finally:
+        c.close()
