@@ -29,6 +29,7 @@ constexpr int kStackCap = 1024;  // node pairs per warp; overflow falls back to 
 constexpr int kLeafQCap = 64;
 constexpr int kTailQCap = 160;   // pairs that passed both plane tests, finished 32 at a time
 constexpr int kStackCapGlobal = 1536;  // obstacle tables in global memory: deeper trees
+constexpr float kTriMargin = 2e-3f;  // triangle-box clearance, same as the two inflated tree boxes
 constexpr int kLeafTrisDev = 4;  // must match rc::kLeafTris of the host builder (rc_bvh.h)
 
 struct CulledArgs {
@@ -298,13 +299,27 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
                     xform(m, B.x, B.y, B.z, r.bx, r.by, r.bz);
                     xform(m, C.x, C.y, C.z, r.cx, r.cy, r.cz);
                     const Plane pr = plane_of(r);
+                    // AABB of the robot triangle, inflated like the tree boxes: a pair whose
+                    // triangle boxes are disjoint with clearance is skipped like a culled node pair
+                    // (it cuts the queued pairs four-fold: most pairs of two overlapping leaves are
+                    // themselves apart)
+                    const float rlx = fminf(fminf(r.ax, r.bx), r.cx) - kTriMargin,
+                                rly = fminf(fminf(r.ay, r.by), r.cy) - kTriMargin,
+                                rlz = fminf(fminf(r.az, r.bz), r.cz) - kTriMargin,
+                                rhx = fmaxf(fmaxf(r.ax, r.bx), r.cx) + kTriMargin,
+                                rhy = fmaxf(fmaxf(r.ay, r.by), r.cy) + kTriMargin,
+                                rhz = fmaxf(fmaxf(r.az, r.bz), r.cz) + kTriMargin;
 #pragma unroll
                     for (int q = 0; q < kLeafTrisDev; q++) {
                         const int k = ofirst + min(q, ocount - 1);
                         const float4 oa = obs_A(k), ob = obs_B(k), oc = obs_C(k);
                         bool pass = act && q < ocount &&
-                                    straddles(sdist(pr, oa.x, oa.y, oa.z), sdist(pr, ob.x, ob.y, ob.z),
-                                              sdist(pr, oc.x, oc.y, oc.z));
+                                    fminf(fminf(oa.x, ob.x), oc.x) <= rhx && fmaxf(fmaxf(oa.x, ob.x), oc.x) >= rlx &&
+                                    fminf(fminf(oa.y, ob.y), oc.y) <= rhy && fmaxf(fmaxf(oa.y, ob.y), oc.y) >= rly &&
+                                    fminf(fminf(oa.z, ob.z), oc.z) <= rhz && fmaxf(fmaxf(oa.z, ob.z), oc.z) >= rlz;
+                        if (pass)
+                            pass = straddles(sdist(pr, oa.x, oa.y, oa.z), sdist(pr, ob.x, ob.y, ob.z),
+                                             sdist(pr, oc.x, oc.y, oc.z));
                         if (pass) {
                             const Plane po = {oa.w, ob.w, oc.w, obs_D(k)};
                             pass = straddles(sdist(po, r.ax, r.ay, r.az), sdist(po, r.bx, r.by, r.bz),
@@ -448,7 +463,7 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
     // small chunks: the per-configuration cost varies 1:8 (cleared / full sweep / colliding)
     a.c.chunk = (int)max(1L, min(16L, n / ((long)grid * warps * 32)));
     a.tail_begin = (long)grid * warps * 4;
-    a.tail_thresh = 32; a.leaf_thresh = 8;
+    a.tail_thresh = 16; a.leaf_thresh = 8;
     const int sd = ctx->knob_seed_depth < 0 ? 2 : min(3, ctx->knob_seed_depth);
     a.n_seed_r = t.n_seed_r[sd]; a.n_seed_o = t.n_seed_o[sd];
     for (int q = 0; q < 8; q++) { a.seed_r[q] = t.seed_r[sd][q]; a.seed_o[q] = t.seed_o[sd][q]; }
