@@ -142,7 +142,7 @@ def run_reference(args):
     n_tot, t_tot = sum(v[0] for v in vals), sum(v[1] for v in vals)
     value = n_tot / t_tot
     info["value"] = value
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "collision-checked configs/sec", "value": value,
         "unit": "configs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_tot / max(1, args.steps), "higher_is_better": True,
@@ -153,11 +153,33 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "configs/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
+
+
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """The ONE JSON line goes to the real stdout; everything else any library prints on fd 1
+    (NCCL's version banner, for one) has been diverted to stderr."""
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
+def divert_stdout():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
 
 
 def main():
     args = parse()
+    divert_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -365,7 +387,7 @@ def main():
         from oracle import pyoracle as po
         out["cpu_baseline"], _, _ = cpu_reference_throughput(rc, po, confs, seconds=12.0)
 
-    print(json.dumps(out))
+    emit(out)
 
 
 if __name__ == "__main__":
