@@ -244,7 +244,7 @@ def main():
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
     value = world * n * args.steps / (total_ms * 1e-3)
-    launches = args.steps  # one kernel of ours per step (memsets and NCCL are not ours)
+    launches = 2 * args.steps  # two kernels of ours per step: classify + descent (memsets and NCCL are not ours)
 
     # ---- end to end: host buffers in, host flags out, through the public host call ---------------
     h_confs = torch.from_numpy(confs).pin_memory()

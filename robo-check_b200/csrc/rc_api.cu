@@ -93,6 +93,22 @@ int upload_obstacle(rc_ctx *ctx, const GatheredTris &g, float4 **a, float4 **b, 
 // context's private stream: work must land on the stream the caller times and orders.
 cudaStream_t stream_of(rc_ctx *, void *stream) { return static_cast<cudaStream_t>(stream); }
 
+int ensure_work_list(rc_ctx *ctx, long n)
+{
+    if (n <= ctx->work_cap) return RC_OK;
+    cudaDeviceSynchronize();  // an earlier asynchronous check may still use the old list
+    if (ctx->d_work_idx) cudaFree(ctx->d_work_idx);
+    if (ctx->d_work_mat) cudaFree(ctx->d_work_mat);
+    ctx->d_work_idx = nullptr; ctx->d_work_mat = nullptr; ctx->work_cap = 0;
+    const long cap = std::max(n, 1L << 17);
+    cudaError_t e;
+    if ((e = cudaMalloc(&ctx->d_work_idx, (size_t)cap * sizeof(uint32_t))) ||
+        (e = cudaMalloc(&ctx->d_work_mat, (size_t)cap * 3 * sizeof(float4))))
+        return check_cuda(ctx, e, "work list");
+    ctx->work_cap = cap;
+    return RC_OK;
+}
+
 int ensure_staging(rc_ctx *ctx, long n)
 {
     if (n <= ctx->stage_capacity) return RC_OK;
@@ -273,6 +289,7 @@ int rc_create(rc_ctx **out, const float *rob_x, const float *rob_y, const float 
             (e = upload(ctx, &t.rob_bvh, rbn)) || (e = upload(ctx, &t.obs_bvh, obn)) ||
             (e = dev_alloc(ctx, &ctx->d_counters, RC_NUM_COUNTERS)) ||
             (e = dev_alloc(ctx, &ctx->d_queues, kHostChunks)) ||
+            (e = dev_alloc(ctx, &ctx->d_work_count, 2)) ||
             (e = dev_alloc(ctx, &ctx->d_obs_box, 1)) ||
             (e = cudaMemcpy(ctx->d_obs_box, &t.obs_box, sizeof(rc_aabb), cudaMemcpyHostToDevice))) {
             rcode = check_cuda(ctx, e, "table upload");
@@ -317,6 +334,8 @@ void rc_destroy(rc_ctx *ctx)
     if (ctx->d_stage_confs) cudaFree(ctx->d_stage_confs);
     if (ctx->d_stage_valid) cudaFree(ctx->d_stage_valid);
     if (ctx->d_block_counts) cudaFree(ctx->d_block_counts);
+    if (ctx->d_work_idx) cudaFree(ctx->d_work_idx);
+    if (ctx->d_work_mat) cudaFree(ctx->d_work_mat);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -348,12 +367,17 @@ int rc_check(rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_valid, ui
     if (!ctx || n < 0 || (n > 0 && !d_confs) || (!d_valid && !d_bitmask)) return RC_ERR_INVALID;
     if (mode != RC_MODE_CULLED && mode != RC_MODE_BRUTE) return RC_ERR_INVALID;
     if (n == 0) return RC_OK;
+    if (n > 0xffffffffL) return RC_ERR_INVALID;
     cudaSetDevice(ctx->device);
+    if (mode == RC_MODE_CULLED) {
+        const int rcode = ensure_work_list(ctx, n);
+        if (rcode != RC_OK) return rcode;
+    }
     cudaError_t e = launch_check(ctx, d_confs, n, d_valid, d_bitmask, mode, ctx->stats_on,
                                  stream_of(ctx, stream), nullptr);
     if (e == cudaErrorInvalidConfiguration)
         return set_error(ctx, RC_ERR_UNSUPPORTED, "mesh tables do not fit in shared memory");
-    ctx->launches++;
+    ctx->launches += mode == RC_MODE_CULLED ? 2 : 1;
     return check_cuda(ctx, e, "rc_check launch");
 }
 
@@ -383,12 +407,13 @@ int rc_check_host(rc_ctx *ctx, const rc_config *h_confs, long n, uint8_t *h_vali
                              cudaMemcpyHostToDevice, s)))
         return check_cuda(ctx, e, "H2D configurations");
     cudaEventRecord(ctx->ev0, s);
+    if (mode == RC_MODE_CULLED && (rcode = ensure_work_list(ctx, n)) != RC_OK) return rcode;
     e = launch_check(ctx, ctx->d_stage_confs, n, ctx->d_stage_valid, nullptr, mode, ctx->stats_on, s,
                      ctx->d_queues);
     if (e == cudaErrorInvalidConfiguration)
         return set_error(ctx, RC_ERR_UNSUPPORTED, "mesh tables do not fit in shared memory");
     if (e) return check_cuda(ctx, e, "rc_check_host launch");
-    ctx->launches++;
+    ctx->launches += mode == RC_MODE_CULLED ? 2 : 1;
     cudaEventRecord(ctx->ev1, s);
     if ((e = cudaMemcpyAsync(dst, ctx->d_stage_valid, (size_t)n, cudaMemcpyDeviceToHost, s)) ||
         (e = cudaStreamSynchronize(s)))

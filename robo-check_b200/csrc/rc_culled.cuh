@@ -43,7 +43,11 @@ struct CulledArgs {
     uint32_t seed_r[8], seed_o[8];                   // traversal starts from this cut of both trees
     int n_seed_r, n_seed_o;
     int tail_thresh, leaf_thresh;
-    int stack_cap;                                         // <= compiled capacity (smaller only in tests)                          // queue fill levels that trigger a round
+    int stack_cap;                                         // <= compiled capacity (smaller only in tests)
+    // work list written by classify_kernel: configurations the cheap tests could not clear
+    const uint32_t *work_idx;
+    const float4 *work_mat;                                // three rows of [R | t] per entry
+    const unsigned long long *work_count;                          // queue fill levels that trigger a round
 };
 
 __device__ __forceinline__ bool boxes_overlap(const Mat34 &m, const float4 r0, const float4 r1,
@@ -97,6 +101,85 @@ __device__ __noinline__ bool narrow_exhaustive(const Mat34 m, const float4 *s_ro
     return hit;
 }
 
+// ---- step 1 of rc_check: one THREAD per configuration ------------------------------------------
+// Matrix (six libdevice sin/cos), bounding-sphere and rotated-bounding-box tests against the
+// obstacle AABB.  A configuration either is provably cleared by the broad phase -- flag byte and a
+// whole bitmask word per warp are written here, 24 B read + 1 B written per configuration, so this
+// step is HBM-bound -- or goes, with its matrix, onto the work list of the warp-per-configuration
+// kernel below.  Doing this per thread instead of per warp computes the trigonometry once per
+// configuration instead of 32 times.
+struct ClassifyArgs {
+    const rc_config *confs;
+    long n;
+    uint8_t *valid;
+    uint32_t *bitmask;
+    rc_aabb obs_box;
+    float sph_x, sph_y, sph_z, sph_r;
+    float box_cx, box_cy, box_cz, box_ex, box_ey, box_ez;
+    uint32_t *work_idx;
+    float4 *work_mat;
+    unsigned long long *work_count;
+    unsigned long long *counters;
+};
+
+template <bool STATS>
+__global__ void __launch_bounds__(256) classify_kernel(const ClassifyArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const long n32 = (a.n + 31) & ~31L;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n32; i += (long)gridDim.x * blockDim.x) {
+        const bool in = i < a.n;
+        const Mat34 m = load_matrix(a.confs, in ? i : a.n - 1);
+        const float sx = fmaf(m.r02, a.sph_z, fmaf(m.r01, a.sph_y, fmaf(m.r00, a.sph_x, m.tx)));
+        const float sy = fmaf(m.r12, a.sph_z, fmaf(m.r11, a.sph_y, fmaf(m.r10, a.sph_x, m.ty)));
+        const float sz = fmaf(m.r22, a.sph_z, fmaf(m.r21, a.sph_y, fmaf(m.r20, a.sph_x, m.tz)));
+        // the robot lies inside its bounding sphere; if the sphere's box clears the obstacle AABB
+        // with margin, so does the exact vertex AABB of the reference
+        const float hx = a.sph_r + 0.01f + 4e-6f * (fabsf(sx) + a.sph_r);
+        const float hy = a.sph_r + 0.01f + 4e-6f * (fabsf(sy) + a.sph_r);
+        const float hz = a.sph_r + 0.01f + 4e-6f * (fabsf(sz) + a.sph_r);
+        bool clear = sx - hx > a.obs_box.x_max || sx + hx < a.obs_box.x_min ||
+                     sy - hy > a.obs_box.y_max || sy + hy < a.obs_box.y_min ||
+                     sz - hz > a.obs_box.z_max || sz + hz < a.obs_box.z_min;
+        if (!clear) {
+            // ... and inside the world AABB of its rotated local bounding box
+            const float cx = fmaf(m.r02, a.box_cz, fmaf(m.r01, a.box_cy, fmaf(m.r00, a.box_cx, m.tx)));
+            const float cy = fmaf(m.r12, a.box_cz, fmaf(m.r11, a.box_cy, fmaf(m.r10, a.box_cx, m.ty)));
+            const float cz = fmaf(m.r22, a.box_cz, fmaf(m.r21, a.box_cy, fmaf(m.r20, a.box_cx, m.tz)));
+            const float ex = fmaf(fabsf(m.r02), a.box_ez, fmaf(fabsf(m.r01), a.box_ey, fabsf(m.r00) * a.box_ex));
+            const float ey = fmaf(fabsf(m.r12), a.box_ez, fmaf(fabsf(m.r11), a.box_ey, fabsf(m.r10) * a.box_ex));
+            const float ez = fmaf(fabsf(m.r22), a.box_ez, fmaf(fabsf(m.r21), a.box_ey, fabsf(m.r20) * a.box_ex));
+            const float gx = ex + 0.01f + 4e-6f * (fabsf(cx) + ex);
+            const float gy = ey + 0.01f + 4e-6f * (fabsf(cy) + ey);
+            const float gz = ez + 0.01f + 4e-6f * (fabsf(cz) + ez);
+            clear = cx - gx > a.obs_box.x_max || cx + gx < a.obs_box.x_min ||
+                    cy - gy > a.obs_box.y_max || cy + gy < a.obs_box.y_min ||
+                    cz - gz > a.obs_box.z_max || cz + gz < a.obs_box.z_min;
+        }
+        clear = clear && in;
+        const bool work = in && !clear;
+        const unsigned mc = __ballot_sync(kFull, clear), mw = __ballot_sync(kFull, work);
+        if (clear && a.valid) a.valid[i] = 1;
+        // the warp covers exactly one bitmask word: write it (the second kernel ORs its bits in)
+        if (lane == 0 && a.bitmask) a.bitmask[i >> 5] = mc;
+        if (mw) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(a.work_count, (unsigned long long)__popc(mw));
+            base = __shfl_sync(kFull, base, 0);
+            if (work) {
+                const unsigned long long pos = base + __popc(mw & lt);
+                a.work_idx[pos] = (uint32_t)i;
+                a.work_mat[3 * pos + 0] = make_float4(m.r00, m.r01, m.r02, m.tx);
+                a.work_mat[3 * pos + 1] = make_float4(m.r10, m.r11, m.r12, m.ty);
+                a.work_mat[3 * pos + 2] = make_float4(m.r20, m.r21, m.r22, m.tz);
+            }
+        }
+        if (STATS && lane == 0 && mc) atomicAdd(a.counters + CNT_SPHERE_CLEARED, (unsigned long long)__popc(mc));
+    }
+}
+
+// ---- step 2: one WARP per remaining configuration ------------------------------------------------
 // GOBS = obstacle tables (BVH + triangles) stay in global memory (L2-resident) instead of being
 // staged into shared memory: meshes of any size (BASELINE config 5, the subdivided obstacle).
 // Pair encodings then use 11 bits for the robot side and 21 bits for the obstacle side.
@@ -158,68 +241,39 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
     uint32_t *stack = s_work + warp * kWarpWork;
     uint32_t *leafq = stack + kStack;
     uint32_t *tailq = leafq + kLeafQCap;
-    unsigned long long st_broad = 0, st_sphere = 0, st_valid = 0, st_invalid = 0, st_nodes = 0,
+    unsigned long long st_broad = 0, st_valid = 0, st_invalid = 0, st_nodes = 0,
                        st_leaves = 0, st_tris = 0, st_over = 0, st_tails = 0, st_nr = 0, st_lr = 0, st_tr = 0;
 
-    // Guided self-scheduling: chunks of c.chunk configurations while plenty of work is left,
-    // single configurations near the end so that no warp is left holding a long chunk.
+    // Guided self-scheduling over the work list: chunks while plenty of work is left, single
+    // configurations near the end so that no warp is left holding a long chunk (the cost per
+    // configuration varies 1:4:6 between cleared / valid after the descent / colliding).
+    const long n_work = (long)*a.work_count;
+    const int chunk = (int)max(1L, min(16L, n_work / ((long)gridDim.x * WARPS * 32)));
     long seen = 0;
     for (;;) {
-        const int take = (seen + a.tail_begin < c.n) ? c.chunk : 1;
+        const int take = (seen + a.tail_begin < n_work) ? chunk : 1;
         long base = 0;
         if (lane == 0) base = (long)atomicAdd(c.queue, (unsigned long long)take);
         base = __shfl_sync(kFull, base, 0);
-        if (base >= c.n) break;
+        if (base >= n_work) break;
         seen = base;
-        const long end = min(base + (long)take, c.n);
-        for (long i = base; i < end; i++) {
-            const Mat34 m = load_matrix(c.confs, i);
-
-            // A0: the robot lies inside its bounding sphere; if the sphere's box clears the
-            // obstacle AABB with margin, so does the exact vertex AABB of the reference.
+        const long end = min(base + (long)take, n_work);
+        for (long w = base; w < end; w++) {
+            const long i = (long)__ldg(a.work_idx + w);
+            Mat34 m;
             {
-                const float sx = fmaf(m.r02, a.sph_z, fmaf(m.r01, a.sph_y, fmaf(m.r00, a.sph_x, m.tx)));
-                const float sy = fmaf(m.r12, a.sph_z, fmaf(m.r11, a.sph_y, fmaf(m.r10, a.sph_x, m.ty)));
-                const float sz = fmaf(m.r22, a.sph_z, fmaf(m.r21, a.sph_y, fmaf(m.r20, a.sph_x, m.tz)));
-                const float gx = a.sph_r + 0.01f + 4e-6f * (fabsf(sx) + a.sph_r);
-                const float gy = a.sph_r + 0.01f + 4e-6f * (fabsf(sy) + a.sph_r);
-                const float gz = a.sph_r + 0.01f + 4e-6f * (fabsf(sz) + a.sph_r);
-                const bool clear = sx - gx > c.obs_box.x_max || sx + gx < c.obs_box.x_min ||
-                                   sy - gy > c.obs_box.y_max || sy + gy < c.obs_box.y_min ||
-                                   sz - gz > c.obs_box.z_max || sz + gz < c.obs_box.z_min;
-                if (clear) {
-                    publish(c, i, true, lane);
-                    if (STATS) st_sphere++;
-                    continue;
-                }
+                const float4 q0 = __ldg(a.work_mat + 3 * w), q1 = __ldg(a.work_mat + 3 * w + 1),
+                             q2 = __ldg(a.work_mat + 3 * w + 2);
+                m.r00 = q0.x; m.r01 = q0.y; m.r02 = q0.z; m.tx = q0.w;
+                m.r10 = q1.x; m.r11 = q1.y; m.r12 = q1.z; m.ty = q1.w;
+                m.r20 = q2.x; m.r21 = q2.y; m.r22 = q2.z; m.tz = q2.w;
             }
 
-            // A: exact broad-phase flag.  Two shortcuts decide it without the full vertex sweep:
-            //  - the world AABB of the robot's local bounding box contains the exact vertex AABB;
-            //    if it clears the obstacle AABB with margin the configuration is valid;
-            //  - if ANY exactly-transformed robot vertex lies inside the obstacle AABB, the two
-            //    AABBs overlap on every axis (robot.min <= v <= obstacle.max, obstacle.min <= v <=
-            //    robot.max), so the broad phase cannot clear it.
-            // Otherwise the lanes transform all vertices and reduce the exact AABB.
-            {
-                const float cx = fmaf(m.r02, a.box_cz, fmaf(m.r01, a.box_cy, fmaf(m.r00, a.box_cx, m.tx)));
-                const float cy = fmaf(m.r12, a.box_cz, fmaf(m.r11, a.box_cy, fmaf(m.r10, a.box_cx, m.ty)));
-                const float cz = fmaf(m.r22, a.box_cz, fmaf(m.r21, a.box_cy, fmaf(m.r20, a.box_cx, m.tz)));
-                const float ex = fmaf(fabsf(m.r02), a.box_ez, fmaf(fabsf(m.r01), a.box_ey, fabsf(m.r00) * a.box_ex));
-                const float ey = fmaf(fabsf(m.r12), a.box_ez, fmaf(fabsf(m.r11), a.box_ey, fabsf(m.r10) * a.box_ex));
-                const float ez = fmaf(fabsf(m.r22), a.box_ez, fmaf(fabsf(m.r21), a.box_ey, fabsf(m.r20) * a.box_ex));
-                const float gx = ex + 0.01f + 4e-6f * (fabsf(cx) + ex);
-                const float gy = ey + 0.01f + 4e-6f * (fabsf(cy) + ey);
-                const float gz = ez + 0.01f + 4e-6f * (fabsf(cz) + ez);
-                const bool clear = cx - gx > c.obs_box.x_max || cx + gx < c.obs_box.x_min ||
-                                   cy - gy > c.obs_box.y_max || cy + gy < c.obs_box.y_min ||
-                                   cz - gz > c.obs_box.z_max || cz + gz < c.obs_box.z_min;
-                if (clear) {
-                    publish(c, i, true, lane);
-                    if (STATS) st_sphere++;
-                    continue;
-                }
-            }
+            // A: exact broad-phase flag.  If ANY exactly-transformed robot vertex lies inside the
+            // obstacle AABB, the two AABBs overlap on every axis (robot.min <= v <= obstacle.max,
+            // obstacle.min <= v <= robot.max), so the broad phase cannot clear the configuration:
+            // 32 probe vertices are tried first.  Otherwise the lanes transform all vertices and
+            // reduce the exact AABB.
             bool certain_overlap;
             {
                 const float4 p = s_rob_v[lane * a.probe_stride];
@@ -392,7 +446,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
         for (int o = 16; o > 0; o >>= 1) st_tris += __shfl_xor_sync(kFull, st_tris, o);
         if (lane == 0) {
             atomicAdd(c.counters + CNT_BROAD_CLEARED, st_broad);
-            atomicAdd(c.counters + CNT_SPHERE_CLEARED, st_sphere);
             atomicAdd(c.counters + CNT_NARROW_VALID, st_valid);
             atomicAdd(c.counters + CNT_NARROW_INVALID, st_invalid);
             atomicAdd(c.counters + CNT_NODE_PAIRS, st_nodes);
@@ -461,7 +514,7 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
     a.probe_stride = max(1, t.n_rob_v / 32);
     const int grid = ctx->sm_count;
     // small chunks: the per-configuration cost varies 1:8 (cleared / full sweep / colliding)
-    a.c.chunk = (int)max(1L, min(16L, n / ((long)grid * warps * 32)));
+    a.c.chunk = 1;  // the list-driven kernel sizes its chunks from the work count on the device
     a.tail_begin = (long)grid * warps * 4;
     a.tail_thresh = 16; a.leaf_thresh = 8;
     const int sd = ctx->knob_seed_depth < 0 ? 2 : min(3, ctx->knob_seed_depth);
@@ -471,9 +524,27 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
     if (ctx->knob_stack_cap > 0) a.stack_cap = max(64, min(a.stack_cap, ctx->knob_stack_cap));
     if (ctx->knob_tail > 0) a.tail_thresh = min(32, ctx->knob_tail);
     if (ctx->knob_leaf > 0) a.leaf_thresh = min(8, ctx->knob_leaf);
-    if (ctx->knob_chunk > 0) a.c.chunk = min(16, ctx->knob_chunk);
+    a.work_idx = ctx->d_work_idx; a.work_mat = ctx->d_work_mat; a.work_count = ctx->d_work_count;
+    if (!ctx->d_work_idx || ctx->work_cap < n) return cudaErrorMemoryAllocation;  // rc_check sizes it
+
+    // step 1: classify (thread per configuration); writes every bitmask word, so no memset
+    ClassifyArgs k;
+    k.confs = d_confs; k.n = n; k.valid = d_valid; k.bitmask = d_bitmask; k.obs_box = t.obs_box;
+    k.sph_x = a.sph_x; k.sph_y = a.sph_y; k.sph_z = a.sph_z; k.sph_r = a.sph_r;
+    k.box_cx = a.box_cx; k.box_cy = a.box_cy; k.box_cz = a.box_cz;
+    k.box_ex = a.box_ex; k.box_ey = a.box_ey; k.box_ez = a.box_ez;
+    k.work_idx = ctx->d_work_idx; k.work_mat = ctx->d_work_mat; k.work_count = ctx->d_work_count;
+    k.counters = ctx->d_counters;
+    cudaError_t e = cudaMemsetAsync(ctx->d_work_count, 0, sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) return e;
+    const int cgrid = (int)min((n + 255) / 256, (long)ctx->sm_count * 64);
+    if (want_stats) classify_kernel<true><<<cgrid, 256, 0, stream>>>(k);
+    else classify_kernel<false><<<cgrid, 256, 0, stream>>>(k);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+
+    // step 2: the remaining configurations, one warp each
     void (*kern)(const CulledArgs) = gobs ? pick_culled<true>(warps, want_stats) : pick_culled<false>(warps, want_stats);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, warps * 32, smem, stream>>>(a);
     return cudaGetLastError();

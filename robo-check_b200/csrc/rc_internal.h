@@ -67,6 +67,11 @@ struct rc_ctx {
     long stage_capacity = 0;
     cudaStream_t own_stream = nullptr, own_stream2 = nullptr;
     cudaEvent_t ev_join = nullptr;
+    // work list between the two kernels of rc_check, grown on demand to the largest n seen
+    uint32_t *d_work_idx = nullptr;
+    float4 *d_work_mat = nullptr;
+    unsigned long long *d_work_count = nullptr;
+    long work_cap = 0;
     uint32_t *d_block_counts = nullptr;        // scratch of rc_compact, grown on demand
     long block_counts_cap = 0;
     unsigned long long *d_queues = nullptr;    // [kHostChunks] work-queue counters of rc_check_host

@@ -9,6 +9,7 @@
 //   check_culled_kernel  same result, BVH-culled (rc_culled.cuh).
 //   stage kernels        the un-fused stage API (transform / AABB / broad / narrow).
 #include <float.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "rc_device.cuh"
@@ -303,7 +304,7 @@ cudaError_t launch_check(const rc_ctx *ctx, const rc_config *d_confs, long n, ui
     if (n <= 0) return cudaSuccess;
     if ((e = cudaMemsetAsync(queue, 0, sizeof(unsigned long long), stream)) != cudaSuccess)
         return e;
-    if (d_bitmask &&
+    if (d_bitmask && mode == RC_MODE_BRUTE &&
         (e = cudaMemsetAsync(d_bitmask, 0, (size_t)((n + 31) / 32) * 4, stream)) != cudaSuccess)
         return e;
 
