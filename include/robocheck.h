@@ -159,10 +159,18 @@ typedef struct {
     unsigned long long broad_cleared, sphere_cleared, narrow_valid, narrow_invalid;
     unsigned long long node_pairs, leaf_pairs, tri_pairs, tail_pairs, overflow, launches;
     unsigned long long node_rounds, leaf_rounds, tail_rounds; /* warp steps of each phase */
+    unsigned long long shared_pieces;  /* parts of a descent one warp handed to another */
+    unsigned long long watchdog, watchdog_where; /* hand-over waits that gave up: must be 0 */
 } rc_stats;
 /* Statistics of rc_check calls since the last reset; counting is off by default. */
 int rc_stats_enable(rc_ctx *ctx, int on);
 int rc_stats_read(rc_ctx *ctx, rc_stats *out, int reset);
+/* Per-configuration trace of the descent step of RC_MODE_CULLED, written while statistics are
+ * enabled, four words per configuration i: [0] SM cycles its warp spent on it (0 if step 1 cleared
+ * it), [1] low 32 bits of the device's nanosecond timer when it was decided, [2] node rounds << 16 |
+ * leaf rounds, [3] tail rounds << 16 | deepest pair stack (rounds of the owning warp only).  The
+ * caller zero-fills 4*n words of device memory; NULL switches the trace off. */
+int rc_stats_trace(rc_ctx *ctx, uint32_t *d_trace);
 /* CUDA-event time of the kernels of the last rc_check_host call, milliseconds. */
 float rc_last_kernel_ms(const rc_ctx *ctx);
 /* Sustained FP32 FMA rate of the device, TFLOP/s (2 flop per FMA), measured by a register-

@@ -13,7 +13,7 @@ launches)
 full)
   python profiles/prof_driver.py all > gpurun_out/plain.log 2>&1 &&
   ncu --set full --clock-control none --import-source on \
-      -k regex:"check_culled|check_brute|transform_soa|transform_aos|aabb_|narrow_soa|broad_kernel" -c 14 \
+      -k regex:"classify|check_culled|check_brute|transform_soa|transform_aos|aabb_|narrow_soa|broad_kernel" -c 18 \
       -o gpurun_out/prof_full python profiles/prof_driver.py all > gpurun_out/ncu_full.log 2>&1
   ;;
 esac

@@ -39,7 +39,7 @@ class rc_stats(C.Structure):
     _fields_ = [(k, C.c_ulonglong) for k in (
         "broad_cleared", "sphere_cleared", "narrow_valid", "narrow_invalid", "node_pairs",
         "leaf_pairs", "tri_pairs", "tail_pairs", "overflow", "launches", "node_rounds",
-        "leaf_rounds", "tail_rounds")]
+        "leaf_rounds", "tail_rounds", "shared_pieces", "watchdog", "watchdog_where")]
 
 
 # every symbol include/robocheck.h declares: (name, restype, argtypes)
@@ -73,6 +73,7 @@ ABI = [
     ("rc_check_spheres", _i, [_vp, _vp, _l, _vp, _vp, _vp]),
     ("rc_stats_enable", _i, [_vp, _i]),
     ("rc_stats_read", _i, [_vp, C.POINTER(rc_stats), _i]),
+    ("rc_stats_trace", _i, [_vp, _vp]),
     ("rc_last_kernel_ms", _f, [_vp]),
     ("rc_measure_fp32_peak", _i, [_vp, C.POINTER(C.c_double)]),
     ("rc_mesh_load_obj", _i, [C.c_char_p, _pp]),
@@ -424,6 +425,10 @@ class Context:
     # measurement -----------------------------------------------------------------------------------
     def stats_enable(self, on=True):
         _check(_lib.rc_stats_enable(self._h, 1 if on else 0), self._h)
+
+    def stats_trace(self, d_trace):
+        """d_trace: zero-filled device tensor of 4*n uint32/int32 words, or None to switch it off."""
+        _check(_lib.rc_stats_trace(self._h, _ptr(d_trace) if d_trace is not None else None), self._h)
 
     def stats(self, reset=False):
         s = rc_stats()

@@ -195,6 +195,8 @@ int rc_create(rc_ctx **out, const float *rob_x, const float *rob_y, const float 
         ctx->knob_chunk = knob("RC_CHUNK", 0);
         ctx->knob_stack_cap = knob("RC_STACK_CAP", 0);
         ctx->knob_global_obstacle = getenv("RC_FORCE_GLOBAL_OBSTACLE") != nullptr;
+        ctx->knob_share = knob("RC_SHARE", 1);
+        ctx->knob_pdl = knob("RC_PDL", 0);
     }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
@@ -289,7 +291,7 @@ int rc_create(rc_ctx **out, const float *rob_x, const float *rob_y, const float 
             (e = upload(ctx, &t.rob_bvh, rbn)) || (e = upload(ctx, &t.obs_bvh, obn)) ||
             (e = dev_alloc(ctx, &ctx->d_counters, RC_NUM_COUNTERS)) ||
             (e = dev_alloc(ctx, &ctx->d_queues, kHostChunks)) ||
-            (e = dev_alloc(ctx, &ctx->d_work_count, 2)) ||
+            (e = dev_alloc(ctx, &ctx->d_work_count, 4)) ||
             (e = dev_alloc(ctx, &ctx->d_obs_box, 1)) ||
             (e = cudaMemcpy(ctx->d_obs_box, &t.obs_box, sizeof(rc_aabb), cudaMemcpyHostToDevice))) {
             rcode = check_cuda(ctx, e, "table upload");
@@ -713,6 +715,13 @@ int rc_stats_enable(rc_ctx *ctx, int on)
     return RC_OK;
 }
 
+int rc_stats_trace(rc_ctx *ctx, uint32_t *d_trace)
+{
+    if (!ctx) return RC_ERR_INVALID;
+    ctx->d_trace = d_trace;
+    return RC_OK;
+}
+
 int rc_stats_read(rc_ctx *ctx, rc_stats *out, int reset)
 {
     if (!ctx || !out) return RC_ERR_INVALID;
@@ -729,6 +738,8 @@ int rc_stats_read(rc_ctx *ctx, rc_stats *out, int reset)
     out->overflow = h[CNT_OVERFLOW]; out->launches = ctx->launches;
     out->node_rounds = h[CNT_NODE_ROUNDS]; out->leaf_rounds = h[CNT_LEAF_ROUNDS];
     out->tail_rounds = h[CNT_TAIL_ROUNDS];
+    out->shared_pieces = h[CNT_SHARED];
+    out->watchdog = h[CNT_WATCHDOG]; out->watchdog_where = h[CNT_WATCHDOG_WHERE];
     if (reset) {
         ctx->launches = 0;
         if ((e = cudaMemset(ctx->d_counters, 0, sizeof h))) return check_cuda(ctx, e, "rc_stats reset");

@@ -10,8 +10,9 @@
 // geometrically disjoint with clearance; every surviving pair is decided with the exact reference
 // arithmetic (rc_device.cuh).  RC_MODE_BRUTE keeps the exhaustive sweep for audits.
 //
-// Per warp and configuration:
-//   A0  bounding-sphere pre-test against the obstacle AABB (clears far-away configurations)
+// Step 1 (classify_kernel, one thread per configuration): matrix, bounding-sphere and rotated-box
+// tests against the obstacle AABB; cleared configurations are written out, the rest go onto a work
+// list.  Step 2 (check_culled_kernel), per warp and listed configuration:
 //   A   all robot vertices transformed by the lanes, warp-shuffle AABB, exact broad-phase flag
 //   B   dual-tree descent: a LIFO of (robot node, obstacle node) pairs in shared memory, 32 pairs
 //       tested per step (one per lane), children appended with ballot/popc compaction
@@ -31,6 +32,23 @@ constexpr int kTailQCap = 160;   // pairs that passed both plane tests, finished
 constexpr int kStackCapGlobal = 1536;  // obstacle tables in global memory: deeper trees
 constexpr float kTriMargin = 2e-3f;  // triangle-box clearance, same as the two inflated tree boxes
 constexpr int kLeafTrisDev = 4;  // must match rc::kLeafTris of the host builder (rc_bvh.h)
+constexpr int kMailSlots = 4;    // per CTA: pieces of a deep descent handed to warps without work
+constexpr int kDonateMin = 64;   // node pairs on a warp's stack before it hands 32 of them out
+constexpr uint32_t kPendHit = 0x80000000u;
+constexpr uint32_t kWatchdogSpins = 1u << 22;  // x 256 ns: about a second
+constexpr uint32_t kAbortTicks = 8192;          // x 2^20 SM cycles: about four seconds after the CTA started
+
+struct __align__(16) Mail {
+    float4 m[3];         // [R | t] of the configuration
+    uint32_t pairs[32];  // node pairs
+    uint32_t state;      // 0 empty, 1 being filled, 2 full, 3 being emptied
+    uint32_t owner;      // warp that owns the configuration (index into s_pend)
+    uint32_t cnt;
+    uint32_t kind;       // 0 node pairs, 1 leaf pairs, 2 triangle pairs for the tail
+};
+
+__device__ __forceinline__ uint32_t ld_volatile(const uint32_t *p) { return *(const volatile uint32_t *)p; }
+__device__ __forceinline__ void st_volatile(uint32_t *p, uint32_t v) { *(volatile uint32_t *)p = v; }
 
 struct CulledArgs {
     CheckArgs c;                  // rob_t / obs_* point at the BVH-ordered tables
@@ -44,10 +62,12 @@ struct CulledArgs {
     int n_seed_r, n_seed_o;
     int tail_thresh, leaf_thresh;
     int stack_cap;                                         // <= compiled capacity (smaller only in tests)
+    int share;                                             // 0: no hand-over between the warps of a CTA
     // work list written by classify_kernel: configurations the cheap tests could not clear
     const uint32_t *work_idx;
     const float4 *work_mat;                                // three rows of [R | t] per entry
-    const unsigned long long *work_count;                          // queue fill levels that trigger a round
+    uint32_t *trace;                 // rc_stats_trace, STATS kernels only
+    unsigned long long *work_count;  // [0] list length  [1] next entry  [2] CTAs finished (self-resetting)
 };
 
 __device__ __forceinline__ bool boxes_overlap(const Mat34 &m, const float4 r0, const float4 r1,
@@ -125,6 +145,9 @@ struct ClassifyArgs {
 template <bool STATS>
 __global__ void __launch_bounds__(256) classify_kernel(const ClassifyArgs a)
 {
+    // the descent kernel is launched with programmatic stream serialisation: let its CTAs start
+    // staging the mesh tables while this grid is still running (they wait before reading the list)
+    asm volatile("griddepcontrol.launch_dependents;");
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const long n32 = (a.n + 31) & ~31L;
@@ -202,6 +225,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
     float *s_obs_d = reinterpret_cast<float *>(s_obs_c + (GOBS ? 0 : c.n_obs_t));
     uint2 *s_rob_t = reinterpret_cast<uint2 *>(s_obs_d + (GOBS ? 0 : pad4(c.n_obs_t)));
     uint32_t *s_work = reinterpret_cast<uint32_t *>(s_rob_t + c.n_rob_t + (c.n_rob_t & 1));
+    Mail *s_mail = reinterpret_cast<Mail *>(s_work + WARPS * kWarpWork);
+    uint32_t *s_pend = reinterpret_cast<uint32_t *>(s_mail + kMailSlots);
+    uint32_t *s_idle = s_pend + WARPS;
+    uint32_t *s_t0 = s_idle + 1;  // kernel start, SM clock >> 20 (the hand-over code never waits longer than kAbortTicks)
     // obstacle accessors: shared memory, or the read-only global path
     auto obs_node = [&](int nb, int half) -> float4 {
         if constexpr (GOBS) return __ldg(a.obs_bvh + 2 * nb + half);
@@ -216,6 +243,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
         mbar_init(bar, 1);
         mbar_fence_init();
     }
+    if (threadIdx.x < kMailSlots) s_mail[threadIdx.x].state = 0u;
+    if (threadIdx.x <= WARPS) s_pend[threadIdx.x] = 0u;  // the last one is s_idle
+    if (threadIdx.x == 0) *s_t0 = (uint32_t)(clock64() >> 20);
     __syncthreads();
     if (threadIdx.x == 0) {
         const uint32_t bv = c.n_rob_v_pad * 16u, bo = c.n_obs_t * 16u,
@@ -234,6 +264,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
             tma_load_1d(s_obs_d, c.obs_d, bd, bar);
         }
     }
+    // everything above reads only the static tables; the work list, the flags and the bitmask
+    // words come from classify_kernel: wait for that grid to complete (programmatic dependency)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     mbar_wait(bar, 0);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -242,28 +275,100 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
     uint32_t *leafq = stack + kStack;
     uint32_t *tailq = leafq + kLeafQCap;
     unsigned long long st_broad = 0, st_valid = 0, st_invalid = 0, st_nodes = 0,
-                       st_leaves = 0, st_tris = 0, st_over = 0, st_tails = 0, st_nr = 0, st_lr = 0, st_tr = 0;
+                       st_leaves = 0, st_tris = 0, st_over = 0, st_tails = 0, st_nr = 0, st_lr = 0, st_tr = 0, st_shared = 0;
 
     // Guided self-scheduling over the work list: chunks while plenty of work is left, single
-    // configurations near the end so that no warp is left holding a long chunk (the cost per
-    // configuration varies 1:4:6 between cleared / valid after the descent / colliding).
-    const long n_work = (long)*a.work_count;
-    const int chunk = (int)max(1L, min(16L, n_work / ((long)gridDim.x * WARPS * 32)));
-    long seen = 0;
+    // configurations near the end so that no warp is left holding a long chunk.  The cost of one
+    // configuration is heavy-tailed (median 9 k cycles, 1 % above 120 k, maximum 280 k = 40 % of
+    // the whole kernel), so once the list is dry the warps of a CTA SHARE what is left: a warp whose
+    // pair stack is deep hands its 32 oldest entries (the largest subtrees) to a mail slot in shared
+    // memory, warps without work of their own pick slots up and run the same descent on them.
+    // A configuration collides iff any of its pieces finds a hit; the owner waits for its pieces
+    // (s_pend: piece count + hit bit) and publishes the flag.
+    const uint32_t n_work = (uint32_t)__ldcg(a.work_count);
+    const uint32_t chunk = max(1u, min(16u, n_work / (gridDim.x * WARPS * 32u)));
+    uint32_t w_next = 0, w_end = 0;
+    bool dry = false;
     for (;;) {
-        const int take = (seen + a.tail_begin < n_work) ? chunk : 1;
-        long base = 0;
-        if (lane == 0) base = (long)atomicAdd(c.queue, (unsigned long long)take);
-        base = __shfl_sync(kFull, base, 0);
-        if (base >= n_work) break;
-        seen = base;
-        const long end = min(base + (long)take, n_work);
-        for (long w = base; w < end; w++) {
-            const long i = (long)__ldg(a.work_idx + w);
-            Mat34 m;
+        if (!dry && w_next >= w_end) {
+            const uint32_t take = ((unsigned long long)w_end + a.tail_begin < n_work) ? chunk : 1u;
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(a.work_count + 1, (unsigned long long)take);
+            base = __shfl_sync(kFull, base, 0);
+            if (base >= n_work) {
+                dry = true;
+                if (lane == 0) atomicAdd(s_idle, 1u);
+            } else {
+                w_next = (uint32_t)base;
+                w_end = (uint32_t)min(base + take, (unsigned long long)n_work);
+            }
+        }
+        Mat34 m;
+        long i = 0;
+        int owner = -1;       // >= 0: this warp works on a piece of that warp's configuration
+        bool sharing = false;  // pieces of the current configuration are (or were) out
+        int sp = 0, lq = 0, tq = 0;
+        long long t_begin = 0;
+        uint32_t tr_nodes = 0, tr_leaves = 0, tr_tails = 0, tr_maxsp = 0;  // rounds of the owner itself
+        if (STATS) t_begin = clock64();
+        auto trace = [&]() {
+            if (STATS && a.trace && lane == 0) {
+                unsigned long long ns;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+                a.trace[4 * i] = (uint32_t)(clock64() - t_begin);
+                a.trace[4 * i + 1] = (uint32_t)ns;
+                a.trace[4 * i + 2] = (tr_nodes << 16) | min(tr_leaves, 0xffffu);
+                a.trace[4 * i + 3] = (tr_tails << 16) | min(tr_maxsp, 0xffffu);
+            }
+        };
+        if (dry) {
+            // no configuration of its own any more: serve the mail slots until every warp of the
+            // CTA is in this state (owners get here only after their pieces have reported back)
+            int k;
+            for (uint32_t spins = 0;; spins++) {
+                k = -1;
+                if (lane == 0) {
+                    for (int q = 0; q < kMailSlots; q++)
+                        if (ld_volatile(&s_mail[q].state) == 2u && atomicCAS(&s_mail[q].state, 2u, 3u) == 2u) {
+                            k = q;
+                            break;
+                        }
+                    if (k < 0 && ld_volatile(s_idle) == (uint32_t)WARPS) k = -2;
+                    if (k != -2 && (spins > kWatchdogSpins || ((k >= 0 || (spins & 1023u) == 1023u) &&
+                                    (uint32_t)(clock64() >> 20) - *s_t0 > kAbortTicks))) {  // cannot happen; never hang the device
+                        atomicAdd(c.counters + CNT_WATCHDOG, 1ULL);
+                        atomicOr(c.counters + CNT_WATCHDOG_WHERE, 1ULL);
+                        k = -2;
+                    }
+                }
+                k = __shfl_sync(kFull, k, 0);
+                if (k != -1) break;
+                __nanosleep(256);
+            }
+            if (k == -2) break;
+            __threadfence_block();
+            Mail &b = s_mail[k];
+            owner = (int)b.owner;
+            sharing = true;
             {
-                const float4 q0 = __ldg(a.work_mat + 3 * w), q1 = __ldg(a.work_mat + 3 * w + 1),
-                             q2 = __ldg(a.work_mat + 3 * w + 2);
+                const int cnt = (int)b.cnt, kind = (int)b.kind;
+                uint32_t *dst = kind == 0 ? stack : kind == 1 ? leafq : tailq;
+                if (lane < cnt) dst[lane] = b.pairs[lane];
+                if (kind == 0) sp = cnt; else if (kind == 1) lq = cnt; else tq = cnt;
+            }
+            m.r00 = b.m[0].x; m.r01 = b.m[0].y; m.r02 = b.m[0].z; m.tx = b.m[0].w;
+            m.r10 = b.m[1].x; m.r11 = b.m[1].y; m.r12 = b.m[1].z; m.ty = b.m[1].w;
+            m.r20 = b.m[2].x; m.r21 = b.m[2].y; m.r22 = b.m[2].z; m.tz = b.m[2].w;
+            __syncwarp();
+            __threadfence_block();
+            if (lane == 0) st_volatile(&s_mail[k].state, 0u);
+            __syncwarp();
+        } else {
+            const uint32_t w = w_next++;
+            i = (long)__ldcg(a.work_idx + w);
+            {
+                const float4 q0 = __ldcg(a.work_mat + 3 * w), q1 = __ldcg(a.work_mat + 3 * w + 1),
+                             q2 = __ldcg(a.work_mat + 3 * w + 2);
                 m.r00 = q0.x; m.r01 = q0.y; m.r02 = q0.z; m.tx = q0.w;
                 m.r10 = q1.x; m.r11 = q1.y; m.r12 = q1.z; m.ty = q1.w;
                 m.r20 = q2.x; m.r21 = q2.y; m.r22 = q2.z; m.tz = q2.w;
@@ -292,154 +397,259 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
                                 c.obs_box.z_max)) {
                     publish(c, i, true, lane);
                     if (STATS) st_broad++;
+                    trace();
                     continue;
                 }
             }
-
-            // B + C + D
             // the descent starts from a cut through both trees instead of (root, root): the top
             // levels almost always overlap here and would cost steps with a handful of lanes
-            int sp = a.n_seed_r * a.n_seed_o, lq = 0, tq = 0;
-            bool hit = false, overflow = false;
+            sp = a.n_seed_r * a.n_seed_o;
             for (int q = lane; q < sp; q += 32)
                 stack[q] = (a.seed_r[q / a.n_seed_o] << SH) | a.seed_o[q % a.n_seed_o];
             __syncwarp();
-            while (sp > 0 || lq > 0 || tq > 0) {
-                if (tq >= a.tail_thresh || (sp == 0 && lq == 0)) {
-                    // ---- D: finish up to 32 queued pairs, one per lane
-                    const int cnt = min(tq, 32);
-                    tq -= cnt;
-                    const bool act = lane < cnt;
-                    const uint32_t e = tailq[tq + (act ? lane : 0)];
-                    const uint2 ti = s_rob_t[e >> SH];
-                    const int k = (int)(e & LOW);
-                    const float4 A = s_rob_v[ti.x & 0xffffu], B = s_rob_v[ti.x >> 16], C = s_rob_v[ti.y];
-                    Tri r;
-                    xform(m, A.x, A.y, A.z, r.ax, r.ay, r.az);
-                    xform(m, B.x, B.y, B.z, r.bx, r.by, r.bz);
-                    xform(m, C.x, C.y, C.z, r.cx, r.cy, r.cz);
-                    const Plane pr = plane_of(r);
-                    const float4 oa = obs_A(k), ob = obs_B(k), oc = obs_C(k);
-                    const Tri o = {oa.x, oa.y, oa.z, ob.x, ob.y, ob.z, oc.x, oc.y, oc.z};
-                    const Plane po = {oa.w, ob.w, oc.w, obs_D(k)};
-                    const float dO0 = sdist(pr, o.ax, o.ay, o.az), dO1 = sdist(pr, o.bx, o.by, o.bz),
-                                dO2 = sdist(pr, o.cx, o.cy, o.cz);
-                    const float dR0 = sdist(po, r.ax, r.ay, r.az), dR1 = sdist(po, r.bx, r.by, r.bz),
-                                dR2 = sdist(po, r.cx, r.cy, r.cz);
-                    const bool h = act && pair_tail(r, pr, dR0, dR1, dR2, o, po, dO0, dO1, dO2);
-                    if (STATS) { st_tails += cnt; st_tr++; }
-                    if (__any_sync(kFull, h)) { hit = true; break; }
-                    __syncwarp();
-                    continue;
-                }
-                if (lq >= a.leaf_thresh || sp == 0) {
-                    // ---- C: up to eight leaf pairs, lane = (slot, robot triangle of the leaf)
-                    const int cnt = min(lq, 8);
-                    lq -= cnt;
-                    const int slot = lane >> 2, ri = lane & 3;
-                    bool act = slot < cnt;
-                    const uint32_t e = leafq[lq + (act ? slot : 0)];
-                    const int na = (int)(e >> SH), nb = (int)(e & LOW);
-                    const uint32_t rfirst = __float_as_uint(s_rob_bvh[2 * na].w) & 0x7fffffffu;
-                    const int rcount = (int)__float_as_uint(s_rob_bvh[2 * na + 1].w);
-                    const uint32_t ofirst = __float_as_uint(obs_node(nb, 0).w) & 0x7fffffffu;
-                    const int ocount = (int)__float_as_uint(obs_node(nb, 1).w);
-                    act = act && ri < rcount;
-                    const uint32_t j = rfirst + (act ? ri : 0);
-                    const uint2 ti = s_rob_t[j];
-                    const float4 A = s_rob_v[ti.x & 0xffffu], B = s_rob_v[ti.x >> 16], C = s_rob_v[ti.y];
-                    Tri r;
-                    xform(m, A.x, A.y, A.z, r.ax, r.ay, r.az);
-                    xform(m, B.x, B.y, B.z, r.bx, r.by, r.bz);
-                    xform(m, C.x, C.y, C.z, r.cx, r.cy, r.cz);
-                    const Plane pr = plane_of(r);
-                    // AABB of the robot triangle, inflated like the tree boxes: a pair whose
-                    // triangle boxes are disjoint with clearance is skipped like a culled node pair
-                    // (it cuts the queued pairs four-fold: most pairs of two overlapping leaves are
-                    // themselves apart)
-                    const float rlx = fminf(fminf(r.ax, r.bx), r.cx) - kTriMargin,
-                                rly = fminf(fminf(r.ay, r.by), r.cy) - kTriMargin,
-                                rlz = fminf(fminf(r.az, r.bz), r.cz) - kTriMargin,
-                                rhx = fmaxf(fmaxf(r.ax, r.bx), r.cx) + kTriMargin,
-                                rhy = fmaxf(fmaxf(r.ay, r.by), r.cy) + kTriMargin,
-                                rhz = fmaxf(fmaxf(r.az, r.bz), r.cz) + kTriMargin;
-#pragma unroll
-                    for (int q = 0; q < kLeafTrisDev; q++) {
-                        const int k = ofirst + min(q, ocount - 1);
-                        const float4 oa = obs_A(k), ob = obs_B(k), oc = obs_C(k);
-                        bool pass = act && q < ocount &&
-                                    fminf(fminf(oa.x, ob.x), oc.x) <= rhx && fmaxf(fmaxf(oa.x, ob.x), oc.x) >= rlx &&
-                                    fminf(fminf(oa.y, ob.y), oc.y) <= rhy && fmaxf(fmaxf(oa.y, ob.y), oc.y) >= rly &&
-                                    fminf(fminf(oa.z, ob.z), oc.z) <= rhz && fmaxf(fmaxf(oa.z, ob.z), oc.z) >= rlz;
-                        if (pass)
-                            pass = straddles(sdist(pr, oa.x, oa.y, oa.z), sdist(pr, ob.x, ob.y, ob.z),
-                                             sdist(pr, oc.x, oc.y, oc.z));
-                        if (pass) {
-                            const Plane po = {oa.w, ob.w, oc.w, obs_D(k)};
-                            pass = straddles(sdist(po, r.ax, r.ay, r.az), sdist(po, r.bx, r.by, r.bz),
-                                             sdist(po, r.cx, r.cy, r.cz));
-                        }
-                        const unsigned mp = __ballot_sync(kFull, pass);
-                        if (pass) tailq[tq + __popc(mp & lt)] = (j << SH) | (uint32_t)k;
-                        tq += __popc(mp);
-                    }
-                    if (STATS) { st_leaves += cnt; st_tris += (act ? ocount : 0); st_lr++; }
-                    __syncwarp();
-                    continue;
-                }
-                // ---- B: pop up to 32 node pairs, test, push children
-                const int cnt = min(sp, 32);
-                sp -= cnt;
-                const bool act = lane < cnt;
-                const uint32_t e = stack[sp + (act ? lane : 0)];
-                const int na = (int)(e >> SH), nb = (int)(e & LOW);
-                const float4 r0 = s_rob_bvh[2 * na], r1 = s_rob_bvh[2 * na + 1];
-                const float4 o0 = obs_node(nb, 0), o1 = obs_node(nb, 1);
-                const bool ov = act && boxes_overlap(m, r0, r1, o0, o1);
-                const uint32_t ra = __float_as_uint(r0.w), rb = __float_as_uint(r1.w);
-                const uint32_t oa = __float_as_uint(o0.w), ob = __float_as_uint(o1.w);
-                const bool la = (ra & 0x80000000u) != 0, lb = (oa & 0x80000000u) != 0;
-                if (STATS) { st_nodes += cnt; st_nr++; }
-                __syncwarp();  // everybody has read its entry before the slots are reused
-                const bool ll = ov && la && lb;
-                const unsigned mll = __ballot_sync(kFull, ll);
-                if (ll) leafq[lq + __popc(mll & lt)] = e;
-                lq += __popc(mll);
-                const bool two = ov && (la != lb), four = ov && !la && !lb;
-                const unsigned m2 = __ballot_sync(kFull, two), m4 = __ballot_sync(kFull, four);
-                const int total = 2 * __popc(m2) + 4 * __popc(m4);
-                if (sp + total > a.stack_cap) { overflow = true; break; }
-                const int off = sp + 2 * __popc(m2 & lt) + 4 * __popc(m4 & lt);
-                if (two) {
-                    if (la) {  // robot node is a leaf: descend the obstacle node
-                        stack[off] = ((uint32_t)na << SH) | oa;
-                        stack[off + 1] = ((uint32_t)na << SH) | ob;
-                    } else {
-                        stack[off] = (ra << SH) | (uint32_t)nb;
-                        stack[off + 1] = (rb << SH) | (uint32_t)nb;
-                    }
-                } else if (four) {
-                    stack[off] = (ra << SH) | oa;
-                    stack[off + 1] = (ra << SH) | ob;
-                    stack[off + 2] = (rb << SH) | oa;
-                    stack[off + 3] = (rb << SH) | ob;
-                }
-                sp += total;
-                __syncwarp();
-            }
-            if (overflow) {
-                if (STATS) st_over++;
-                if constexpr (GOBS)
-                    hit = narrow_exhaustive(m, s_rob_v, s_rob_t, c.n_rob_t, c.obs_a, c.obs_b, c.obs_c,
-                                            c.obs_d, c.n_obs_t, lane);
-                else
-                    hit = narrow_exhaustive(m, s_rob_v, s_rob_t, c.n_rob_t, s_obs_a, s_obs_b, s_obs_c,
-                                            s_obs_d, c.n_obs_t, lane);
-            }
-            __syncwarp();
-            publish(c, i, !hit, lane);
-            if (STATS) { if (hit) st_invalid++; else st_valid++; }
         }
+        const int pend_slot = owner >= 0 ? owner : warp;
+
+        // B + C + D
+        bool hit = false, overflow = false;
+        while (sp > 0 || lq > 0 || tq > 0) {
+            // ---- sharing (only once some warp of the CTA has run out of configurations): hand out
+            // a tail round's worth of triangle pairs (the longest rounds), else a leaf round's
+            // worth of leaf pairs, else up to half of the node pairs, oldest = largest subtrees
+            // (what other warps publish is read by lane 0 and broadcast: two lanes reading the same
+            // word at different moments could otherwise take different branches of this loop)
+            uint32_t seen = 0;
+            if (a.share) {
+                if (lane == 0) {
+                    seen = ld_volatile(s_idle) != 0u ? 1u : 0u;
+                    if (seen && sharing && (ld_volatile(&s_pend[pend_slot]) & kPendHit) != 0u) seen = 3u;
+                    if (seen && (uint32_t)(clock64() >> 20) - *s_t0 > kAbortTicks) seen = 4u;
+                }
+                seen = __shfl_sync(kFull, seen, 0);
+            }
+            if (seen & 2u) {
+                hit = true;  // another piece of this configuration has found a hit
+                break;
+            }
+            if (seen & 4u) {  // cannot happen; never hang the device
+                if (lane == 0) {
+                    atomicAdd(c.counters + CNT_WATCHDOG, 1ULL);
+                    atomicOr(c.counters + CNT_WATCHDOG_WHERE, 4ULL);
+                }
+                break;
+            }
+            if (seen) {
+                // a warp always keeps work for itself, so what it receives is never passed on
+                // untouched (a piece bouncing between idle warps would never be decided)
+                const int kind = (tq >= a.tail_thresh && (sp > 0 || lq > 0 || tq > 32)) ? 2
+                                 : lq >= 16 ? 1 : sp >= kDonateMin ? 0 : -1;
+                int k = -1;
+                if (kind >= 0 && lane == 0)
+                    for (int q = 0; q < kMailSlots; q++)
+                        if (ld_volatile(&s_mail[q].state) == 0u && atomicCAS(&s_mail[q].state, 0u, 1u) == 0u) {
+                            k = q;
+                            break;
+                        }
+                k = __shfl_sync(kFull, k, 0);
+                if (k >= 0) {
+                    Mail &b = s_mail[k];
+                    const int cnt = kind == 2 ? min(tq, 32) : kind == 1 ? 8 : 32;
+                    const int src = lane < cnt ? lane : 0;
+                    uint32_t out;
+                    if (kind == 2) {
+                        tq -= cnt;
+                        out = tailq[tq + src];
+                    } else if (kind == 1) {
+                        lq -= cnt;
+                        out = leafq[lq + src];
+                    } else {
+                        out = stack[src];
+                        const uint32_t top = stack[sp - cnt + src];  // the newest take their place
+                        __syncwarp();
+                        if (lane < cnt) stack[lane] = top;
+                        sp -= cnt;
+                    }
+                    if (lane < cnt) b.pairs[lane] = out;
+                    if (lane == 0) {
+                        b.m[0] = make_float4(m.r00, m.r01, m.r02, m.tx);
+                        b.m[1] = make_float4(m.r10, m.r11, m.r12, m.ty);
+                        b.m[2] = make_float4(m.r20, m.r21, m.r22, m.tz);
+                        b.owner = (uint32_t)pend_slot;
+                        b.cnt = (uint32_t)cnt;
+                        b.kind = (uint32_t)kind;
+                        atomicAdd(&s_pend[pend_slot], 1u);
+                    }
+                    if (STATS) st_shared++;
+                    sharing = true;
+                    __syncwarp();
+                    __threadfence_block();
+                    if (lane == 0) st_volatile(&s_mail[k].state, 2u);
+                    __syncwarp();
+                    continue;
+                }
+            }
+            if (tq >= a.tail_thresh || (sp == 0 && lq == 0)) {
+                // ---- D: finish up to 32 queued pairs, one per lane
+                const int cnt = min(tq, 32);
+                tq -= cnt;
+                const bool act = lane < cnt;
+                const uint32_t e = tailq[tq + (act ? lane : 0)];
+                const uint2 ti = s_rob_t[e >> SH];
+                const int k = (int)(e & LOW);
+                const float4 A = s_rob_v[ti.x & 0xffffu], B = s_rob_v[ti.x >> 16], C = s_rob_v[ti.y];
+                Tri r;
+                xform(m, A.x, A.y, A.z, r.ax, r.ay, r.az);
+                xform(m, B.x, B.y, B.z, r.bx, r.by, r.bz);
+                xform(m, C.x, C.y, C.z, r.cx, r.cy, r.cz);
+                const Plane pr = plane_of(r);
+                const float4 oa = obs_A(k), ob = obs_B(k), oc = obs_C(k);
+                const Tri o = {oa.x, oa.y, oa.z, ob.x, ob.y, ob.z, oc.x, oc.y, oc.z};
+                const Plane po = {oa.w, ob.w, oc.w, obs_D(k)};
+                const float dO0 = sdist(pr, o.ax, o.ay, o.az), dO1 = sdist(pr, o.bx, o.by, o.bz),
+                            dO2 = sdist(pr, o.cx, o.cy, o.cz);
+                const float dR0 = sdist(po, r.ax, r.ay, r.az), dR1 = sdist(po, r.bx, r.by, r.bz),
+                            dR2 = sdist(po, r.cx, r.cy, r.cz);
+                const bool h = act && pair_tail(r, pr, dR0, dR1, dR2, o, po, dO0, dO1, dO2);
+                if (STATS) { st_tails += cnt; st_tr++; tr_tails++; }
+                if (__any_sync(kFull, h)) { hit = true; break; }
+                __syncwarp();
+                continue;
+            }
+            if (lq >= a.leaf_thresh || sp == 0) {
+                // ---- C: up to eight leaf pairs, lane = (slot, robot triangle of the leaf)
+                const int cnt = min(lq, 8);
+                lq -= cnt;
+                const int slot = lane >> 2, ri = lane & 3;
+                bool act = slot < cnt;
+                const uint32_t e = leafq[lq + (act ? slot : 0)];
+                const int na = (int)(e >> SH), nb = (int)(e & LOW);
+                const uint32_t rfirst = __float_as_uint(s_rob_bvh[2 * na].w) & 0x7fffffffu;
+                const int rcount = (int)__float_as_uint(s_rob_bvh[2 * na + 1].w);
+                const uint32_t ofirst = __float_as_uint(obs_node(nb, 0).w) & 0x7fffffffu;
+                const int ocount = (int)__float_as_uint(obs_node(nb, 1).w);
+                act = act && ri < rcount;
+                const uint32_t j = rfirst + (act ? ri : 0);
+                const uint2 ti = s_rob_t[j];
+                const float4 A = s_rob_v[ti.x & 0xffffu], B = s_rob_v[ti.x >> 16], C = s_rob_v[ti.y];
+                Tri r;
+                xform(m, A.x, A.y, A.z, r.ax, r.ay, r.az);
+                xform(m, B.x, B.y, B.z, r.bx, r.by, r.bz);
+                xform(m, C.x, C.y, C.z, r.cx, r.cy, r.cz);
+                const Plane pr = plane_of(r);
+                // AABB of the robot triangle, inflated like the tree boxes: a pair whose
+                // triangle boxes are disjoint with clearance is skipped like a culled node pair
+                // (it cuts the queued pairs four-fold: most pairs of two overlapping leaves are
+                // themselves apart)
+                const float rlx = fminf(fminf(r.ax, r.bx), r.cx) - kTriMargin,
+                            rly = fminf(fminf(r.ay, r.by), r.cy) - kTriMargin,
+                            rlz = fminf(fminf(r.az, r.bz), r.cz) - kTriMargin,
+                            rhx = fmaxf(fmaxf(r.ax, r.bx), r.cx) + kTriMargin,
+                            rhy = fmaxf(fmaxf(r.ay, r.by), r.cy) + kTriMargin,
+                            rhz = fmaxf(fmaxf(r.az, r.bz), r.cz) + kTriMargin;
+#pragma unroll
+                for (int q = 0; q < kLeafTrisDev; q++) {
+                    const int k = ofirst + min(q, ocount - 1);
+                    const float4 oa = obs_A(k), ob = obs_B(k), oc = obs_C(k);
+                    bool pass = act && q < ocount &&
+                                fminf(fminf(oa.x, ob.x), oc.x) <= rhx && fmaxf(fmaxf(oa.x, ob.x), oc.x) >= rlx &&
+                                fminf(fminf(oa.y, ob.y), oc.y) <= rhy && fmaxf(fmaxf(oa.y, ob.y), oc.y) >= rly &&
+                                fminf(fminf(oa.z, ob.z), oc.z) <= rhz && fmaxf(fmaxf(oa.z, ob.z), oc.z) >= rlz;
+                    if (pass)
+                        pass = straddles(sdist(pr, oa.x, oa.y, oa.z), sdist(pr, ob.x, ob.y, ob.z),
+                                         sdist(pr, oc.x, oc.y, oc.z));
+                    if (pass) {
+                        const Plane po = {oa.w, ob.w, oc.w, obs_D(k)};
+                        pass = straddles(sdist(po, r.ax, r.ay, r.az), sdist(po, r.bx, r.by, r.bz),
+                                         sdist(po, r.cx, r.cy, r.cz));
+                    }
+                    const unsigned mp = __ballot_sync(kFull, pass);
+                    if (pass) tailq[tq + __popc(mp & lt)] = (j << SH) | (uint32_t)k;
+                    tq += __popc(mp);
+                }
+                if (STATS) { st_leaves += cnt; st_tris += (act ? ocount : 0); st_lr++; tr_leaves++; }
+                __syncwarp();
+                continue;
+            }
+            // ---- B: pop up to 32 node pairs, test, push children
+            const int cnt = min(sp, 32);
+            sp -= cnt;
+            const bool act = lane < cnt;
+            const uint32_t e = stack[sp + (act ? lane : 0)];
+            const int na = (int)(e >> SH), nb = (int)(e & LOW);
+            const float4 r0 = s_rob_bvh[2 * na], r1 = s_rob_bvh[2 * na + 1];
+            const float4 o0 = obs_node(nb, 0), o1 = obs_node(nb, 1);
+            const bool ov = act && boxes_overlap(m, r0, r1, o0, o1);
+            const uint32_t ra = __float_as_uint(r0.w), rb = __float_as_uint(r1.w);
+            const uint32_t oa = __float_as_uint(o0.w), ob = __float_as_uint(o1.w);
+            const bool la = (ra & 0x80000000u) != 0, lb = (oa & 0x80000000u) != 0;
+            if (STATS) { st_nodes += cnt; st_nr++; tr_nodes++; tr_maxsp = max(tr_maxsp, (uint32_t)(sp + cnt)); }
+            __syncwarp();  // everybody has read its entry before the slots are reused
+            const bool ll = ov && la && lb;
+            const unsigned mll = __ballot_sync(kFull, ll);
+            if (ll) leafq[lq + __popc(mll & lt)] = e;
+            lq += __popc(mll);
+            const bool two = ov && (la != lb), four = ov && !la && !lb;
+            const unsigned m2 = __ballot_sync(kFull, two), m4 = __ballot_sync(kFull, four);
+            const int total = 2 * __popc(m2) + 4 * __popc(m4);
+            if (sp + total > a.stack_cap) { overflow = true; break; }
+            const int off = sp + 2 * __popc(m2 & lt) + 4 * __popc(m4 & lt);
+            if (two) {
+                if (la) {  // robot node is a leaf: descend the obstacle node
+                    stack[off] = ((uint32_t)na << SH) | oa;
+                    stack[off + 1] = ((uint32_t)na << SH) | ob;
+                } else {
+                    stack[off] = (ra << SH) | (uint32_t)nb;
+                    stack[off + 1] = (rb << SH) | (uint32_t)nb;
+                }
+            } else if (four) {
+                stack[off] = (ra << SH) | oa;
+                stack[off + 1] = (ra << SH) | ob;
+                stack[off + 2] = (rb << SH) | oa;
+                stack[off + 3] = (rb << SH) | ob;
+            }
+            sp += total;
+            __syncwarp();
+        }
+        if (overflow) {
+            if (STATS) st_over++;
+            if constexpr (GOBS)
+                hit = narrow_exhaustive(m, s_rob_v, s_rob_t, c.n_rob_t, c.obs_a, c.obs_b, c.obs_c,
+                                        c.obs_d, c.n_obs_t, lane);
+            else
+                hit = narrow_exhaustive(m, s_rob_v, s_rob_t, c.n_rob_t, s_obs_a, s_obs_b, s_obs_c,
+                                        s_obs_d, c.n_obs_t, lane);
+        }
+        __syncwarp();
+        if (owner >= 0) {
+            // a piece: report to the owner of the configuration
+            if (lane == 0) {
+                if (hit) atomicOr(&s_pend[owner], kPendHit);
+                __threadfence_block();
+                atomicSub(&s_pend[owner], 1u);
+            }
+            continue;
+        }
+        if (sharing) {
+            // pieces of this configuration went out: wait for all of them, take over their verdict
+            uint32_t v = 0;
+            if (lane == 0) {
+                uint32_t spins = 0;
+                while (((v = ld_volatile(&s_pend[warp])) & ~kPendHit) != 0u) {
+                    if (++spins > 2u * kWatchdogSpins) {  // cannot happen; never hang the device
+                        atomicAdd(c.counters + CNT_WATCHDOG, 1ULL);
+                        atomicOr(c.counters + CNT_WATCHDOG_WHERE, 2ULL);
+                        break;
+                    }
+                    __nanosleep(128);
+                }
+                st_volatile(&s_pend[warp], 0u);
+            }
+            v = __shfl_sync(kFull, v, 0);
+            hit = hit || (v & kPendHit) != 0u;
+        }
+        publish(c, i, !hit, lane);
+        if (STATS) { if (hit) st_invalid++; else st_valid++; }
+        trace();
     }
     if (STATS) {
 #pragma unroll
@@ -456,6 +666,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
             atomicAdd(c.counters + CNT_NODE_ROUNDS, st_nr);
             atomicAdd(c.counters + CNT_LEAF_ROUNDS, st_lr);
             atomicAdd(c.counters + CNT_TAIL_ROUNDS, st_tr);
+            atomicAdd(c.counters + CNT_SHARED, st_shared);
+        }
+    }
+    // the last CTA to finish leaves the three counters at zero for the next call (no memset per
+    // call): every CTA has read the list length and drawn its last entry by the time it gets here
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(a.work_count + 2, 1ULL) == (unsigned long long)gridDim.x - 1ULL) {
+            a.work_count[0] = 0; a.work_count[1] = 0; a.work_count[2] = 0;
         }
     }
 }
@@ -467,6 +687,7 @@ static size_t culled_smem_bytes(const DeviceTables &t, int warps, bool gobs)
     if (!gobs)
         b += (size_t)t.n_obs_nodes * 32 + (size_t)t.n_obs_t * 48 + (size_t)pad4(t.n_obs_t) * 4;
     b += (size_t)warps * ((gobs ? kStackCapGlobal : kStackCap) + kLeafQCap + kTailQCap) * 4;
+    b = (b + 15) / 16 * 16 + kMailSlots * sizeof(Mail) + ((size_t)warps + 4) * 4;  // + s_pend, s_idle, s_t0
     return b;
 }
 
@@ -524,6 +745,8 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
     if (ctx->knob_stack_cap > 0) a.stack_cap = max(64, min(a.stack_cap, ctx->knob_stack_cap));
     if (ctx->knob_tail > 0) a.tail_thresh = min(32, ctx->knob_tail);
     if (ctx->knob_leaf > 0) a.leaf_thresh = min(8, ctx->knob_leaf);
+    a.share = ctx->knob_share;
+    a.trace = want_stats ? ctx->d_trace : nullptr;
     a.work_idx = ctx->d_work_idx; a.work_mat = ctx->d_work_mat; a.work_count = ctx->d_work_count;
     if (!ctx->d_work_idx || ctx->work_cap < n) return cudaErrorMemoryAllocation;  // rc_check sizes it
 
@@ -535,19 +758,27 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
     k.box_ex = a.box_ex; k.box_ey = a.box_ey; k.box_ez = a.box_ez;
     k.work_idx = ctx->d_work_idx; k.work_mat = ctx->d_work_mat; k.work_count = ctx->d_work_count;
     k.counters = ctx->d_counters;
-    cudaError_t e = cudaMemsetAsync(ctx->d_work_count, 0, sizeof(unsigned long long), stream);
+    void (*kern)(const CulledArgs) = gobs ? pick_culled<true>(warps, want_stats) : pick_culled<false>(warps, want_stats);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int cgrid = (int)min((n + 255) / 256, (long)ctx->sm_count * 64);
     if (want_stats) classify_kernel<true><<<cgrid, 256, 0, stream>>>(k);
     else classify_kernel<false><<<cgrid, 256, 0, stream>>>(k);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
 
-    // step 2: the remaining configurations, one warp each
-    void (*kern)(const CulledArgs) = gobs ? pick_culled<true>(warps, want_stats) : pick_culled<false>(warps, want_stats);
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    kern<<<grid, warps * 32, smem, stream>>>(a);
-    return cudaGetLastError();
+    // step 2: the remaining configurations, one warp each; programmatic dependent launch, so the
+    // CTAs are placed and stage their tables while the tail of step 1 is still running
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)(warps * 32));
+    cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = ctx->knob_pdl ? 1 : 0;
+    e = cudaLaunchKernelEx(&cfg, kern, a);
+    if (e != cudaSuccess)  // the list counters were filled by step 1 and nobody will reset them
+        cudaMemsetAsync(ctx->d_work_count, 0, 3 * sizeof(unsigned long long), stream);
+    return e;
 }
 
 }  // namespace rc

@@ -59,6 +59,7 @@ struct rc_ctx {
     unsigned long long *d_counters = nullptr;  // [RC_NUM_COUNTERS] work queue + statistics
     rc_aabb *d_obs_box = nullptr;              // obstacle AABB on the device (broad-phase stage)
     int stats_on = 0;
+    uint32_t *d_trace = nullptr;               // rc_stats_trace (caller's memory)
     unsigned long long launches = 0;           // kernels launched through this context
     rc_config *d_stage_confs = nullptr;        // device staging for rc_check_host
     uint8_t *d_stage_valid = nullptr;
@@ -82,6 +83,8 @@ struct rc_ctx {
     int knob_warps = 0, knob_seed_depth = -1, knob_tail = 0, knob_leaf = 0, knob_chunk = 0;
     int knob_stack_cap = 0;  // RC_STACK_CAP: shrink the pair stack to exercise the overflow fallback
     bool knob_global_obstacle = false;
+    int knob_pdl = 0;        // RC_PDL=1: programmatic dependent launch of the descent step
+    int knob_share = 1;      // RC_SHARE=0: warps of a CTA do not hand pieces of a deep descent to each other
     std::string last_error;
     std::vector<void *> allocations;
 };
@@ -103,7 +106,10 @@ enum Counter {
     CNT_NODE_ROUNDS,
     CNT_LEAF_ROUNDS,
     CNT_TAIL_ROUNDS,
-    RC_NUM_COUNTERS = 16
+    CNT_SHARED,           // pieces of a descent handed from one warp to another
+    CNT_WATCHDOG,         // spin loops of the hand-over protocol that gave up (always counted; must stay 0)
+    CNT_WATCHDOG_WHERE,   // bit 0: serve loop, bit 1: owner waiting for its pieces
+    RC_NUM_COUNTERS = 24
 };
 constexpr int kHostChunks = 8;
 

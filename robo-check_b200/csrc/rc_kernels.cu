@@ -9,7 +9,6 @@
 //   check_culled_kernel  same result, BVH-culled (rc_culled.cuh).
 //   stage kernels        the un-fused stage API (transform / AABB / broad / narrow).
 #include <float.h>
-#include <stdio.h>
 #include <stdlib.h>
 
 #include "rc_device.cuh"
@@ -302,7 +301,9 @@ cudaError_t launch_check(const rc_ctx *ctx, const rc_config *d_confs, long n, ui
     const DeviceTables &t = ctx->t;
     cudaError_t e;
     if (n <= 0) return cudaSuccess;
-    if ((e = cudaMemsetAsync(queue, 0, sizeof(unsigned long long), stream)) != cudaSuccess)
+    // the culled path keeps its own self-resetting counters
+    if (mode == RC_MODE_BRUTE &&
+        (e = cudaMemsetAsync(queue, 0, sizeof(unsigned long long), stream)) != cudaSuccess)
         return e;
     if (d_bitmask && mode == RC_MODE_BRUTE &&
         (e = cudaMemsetAsync(d_bitmask, 0, (size_t)((n + 31) / 32) * 4, stream)) != cudaSuccess)
