@@ -27,6 +27,8 @@ torch.cuda.synchronize()
 ctx.stats_trace(None)
 ctx.stats_enable(False)
 t = d_trace.cpu().numpy().view(np.uint32).reshape(n, 4)
+if os.environ.get("RC_TRACE_DUMP"):
+    np.savez_compressed(os.environ["RC_TRACE_DUMP"], trace=t, valid=d_valid.cpu().numpy(), confs=confs)
 v = d_valid.cpu().numpy()
 cyc, ns = t[:, 0].astype(np.int64), t[:, 1].astype(np.int64)
 listed = cyc > 0

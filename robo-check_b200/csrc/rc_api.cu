@@ -31,6 +31,8 @@ namespace {
 
 // culling boxes are inflated by this much on each side (scene extent is ~90 units)
 constexpr float kBoxMargin = 1e-3f;
+// groups of robot vertices whose rotated boxes bound the vertex AABB in classify_kernel
+constexpr int kBoundBoxes = 64;
 
 template <class T>
 cudaError_t dev_alloc(rc_ctx *ctx, T **p, size_t count)
@@ -52,6 +54,62 @@ cudaError_t upload(rc_ctx *ctx, T **p, const std::vector<T> &h, size_t padded_co
     if (e != cudaSuccess) return e;
     if (h.empty()) return cudaSuccess;
     return cudaMemcpy(*p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+// k-d partition of the robot's vertices into at most `want` groups (median split on the longest
+// axis); returns (centre, half extent) per group, extents measured from the rounded centre and
+// rounded up.  Every vertex -- referenced by a triangle or not -- is inside exactly one box, so
+// the union of the rotated boxes contains the exact vertex AABB of broadPhaseFusedKernel_sep.
+std::vector<float4> vertex_bound_boxes(const float *x, const float *y, const float *z, int n, int want)
+{
+    std::vector<float4> out;
+    if (n <= 0) return out;
+    std::vector<int> idx((size_t)n);
+    for (int i = 0; i < n; i++) idx[i] = i;
+    struct Range { int lo, hi; };
+    std::vector<Range> groups{{0, n}};
+    const float *c[3] = {x, y, z};
+    auto extent = [&](const Range &r, double lo[3], double hi[3]) {
+        for (int k = 0; k < 3; k++) { lo[k] = 1e300; hi[k] = -1e300; }
+        for (int i = r.lo; i < r.hi; i++)
+            for (int k = 0; k < 3; k++) {
+                lo[k] = std::min(lo[k], (double)c[k][idx[i]]);
+                hi[k] = std::max(hi[k], (double)c[k][idx[i]]);
+            }
+    };
+    while ((int)groups.size() < want) {
+        // split the group with the longest box edge
+        int best = -1, best_ax = 0;
+        double best_len = 0;
+        for (size_t g = 0; g < groups.size(); g++) {
+            if (groups[g].hi - groups[g].lo < 2) continue;
+            double lo[3], hi[3];
+            extent(groups[g], lo, hi);
+            for (int k = 0; k < 3; k++)
+                if (hi[k] - lo[k] > best_len) { best_len = hi[k] - lo[k]; best = (int)g; best_ax = k; }
+        }
+        if (best < 0) break;
+        const Range r = groups[best];
+        const int mid = (r.lo + r.hi) / 2;
+        const float *key = c[best_ax];
+        std::nth_element(idx.begin() + r.lo, idx.begin() + mid, idx.begin() + r.hi,
+                         [&](int a, int b) { return key[a] < key[b] || (key[a] == key[b] && a < b); });
+        groups[best] = Range{r.lo, mid};
+        groups.push_back(Range{mid, r.hi});
+    }
+    for (const Range &r : groups) {
+        double lo[3], hi[3];
+        extent(r, lo, hi);
+        float cen[3], ext[3];
+        for (int k = 0; k < 3; k++) {
+            cen[k] = (float)(0.5 * (lo[k] + hi[k]));
+            const double e = std::max(hi[k] - (double)cen[k], (double)cen[k] - lo[k]);
+            ext[k] = (float)(e * (1.0 + 1e-6)) + 1e-5f;
+        }
+        out.push_back(make_float4(cen[0], cen[1], cen[2], 0.f));
+        out.push_back(make_float4(ext[0], ext[1], ext[2], 0.f));
+    }
+    return out;
 }
 
 struct GatheredTris {
@@ -102,7 +160,7 @@ int ensure_work_list(rc_ctx *ctx, long n)
     ctx->d_work_idx = nullptr; ctx->d_work_mat = nullptr; ctx->work_cap = 0;
     const long cap = std::max(n, 1L << 17);
     cudaError_t e;
-    if ((e = cudaMalloc(&ctx->d_work_idx, (size_t)cap * sizeof(uint32_t))) ||
+    if ((e = cudaMalloc(&ctx->d_work_idx, (size_t)cap * kWorkBins * sizeof(uint32_t))) ||
         (e = cudaMalloc(&ctx->d_work_mat, (size_t)cap * 3 * sizeof(float4))))
         return check_cuda(ctx, e, "work list");
     ctx->work_cap = cap;
@@ -197,6 +255,9 @@ int rc_create(rc_ctx **out, const float *rob_x, const float *rob_y, const float 
         ctx->knob_global_obstacle = getenv("RC_FORCE_GLOBAL_OBSTACLE") != nullptr;
         ctx->knob_share = knob("RC_SHARE", 1);
         ctx->knob_pdl = knob("RC_PDL", 0);
+        ctx->knob_bound = knob("RC_BOUND", 1);
+        ctx->knob_mail_slots = knob("RC_MAIL_SLOTS", 4);
+        ctx->knob_donate_min = knob("RC_DONATE_MIN", 40);
     }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
@@ -286,12 +347,14 @@ int rc_create(rc_ctx **out, const float *rob_x, const float *rob_y, const float 
         std::memcpy(obn.data(), ob.nodes.data(), ob.nodes.size() * sizeof(float));
 
         const size_t rt_pad = (size_t)n_rob_t + (n_rob_t & 1);
-        if ((e = upload(ctx, &t.rob_v, rv)) || (e = upload(ctx, &t.rob_aos, raos)) ||
+        const std::vector<float4> bound = vertex_bound_boxes(rob_x, rob_y, rob_z, n_rob_v, kBoundBoxes);
+        t.n_rob_bound = (int)(bound.size() / 2);
+        if ((e = upload(ctx, &t.rob_bound, bound)) || (e = upload(ctx, &t.rob_v, rv)) || (e = upload(ctx, &t.rob_aos, raos)) ||
             (e = upload(ctx, &t.rob_t, rt, rt_pad)) || (e = upload(ctx, &t.rob_t_sorted, rts, rt_pad)) ||
             (e = upload(ctx, &t.rob_bvh, rbn)) || (e = upload(ctx, &t.obs_bvh, obn)) ||
             (e = dev_alloc(ctx, &ctx->d_counters, RC_NUM_COUNTERS)) ||
             (e = dev_alloc(ctx, &ctx->d_queues, kHostChunks)) ||
-            (e = dev_alloc(ctx, &ctx->d_work_count, 4)) ||
+            (e = dev_alloc(ctx, &ctx->d_work_count, kWorkCounters)) ||
             (e = dev_alloc(ctx, &ctx->d_obs_box, 1)) ||
             (e = cudaMemcpy(ctx->d_obs_box, &t.obs_box, sizeof(rc_aabb), cudaMemcpyHostToDevice))) {
             rcode = check_cuda(ctx, e, "table upload");

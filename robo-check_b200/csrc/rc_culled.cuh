@@ -32,7 +32,7 @@ constexpr int kTailQCap = 160;   // pairs that passed both plane tests, finished
 constexpr int kStackCapGlobal = 1536;  // obstacle tables in global memory: deeper trees
 constexpr float kTriMargin = 2e-3f;  // triangle-box clearance, same as the two inflated tree boxes
 constexpr int kLeafTrisDev = 4;  // must match rc::kLeafTris of the host builder (rc_bvh.h)
-constexpr int kMailSlots = 4;    // per CTA: pieces of a deep descent handed to warps without work
+constexpr int kMailSlots = 16;   // per CTA (capacity; a.mail_slots are used): pieces of a deep descent handed to warps without work
 constexpr int kDonateMin = 64;   // node pairs on a warp's stack before it hands 32 of them out
 constexpr uint32_t kPendHit = 0x80000000u;
 constexpr uint32_t kWatchdogSpins = 1u << 22;  // x 256 ns: about a second
@@ -63,11 +63,13 @@ struct CulledArgs {
     int tail_thresh, leaf_thresh;
     int stack_cap;                                         // <= compiled capacity (smaller only in tests)
     int share;                                             // 0: no hand-over between the warps of a CTA
+    int mail_slots, donate_min;                            // hand-over tuning (<= kMailSlots; node pairs kept before giving)
     // work list written by classify_kernel: configurations the cheap tests could not clear
-    const uint32_t *work_idx;
-    const float4 *work_mat;                                // three rows of [R | t] per entry
+    const uint32_t *work_idx;                              // [kWorkBins][work_cap] configuration indices
+    const float4 *work_mat;                                // three rows of [R | t] per CONFIGURATION
+    long work_cap;
     uint32_t *trace;                 // rc_stats_trace, STATS kernels only
-    unsigned long long *work_count;  // [0] list length  [1] next entry  [2] CTAs finished (self-resetting)
+    unsigned long long *work_count;  // [0..7] entries per cost class  [8] next entry  [9] CTAs finished (self-resetting)
 };
 
 __device__ __forceinline__ bool boxes_overlap(const Mat34 &m, const float4 r0, const float4 r1,
@@ -136,8 +138,11 @@ struct ClassifyArgs {
     rc_aabb obs_box;
     float sph_x, sph_y, sph_z, sph_r;
     float box_cx, box_cy, box_cz, box_ex, box_ey, box_ez;
+    const float4 *bound;  // (centre, half extent) of the vertex groups, local frame
+    int n_bound;
     uint32_t *work_idx;
     float4 *work_mat;
+    long work_cap;
     unsigned long long *work_count;
     unsigned long long *counters;
 };
@@ -180,6 +185,37 @@ __global__ void __launch_bounds__(256) classify_kernel(const ClassifyArgs a)
                     cy - gy > a.obs_box.y_max || cy + gy < a.obs_box.y_min ||
                     cz - gz > a.obs_box.z_max || cz + gz < a.obs_box.z_min;
         }
+        int inside = 0;  // vertex groups whose box meets the obstacle AABB: the cost class of the descent
+        if (!clear && a.n_bound > 1) {
+            // ... and inside the union of the rotated boxes of its vertex groups: close to the exact
+            // vertex AABB, so all but a thin band of the configurations the reference's broad phase
+            // clears are decided here, by one thread, without transforming a single vertex.
+            float lox = FLT_MAX, loy = FLT_MAX, loz = FLT_MAX, hix = -FLT_MAX, hiy = -FLT_MAX, hiz = -FLT_MAX;
+            const float ax = fabsf(m.r00), ay = fabsf(m.r01), az = fabsf(m.r02);
+            const float bx = fabsf(m.r10), by = fabsf(m.r11), bz = fabsf(m.r12);
+            const float cx = fabsf(m.r20), cy = fabsf(m.r21), cz = fabsf(m.r22);
+            for (int r = 0; r < a.n_bound; r++) {
+                const float4 bc = __ldg(a.bound + 2 * r), be = __ldg(a.bound + 2 * r + 1);
+                const float px = fmaf(m.r02, bc.z, fmaf(m.r01, bc.y, fmaf(m.r00, bc.x, m.tx)));
+                const float py = fmaf(m.r12, bc.z, fmaf(m.r11, bc.y, fmaf(m.r10, bc.x, m.ty)));
+                const float pz = fmaf(m.r22, bc.z, fmaf(m.r21, bc.y, fmaf(m.r20, bc.x, m.tz)));
+                const float ex = fmaf(az, be.z, fmaf(ay, be.y, ax * be.x));
+                const float ey = fmaf(bz, be.z, fmaf(by, be.y, bx * be.x));
+                const float ez = fmaf(cz, be.z, fmaf(cy, be.y, cx * be.x));
+                const float l0 = px - ex, h0 = px + ex, l1 = py - ey, h1 = py + ey, l2 = pz - ez, h2 = pz + ez;
+                lox = fminf(lox, l0); hix = fmaxf(hix, h0);
+                loy = fminf(loy, l1); hiy = fmaxf(hiy, h1);
+                loz = fminf(loz, l2); hiz = fmaxf(hiz, h2);
+                inside += (l0 <= a.obs_box.x_max && h0 >= a.obs_box.x_min && l1 <= a.obs_box.y_max &&
+                           h1 >= a.obs_box.y_min && l2 <= a.obs_box.z_max && h2 >= a.obs_box.z_min) ? 1 : 0;
+            }
+            const float gx = 0.01f + 4e-6f * fmaxf(fabsf(lox), fabsf(hix));
+            const float gy = 0.01f + 4e-6f * fmaxf(fabsf(loy), fabsf(hiy));
+            const float gz = 0.01f + 4e-6f * fmaxf(fabsf(loz), fabsf(hiz));
+            clear = lox - gx > a.obs_box.x_max || hix + gx < a.obs_box.x_min ||
+                    loy - gy > a.obs_box.y_max || hiy + gy < a.obs_box.y_min ||
+                    loz - gz > a.obs_box.z_max || hiz + gz < a.obs_box.z_min;
+        }
         clear = clear && in;
         const bool work = in && !clear;
         const unsigned mc = __ballot_sync(kFull, clear), mw = __ballot_sync(kFull, work);
@@ -187,15 +223,20 @@ __global__ void __launch_bounds__(256) classify_kernel(const ClassifyArgs a)
         // the warp covers exactly one bitmask word: write it (the second kernel ORs its bits in)
         if (lane == 0 && a.bitmask) a.bitmask[i >> 5] = mc;
         if (mw) {
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(a.work_count, (unsigned long long)__popc(mw));
-            base = __shfl_sync(kFull, base, 0);
+            // cost class from the share of the robot inside the obstacle AABB (edges ~ 1/64, 3/64, 7/64,
+            // 13/64, 21/64, 31/64, 43/64 of the groups), one list per class, warp-aggregated append
+            const int f = a.n_bound > 0 ? inside * 64 / a.n_bound : 0;
+            const int bin = (f >= 1) + (f >= 3) + (f >= 7) + (f >= 13) + (f >= 21) + (f >= 31) + (f >= 43);
+            const unsigned peers = __match_any_sync(kFull, work ? bin : kWorkBins);
             if (work) {
-                const unsigned long long pos = base + __popc(mw & lt);
-                a.work_idx[pos] = (uint32_t)i;
-                a.work_mat[3 * pos + 0] = make_float4(m.r00, m.r01, m.r02, m.tx);
-                a.work_mat[3 * pos + 1] = make_float4(m.r10, m.r11, m.r12, m.ty);
-                a.work_mat[3 * pos + 2] = make_float4(m.r20, m.r21, m.r22, m.tz);
+                const int leader = __ffs(peers) - 1;
+                unsigned long long base = 0;
+                if (lane == leader) base = atomicAdd(a.work_count + bin, (unsigned long long)__popc(peers));
+                base = __shfl_sync(peers, base, leader);
+                a.work_idx[(size_t)bin * a.work_cap + base + __popc(peers & lt)] = (uint32_t)i;
+                a.work_mat[3 * i + 0] = make_float4(m.r00, m.r01, m.r02, m.tx);
+                a.work_mat[3 * i + 1] = make_float4(m.r10, m.r11, m.r12, m.ty);
+                a.work_mat[3 * i + 2] = make_float4(m.r20, m.r21, m.r22, m.tz);
             }
         }
         if (STATS && lane == 0 && mc) atomicAdd(a.counters + CNT_SPHERE_CLEARED, (unsigned long long)__popc(mc));
@@ -229,6 +270,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
     uint32_t *s_pend = reinterpret_cast<uint32_t *>(s_mail + kMailSlots);
     uint32_t *s_idle = s_pend + WARPS;
     uint32_t *s_t0 = s_idle + 1;  // kernel start, SM clock >> 20 (the hand-over code never waits longer than kAbortTicks)
+    uint32_t *s_bin = s_t0 + 1;   // [kWorkBins + 1] first list position of each cost class, dearest class first
     // obstacle accessors: shared memory, or the read-only global path
     auto obs_node = [&](int nb, int half) -> float4 {
         if constexpr (GOBS) return __ldg(a.obs_bvh + 2 * nb + half);
@@ -267,6 +309,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
     // everything above reads only the static tables; the work list, the flags and the bitmask
     // words come from classify_kernel: wait for that grid to complete (programmatic dependency)
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int o = 0; o < kWorkBins; o++) {
+            s_bin[o] = acc;
+            acc += (uint32_t)__ldcg(a.work_count + (kWorkBins - 1 - o));
+        }
+        s_bin[kWorkBins] = acc;
+    }
+    __syncthreads();
     mbar_wait(bar, 0);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -285,7 +336,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
     // memory, warps without work of their own pick slots up and run the same descent on them.
     // A configuration collides iff any of its pieces finds a hit; the owner waits for its pieces
     // (s_pend: piece count + hit bit) and publishes the flag.
-    const uint32_t n_work = (uint32_t)__ldcg(a.work_count);
+    const uint32_t n_work = s_bin[kWorkBins];
     const uint32_t chunk = max(1u, min(16u, n_work / (gridDim.x * WARPS * 32u)));
     uint32_t w_next = 0, w_end = 0;
     bool dry = false;
@@ -293,7 +344,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
         if (!dry && w_next >= w_end) {
             const uint32_t take = ((unsigned long long)w_end + a.tail_begin < n_work) ? chunk : 1u;
             unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(a.work_count + 1, (unsigned long long)take);
+            if (lane == 0) base = atomicAdd(a.work_count + kWorkBins, (unsigned long long)take);
             base = __shfl_sync(kFull, base, 0);
             if (base >= n_work) {
                 dry = true;
@@ -328,7 +379,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
             for (uint32_t spins = 0;; spins++) {
                 k = -1;
                 if (lane == 0) {
-                    for (int q = 0; q < kMailSlots; q++)
+                    for (int q = 0; q < a.mail_slots; q++)
                         if (ld_volatile(&s_mail[q].state) == 2u && atomicCAS(&s_mail[q].state, 2u, 3u) == 2u) {
                             k = q;
                             break;
@@ -365,10 +416,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
             __syncwarp();
         } else {
             const uint32_t w = w_next++;
-            i = (long)__ldcg(a.work_idx + w);
             {
-                const float4 q0 = __ldcg(a.work_mat + 3 * w), q1 = __ldcg(a.work_mat + 3 * w + 1),
-                             q2 = __ldcg(a.work_mat + 3 * w + 2);
+                // list position -> (cost class, position in its list): dearest class first
+                const uint32_t o = __popc(__ballot_sync(kFull, lane >= 1 && lane < kWorkBins && w >= s_bin[lane & (kWorkBins - 1)]));
+                i = (long)__ldcg(a.work_idx + (size_t)(kWorkBins - 1 - o) * a.work_cap + (w - s_bin[o]));
+            }
+            {
+                const float4 q0 = __ldcg(a.work_mat + 3 * i), q1 = __ldcg(a.work_mat + 3 * i + 1),
+                             q2 = __ldcg(a.work_mat + 3 * i + 2);
                 m.r00 = q0.x; m.r01 = q0.y; m.r02 = q0.z; m.tx = q0.w;
                 m.r10 = q1.x; m.r11 = q1.y; m.r12 = q1.z; m.ty = q1.w;
                 m.r20 = q2.x; m.r21 = q2.y; m.r22 = q2.z; m.tz = q2.w;
@@ -416,10 +471,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
             // ---- sharing (only once some warp of the CTA has run out of configurations): hand out
             // a tail round's worth of triangle pairs (the longest rounds), else a leaf round's
             // worth of leaf pairs, else up to half of the node pairs, oldest = largest subtrees
-            // (what other warps publish is read by lane 0 and broadcast: two lanes reading the same
-            // word at different moments could otherwise take different branches of this loop)
+            // a warp always keeps work for itself, so what it receives is never passed on untouched
+            // (a piece bouncing between idle warps would never be decided)
+            const int kind = !a.share ? -1
+                             : (tq >= a.tail_thresh && (sp > 0 || lq > 0 || tq > 32)) ? 2
+                             : lq >= 16 ? 1 : sp >= a.donate_min ? 0 : -1;
+            // What other warps publish is read by lane 0 and broadcast (two lanes reading the same word
+            // at different moments could otherwise take different branches of this loop), and only in
+            // rounds where it matters: something to give, or pieces of this configuration are out.
             uint32_t seen = 0;
-            if (a.share) {
+            if (kind >= 0 || sharing) {
                 if (lane == 0) {
                     seen = ld_volatile(s_idle) != 0u ? 1u : 0u;
                     if (seen && sharing && (ld_volatile(&s_pend[pend_slot]) & kPendHit) != 0u) seen = 3u;
@@ -438,14 +499,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
                 }
                 break;
             }
-            if (seen) {
-                // a warp always keeps work for itself, so what it receives is never passed on
-                // untouched (a piece bouncing between idle warps would never be decided)
-                const int kind = (tq >= a.tail_thresh && (sp > 0 || lq > 0 || tq > 32)) ? 2
-                                 : lq >= 16 ? 1 : sp >= kDonateMin ? 0 : -1;
+            if (seen && kind >= 0) {
                 int k = -1;
-                if (kind >= 0 && lane == 0)
-                    for (int q = 0; q < kMailSlots; q++)
+                if (lane == 0)
+                    for (int q = 0; q < a.mail_slots; q++)
                         if (ld_volatile(&s_mail[q].state) == 0u && atomicCAS(&s_mail[q].state, 0u, 1u) == 0u) {
                             k = q;
                             break;
@@ -453,7 +510,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
                 k = __shfl_sync(kFull, k, 0);
                 if (k >= 0) {
                     Mail &b = s_mail[k];
-                    const int cnt = kind == 2 ? min(tq, 32) : kind == 1 ? 8 : 32;
+                    const int cnt = kind == 2 ? min(tq, 32) : kind == 1 ? 8 : min(32, sp >> 1);  // node pairs: at most half
                     const int src = lane < cnt ? lane : 0;
                     uint32_t out;
                     if (kind == 2) {
@@ -669,14 +726,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
             atomicAdd(c.counters + CNT_SHARED, st_shared);
         }
     }
-    // the last CTA to finish leaves the three counters at zero for the next call (no memset per
+    // the last CTA to finish leaves the list counters at zero for the next call (no memset per
     // call): every CTA has read the list length and drawn its last entry by the time it gets here
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        if (atomicAdd(a.work_count + 2, 1ULL) == (unsigned long long)gridDim.x - 1ULL) {
-            a.work_count[0] = 0; a.work_count[1] = 0; a.work_count[2] = 0;
-        }
+        if (atomicAdd(a.work_count + kWorkBins + 1, 1ULL) == (unsigned long long)gridDim.x - 1ULL)
+            for (int q = 0; q < kWorkBins + 2; q++) a.work_count[q] = 0;
     }
 }
 
@@ -687,7 +743,7 @@ static size_t culled_smem_bytes(const DeviceTables &t, int warps, bool gobs)
     if (!gobs)
         b += (size_t)t.n_obs_nodes * 32 + (size_t)t.n_obs_t * 48 + (size_t)pad4(t.n_obs_t) * 4;
     b += (size_t)warps * ((gobs ? kStackCapGlobal : kStackCap) + kLeafQCap + kTailQCap) * 4;
-    b = (b + 15) / 16 * 16 + kMailSlots * sizeof(Mail) + ((size_t)warps + 4) * 4;  // + s_pend, s_idle, s_t0
+    b = (b + 15) / 16 * 16 + kMailSlots * sizeof(Mail) + ((size_t)warps + 4 + kWorkBins + 1) * 4;  // + s_pend, s_idle, s_t0, s_bin
     return b;
 }
 
@@ -746,8 +802,11 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
     if (ctx->knob_tail > 0) a.tail_thresh = min(32, ctx->knob_tail);
     if (ctx->knob_leaf > 0) a.leaf_thresh = min(8, ctx->knob_leaf);
     a.share = ctx->knob_share;
+    a.mail_slots = max(1, min(kMailSlots, ctx->knob_mail_slots));
+    a.donate_min = max(40, ctx->knob_donate_min);
     a.trace = want_stats ? ctx->d_trace : nullptr;
     a.work_idx = ctx->d_work_idx; a.work_mat = ctx->d_work_mat; a.work_count = ctx->d_work_count;
+    a.work_cap = ctx->work_cap;
     if (!ctx->d_work_idx || ctx->work_cap < n) return cudaErrorMemoryAllocation;  // rc_check sizes it
 
     // step 1: classify (thread per configuration); writes every bitmask word, so no memset
@@ -756,7 +815,9 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
     k.sph_x = a.sph_x; k.sph_y = a.sph_y; k.sph_z = a.sph_z; k.sph_r = a.sph_r;
     k.box_cx = a.box_cx; k.box_cy = a.box_cy; k.box_cz = a.box_cz;
     k.box_ex = a.box_ex; k.box_ey = a.box_ey; k.box_ez = a.box_ez;
+    k.bound = t.rob_bound; k.n_bound = ctx->knob_bound ? t.n_rob_bound : 0;
     k.work_idx = ctx->d_work_idx; k.work_mat = ctx->d_work_mat; k.work_count = ctx->d_work_count;
+    k.work_cap = ctx->work_cap;
     k.counters = ctx->d_counters;
     void (*kern)(const CulledArgs) = gobs ? pick_culled<true>(warps, want_stats) : pick_culled<false>(warps, want_stats);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -777,7 +838,7 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
     cfg.attrs = attr; cfg.numAttrs = ctx->knob_pdl ? 1 : 0;
     e = cudaLaunchKernelEx(&cfg, kern, a);
     if (e != cudaSuccess)  // the list counters were filled by step 1 and nobody will reset them
-        cudaMemsetAsync(ctx->d_work_count, 0, 3 * sizeof(unsigned long long), stream);
+        cudaMemsetAsync(ctx->d_work_count, 0, kWorkCounters * sizeof(unsigned long long), stream);
     return e;
 }
 

@@ -39,12 +39,22 @@ struct DeviceTables {
     float rob_center[3];        // bounding sphere of the robot in its local frame
     float rob_radius;
     float rob_box_c[3], rob_box_e[3];
+    // boxes (local frame) of a k-d partition of ALL robot vertices: a much tighter outer bound of
+    // the exact vertex AABB than the single rotated box; two float4 (centre, half extent) each
+    float4 *rob_bound = nullptr;
+    int n_rob_bound = 0;
     // traversal seeds: node cuts at depth 0..3 of both trees (<= 8 nodes each)
     uint32_t seed_r[4][8], seed_o[4][8];
     int n_seed_r[4], n_seed_o[4];  // robot local AABB: centre and half extent (rounded up)
 };
 
 }  // namespace rc
+
+// classify_kernel sorts the configurations it cannot clear into this many cost classes (how much
+// of the robot lies inside the obstacle AABB); the descent takes the dearest class first so that
+// the long descents are under way early and the work list ends with cheap ones
+constexpr int kWorkBins = 8;
+constexpr int kWorkCounters = 16;  // [0..7] entries per class, [8] next entry, [9] CTAs finished
 
 struct rc_ctx {
     int device = 0;
@@ -69,7 +79,7 @@ struct rc_ctx {
     cudaStream_t own_stream = nullptr, own_stream2 = nullptr;
     cudaEvent_t ev_join = nullptr;
     // work list between the two kernels of rc_check, grown on demand to the largest n seen
-    uint32_t *d_work_idx = nullptr;
+    uint32_t *d_work_idx = nullptr;            // [kWorkBins][work_cap]: configuration indices per cost class
     float4 *d_work_mat = nullptr;
     unsigned long long *d_work_count = nullptr;
     long work_cap = 0;
@@ -84,6 +94,8 @@ struct rc_ctx {
     int knob_stack_cap = 0;  // RC_STACK_CAP: shrink the pair stack to exercise the overflow fallback
     bool knob_global_obstacle = false;
     int knob_pdl = 0;        // RC_PDL=1: programmatic dependent launch of the descent step
+    int knob_bound = 1;      // RC_BOUND=0: classify without the vertex-group boxes
+    int knob_mail_slots = 4, knob_donate_min = 40;  // RC_MAIL_SLOTS, RC_DONATE_MIN
     int knob_share = 1;      // RC_SHARE=0: warps of a CTA do not hand pieces of a deep descent to each other
     std::string last_error;
     std::vector<void *> allocations;

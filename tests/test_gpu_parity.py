@@ -103,6 +103,43 @@ def test_culled_equals_brute_large(rc, ctx):
     assert st["narrow_valid"] + st["broad_cleared"] + st["sphere_cleared"] == int(a.sum())
 
 
+@pytest.mark.parametrize("knobs", [
+    {},                                                       # defaults
+    {"RC_DONATE_MIN": "40", "RC_MAIL_SLOTS": "16"},           # hand over early and often
+    {"RC_TAIL_THRESH": "8", "RC_LEAF_THRESH": "4"},           # many short finishing rounds
+    {"RC_DONATE_MIN": "200", "RC_MAIL_SLOTS": "1"},           # one slot, rare hand-overs
+    {"RC_SHARE": "0"},                                        # no hand-over at all
+    {"RC_BOUND": "0"},                                        # one cost class, no vertex-group bound
+    {"RC_PDL": "1"},                                          # programmatic dependent launch
+    {"RC_CULLED_WARPS": "16"},
+])
+def test_descent_scheduling_variants_equal_brute(rc, meshes, knobs, monkeypatch):
+    """How the descent is scheduled (cost classes, hand-over of pieces between the warps of a CTA,
+    queue thresholds) must never change a flag: 100,000 hard configurations, repeated three times
+    (the hand-over is timing dependent), against the exhaustive kernel; the watchdog stays silent."""
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    confs = rc.createAlphaBotConfigurations(100000, True, 777)
+    c = rc.Context(meshes[0], meshes[1], device=0)
+    try:
+        want = run_check(c, confs, rc.RC_MODE_BRUTE)
+        c.stats_enable(True)
+        c.stats(reset=True)
+        got_stats = run_check(c, confs, rc.RC_MODE_CULLED)
+        st = c.stats(reset=True)
+        c.stats_enable(False)
+        assert int((got_stats != want).sum()) == 0
+        for _ in range(3):
+            got = run_check(c, confs, rc.RC_MODE_CULLED)
+            assert int((got != want).sum()) == 0
+    finally:
+        c.close()
+    assert st["watchdog"] == 0 and st["overflow"] == 0
+    if knobs.get("RC_SHARE") == "0":
+        assert st["shared_pieces"] == 0
+    assert st["broad_cleared"] + st["sphere_cleared"] + st["narrow_valid"] + st["narrow_invalid"] == len(confs)
+
+
 # ---- stage API -------------------------------------------------------------------------------
 def test_transform_bit_exact_vs_oracle(rc, ctx, po, omeshes):
     torch = _torch()
