@@ -84,6 +84,22 @@ int rc_check(rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_valid, ui
  * call behind the broadPhaseFused_sep(std::vector<Configuration>&, bool*) shim. */
 int rc_check_host(rc_ctx *ctx, const rc_config *h_confs, long n, uint8_t *h_valid, int mode);
 
+/* Single-process multi-GPU check (north_star: configurations shard across the GPUs of one box, the
+ * meshes replicated, only the validity bitmask gathered).  ctxs[g] = one context per device, built
+ * from the same meshes.  Shard g = the rc_shard_size(n, n_gpus) configurations starting at
+ * g * rc_shard_size (a multiple of 32, so every shard owns whole bitmask words; trailing shards may
+ * be short or empty).  Every device stages and checks its shard concurrently.  Outputs, each
+ * optional: h_bitmask ((n+31)/32 words, bit i%32 of word i/32 = configuration i is valid), h_valid
+ * (n flag bytes), d_bitmask_all[g] = device buffer of (n+31)/32 words on ctxs[g]'s device: every
+ * device ends up with the FULL bitmask -- each kernel writes its words into its own slot and the
+ * slot is copied to the peers (cudaMemcpyPeerAsync, NVLink / NVSwitch), i.e. the all-gather of the
+ * reference design without a communicator.  Blocking; returns when all outputs are complete.
+ * (Multi-process callers -- one rank per GPU -- use rc_check + ncclAllGather on the bitmask
+ * instead, see robo-check_b200/sharding.py and bench.py.) */
+int rc_shard_size(long n, int n_gpus);
+int rc_check_multi(rc_ctx **ctxs, int n_gpus, const rc_config *h_confs, long n, uint32_t *h_bitmask,
+                   uint8_t *h_valid, uint32_t **d_bitmask_all);
+
 /* ---- stage API ---------------------------------------------------------------------------- */
 /* transformation/transform.hu:10-12 genTransformedCopies: AoS copies [conf][vertex].  d_base
  * may be NULL (use the context's robot).  Arithmetic is the live fused kernel's. */

@@ -57,6 +57,8 @@ ctx = rc.Context(rob, obs, device=0)
 flags = run("C1 easy_confs10,000.conf", ctx, gold["confs"])
 assert np.array_equal(flags, gold["tags"]), "C1 must reproduce the FCL tags"
 run("C2 hard 100,000 (seed 508)", ctx, rc.createAlphaBotConfigurations(100_000, True, 508))
+run("C2s hard 10,000 (seed 508; a planner-sized batch)", ctx, rc.createAlphaBotConfigurations(10_000, True, 508))
+run("C2t hard 2,000 (seed 508)", ctx, rc.createAlphaBotConfigurations(2_000, True, 508))
 run("C4 uniform 1,000,000 (easy sampler, seed 510)", ctx, rc.createAlphaBotConfigurations(1_000_000, False, 510))
 run("C2x hard 1,000,000 (seed 512)", ctx, rc.createAlphaBotConfigurations(1_000_000, True, 512))
 run("C3 sphere robot (1008 spheres), easy 1,000,000 (seed 509)", ctx,

@@ -56,6 +56,8 @@ ABI = [
     ("rc_obstacle_aabb", _i, [_vp, _vp]),
     ("rc_check", _i, [_vp, _vp, _l, _vp, _vp, _i, _vp]),
     ("rc_check_host", _i, [_vp, _vp, _l, _vp, _i]),
+    ("rc_shard_size", _i, [_l, _i]),
+    ("rc_check_multi", _i, [_vp, _i, _vp, _l, _vp, _vp, _vp]),
     ("rc_transform_aos", _i, [_vp, _vp, _l, _vp, _i, _vp, _vp]),
     ("rc_generate_aabb", _i, [_vp, _vp, _u, _u, _vp, _vp]),
     ("rc_generate_aabb_host", _i, [_vp, _vp, _u, _u, _vp]),
@@ -442,6 +444,24 @@ class Context:
         v = C.c_double()
         _check(_lib.rc_measure_fp32_peak(self._h, C.byref(v)), self._h)
         return v.value
+
+
+def check_multi(contexts, confs, want_flags=False, d_bitmask_all=None):
+    """rc_check_multi: one Context per device, host configurations in, the full validity bitmask
+    (and optionally the flag bytes) out; d_bitmask_all = one device tensor of (n+31)//32 int32 words
+    per context to leave the full bitmask on every device as well."""
+    confs = np.ascontiguousarray(confs, dtype=np.float32).reshape(-1, 6)
+    n = len(confs)
+    g = len(contexts)
+    handles = (C.c_void_p * g)(*[c._h for c in contexts])
+    mask = np.zeros((n + 31) // 32, dtype=np.uint32)
+    flags = np.zeros(n, dtype=np.uint8) if want_flags else None
+    dall = None
+    if d_bitmask_all is not None:
+        dall = (C.c_void_p * g)(*[_ptr(t) for t in d_bitmask_all])
+    _check(_lib.rc_check_multi(handles, g, confs.ctypes.data, n, mask.ctypes.data,
+                               flags.ctypes.data if want_flags else None, dall))
+    return (mask, flags) if want_flags else mask
 
 
 def narrowPhase(rob_trs, rob_pts, obs_trs, obs_pts, valid, device=0):

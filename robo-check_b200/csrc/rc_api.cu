@@ -174,15 +174,19 @@ int ensure_staging(rc_ctx *ctx, long n)
     if (ctx->h_pinned_valid) cudaFreeHost(ctx->h_pinned_valid);
     if (ctx->d_stage_confs) cudaFree(ctx->d_stage_confs);
     if (ctx->d_stage_valid) cudaFree(ctx->d_stage_valid);
-    ctx->h_pinned_confs = nullptr; ctx->h_pinned_valid = nullptr;
-    ctx->d_stage_confs = nullptr; ctx->d_stage_valid = nullptr;
+    if (ctx->d_stage_mask) cudaFree(ctx->d_stage_mask);
+    if (ctx->h_pinned_mask) cudaFreeHost(ctx->h_pinned_mask);
+    ctx->h_pinned_confs = nullptr; ctx->h_pinned_valid = nullptr; ctx->h_pinned_mask = nullptr;
+    ctx->d_stage_confs = nullptr; ctx->d_stage_valid = nullptr; ctx->d_stage_mask = nullptr;
     ctx->stage_capacity = 0;
     const long cap = std::max(n, 1L << 16);
     cudaError_t e;
     if ((e = cudaMallocHost(&ctx->h_pinned_confs, (size_t)cap * sizeof(rc_config))) ||
         (e = cudaMallocHost(&ctx->h_pinned_valid, (size_t)cap)) ||
         (e = cudaMalloc(&ctx->d_stage_confs, (size_t)cap * sizeof(rc_config))) ||
-        (e = cudaMalloc(&ctx->d_stage_valid, (size_t)cap)))
+        (e = cudaMalloc(&ctx->d_stage_valid, (size_t)cap)) ||
+        (e = cudaMalloc(&ctx->d_stage_mask, (size_t)((cap + 31) / 32) * sizeof(uint32_t))) ||
+        (e = cudaMallocHost(&ctx->h_pinned_mask, (size_t)((cap + 31) / 32) * sizeof(uint32_t))))
         return check_cuda(ctx, e, "staging buffers");
     ctx->stage_capacity = cap;
     return RC_OK;
@@ -398,6 +402,8 @@ void rc_destroy(rc_ctx *ctx)
     if (ctx->h_pinned_valid) cudaFreeHost(ctx->h_pinned_valid);
     if (ctx->d_stage_confs) cudaFree(ctx->d_stage_confs);
     if (ctx->d_stage_valid) cudaFree(ctx->d_stage_valid);
+    if (ctx->d_stage_mask) cudaFree(ctx->d_stage_mask);
+    if (ctx->h_pinned_mask) cudaFreeHost(ctx->h_pinned_mask);
     if (ctx->d_block_counts) cudaFree(ctx->d_block_counts);
     if (ctx->d_work_idx) cudaFree(ctx->d_work_idx);
     if (ctx->d_work_mat) cudaFree(ctx->d_work_mat);
@@ -486,6 +492,94 @@ int rc_check_host(rc_ctx *ctx, const rc_config *h_confs, long n, uint8_t *h_vali
     cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev0, ctx->ev1);
     if (!out_pinned) std::memcpy(h_valid, ctx->h_pinned_valid, (size_t)n);
     return RC_OK;
+}
+
+int rc_shard_size(long n, int n_gpus)
+{
+    if (n < 0 || n_gpus <= 0) return RC_ERR_INVALID;
+    const long per = ((n + n_gpus - 1) / n_gpus + 31) / 32 * 32;
+    return per > 0x7fffffffL ? RC_ERR_INVALID : (int)per;
+}
+
+int rc_check_multi(rc_ctx **ctxs, int n_gpus, const rc_config *h_confs, long n, uint32_t *h_bitmask,
+                   uint8_t *h_valid, uint32_t **d_bitmask_all)
+{
+    if (!ctxs || n_gpus <= 0 || n < 0 || (n > 0 && (!h_confs || (!h_bitmask && !h_valid && !d_bitmask_all))))
+        return RC_ERR_INVALID;
+    for (int g = 0; g < n_gpus; g++) {
+        if (!ctxs[g]) return RC_ERR_INVALID;
+        if (d_bitmask_all && !d_bitmask_all[g]) return RC_ERR_INVALID;
+    }
+    if (n == 0) return RC_OK;
+    const long per = rc_shard_size(n, n_gpus);
+    if (per <= 0) return RC_ERR_INVALID;
+    cudaPointerAttributes pa{};
+    const bool pinned = cudaPointerGetAttributes(&pa, h_confs) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (d_bitmask_all)  // direct peer copies where the topology allows them (once per pair)
+        for (int g = 0; g < n_gpus; g++)
+            for (int p = 0; p < n_gpus; p++) {
+                const int dg = ctxs[g]->device, dp = ctxs[p]->device;
+                if (dg == dp || dp >= 64 || (ctxs[g]->peers_enabled >> dp & 1ULL)) continue;
+                int can = 0;
+                cudaSetDevice(dg);
+                if (cudaDeviceCanAccessPeer(&can, dg, dp) == cudaSuccess && can) cudaDeviceEnablePeerAccess(dp, 0);
+                cudaGetLastError();  // "already enabled" is fine
+                ctxs[g]->peers_enabled |= 1ULL << dp;
+            }
+    // 1. every device: stage its shard, launch the check (asynchronous: the devices overlap)
+    for (int g = 0; g < n_gpus; g++) {
+        rc_ctx *ctx = ctxs[g];
+        const long lo = std::min(n, (long)g * per), cnt = std::min(n, lo + per) - lo;
+        if (cnt <= 0) continue;
+        cudaSetDevice(ctx->device);
+        int rcode = ensure_staging(ctx, cnt);
+        if (rcode == RC_OK) rcode = ensure_work_list(ctx, cnt);
+        if (rcode != RC_OK) return rcode;
+        cudaStream_t s = ctx->own_stream;
+        const rc_config *src = h_confs + lo;
+        if (!pinned) {
+            std::memcpy(ctx->h_pinned_confs, src, (size_t)cnt * sizeof(rc_config));
+            src = ctx->h_pinned_confs;
+        }
+        cudaError_t e = cudaMemcpyAsync(ctx->d_stage_confs, src, (size_t)cnt * sizeof(rc_config),
+                                        cudaMemcpyHostToDevice, s);
+        if (e) return check_cuda(ctx, e, "rc_check_multi H2D");
+        // with a gather buffer on this device the kernel writes its words straight into its slot
+        uint32_t *mask = d_bitmask_all ? d_bitmask_all[g] + lo / 32 : ctx->d_stage_mask;
+        e = launch_check(ctx, ctx->d_stage_confs, cnt, h_valid ? ctx->d_stage_valid : nullptr, mask,
+                         RC_MODE_CULLED, ctx->stats_on, s, ctx->d_queues);
+        if (e == cudaErrorInvalidConfiguration)
+            return set_error(ctx, RC_ERR_UNSUPPORTED, "mesh tables do not fit in shared memory");
+        if (e) return check_cuda(ctx, e, "rc_check_multi launch");
+        ctx->launches += 2;
+        const size_t words = (size_t)(cnt + 31) / 32;
+        if (h_bitmask && (e = cudaMemcpyAsync(ctx->h_pinned_mask, mask, words * 4, cudaMemcpyDeviceToHost, s)))
+            return check_cuda(ctx, e, "rc_check_multi D2H bitmask");
+        if (h_valid && (e = cudaMemcpyAsync(ctx->h_pinned_valid, ctx->d_stage_valid, (size_t)cnt,
+                                            cudaMemcpyDeviceToHost, s)))
+            return check_cuda(ctx, e, "rc_check_multi D2H flags");
+        // 2. all-gather without a communicator: this shard's words go to every peer's buffer
+        //    (cudaMemcpyPeerAsync: NVLink / NVSwitch when peer access is available, staged otherwise)
+        if (d_bitmask_all)
+            for (int p = 0; p < n_gpus; p++)
+                if (p != g && (e = cudaMemcpyPeerAsync(d_bitmask_all[p] + lo / 32, ctxs[p]->device, mask,
+                                                       ctx->device, words * 4, s)))
+                    return check_cuda(ctx, e, "rc_check_multi peer copy");
+    }
+    // 3. join
+    int rcode = RC_OK;
+    for (int g = 0; g < n_gpus; g++) {
+        rc_ctx *ctx = ctxs[g];
+        const long lo = std::min(n, (long)g * per), cnt = std::min(n, lo + per) - lo;
+        if (cnt <= 0) continue;
+        cudaSetDevice(ctx->device);
+        const cudaError_t e = cudaStreamSynchronize(ctx->own_stream);
+        if (e) { rcode = check_cuda(ctx, e, "rc_check_multi join"); continue; }
+        if (h_bitmask) std::memcpy(h_bitmask + lo / 32, ctx->h_pinned_mask, (size_t)((cnt + 31) / 32) * 4);
+        if (h_valid) std::memcpy(h_valid + lo, ctx->h_pinned_valid, (size_t)cnt);
+    }
+    return rcode;
 }
 
 float rc_last_kernel_ms(const rc_ctx *ctx) { return ctx ? ctx->last_kernel_ms : 0.f; }

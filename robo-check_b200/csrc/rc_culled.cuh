@@ -476,17 +476,21 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
             const int kind = !a.share ? -1
                              : (tq >= a.tail_thresh && (sp > 0 || lq > 0 || tq > 32)) ? 2
                              : lq >= 16 ? 1 : sp >= a.donate_min ? 0 : -1;
-            // What other warps publish is read by lane 0 and broadcast (two lanes reading the same word
-            // at different moments could otherwise take different branches of this loop), and only in
-            // rounds where it matters: something to give, or pieces of this configuration are out.
+            // What other warps publish is agreed on by the whole warp (vote / broadcast: two lanes
+            // reading the same word at different moments could otherwise take different branches of
+            // this loop), and only in rounds where it matters: something to give, or pieces of this
+            // configuration are out.  s_idle only ever grows, so the common case is one shared-memory
+            // read and one vote.
             uint32_t seen = 0;
             if (kind >= 0 || sharing) {
-                if (lane == 0) {
-                    seen = ld_volatile(s_idle) != 0u ? 1u : 0u;
-                    if (seen && sharing && (ld_volatile(&s_pend[pend_slot]) & kPendHit) != 0u) seen = 3u;
-                    if (seen && (uint32_t)(clock64() >> 20) - *s_t0 > kAbortTicks) seen = 4u;
+                if (__any_sync(kFull, ld_volatile(s_idle) != 0u)) {
+                    if (lane == 0) {
+                        seen = 1u;
+                        if (sharing && (ld_volatile(&s_pend[pend_slot]) & kPendHit) != 0u) seen = 3u;
+                        if ((uint32_t)(clock64() >> 20) - *s_t0 > kAbortTicks) seen = 4u;
+                    }
+                    seen = __shfl_sync(kFull, seen, 0);
                 }
-                seen = __shfl_sync(kFull, seen, 0);
             }
             if (seen & 2u) {
                 hit = true;  // another piece of this configuration has found a hit

@@ -73,6 +73,9 @@ struct rc_ctx {
     unsigned long long launches = 0;           // kernels launched through this context
     rc_config *d_stage_confs = nullptr;        // device staging for rc_check_host
     uint8_t *d_stage_valid = nullptr;
+    uint32_t *d_stage_mask = nullptr;          // bitmask words of the staged configurations (rc_check_multi)
+    uint32_t *h_pinned_mask = nullptr;
+    unsigned long long peers_enabled = 0;      // devices this context's device may copy to directly
     rc_config *h_pinned_confs = nullptr;
     uint8_t *h_pinned_valid = nullptr;
     long stage_capacity = 0;

@@ -57,3 +57,32 @@ def test_two_gpu_sharded_check():
     ok = q.get(timeout=300)
     [p.join(timeout=60) for p in procs]
     assert ok and all(p.exitcode == 0 for p in procs)
+
+
+def test_check_multi_one_context_per_gpu():
+    """rc_check_multi with one context per device (single process): host bitmask and flags, and the
+    full bitmask on every device after the peer copies, equal the single-GPU result."""
+    import torch
+    n_dev = torch.cuda.device_count()
+    if n_dev < 2:
+        pytest.skip("needs two GPUs")
+    import robocheck_b200 as rc
+    n = 200_003
+    confs = np.concatenate([rc.createAlphaBotConfigurations(n // 2, True, 51),
+                            rc.createAlphaBotConfigurations(n - n // 2, False, 52)])
+    confs = confs[np.random.default_rng(6).permutation(n)]
+    ctxs = [rc.Context(device=d) for d in range(n_dev)]
+    try:
+        want = ctxs[0].check_host(confs)
+        words = (n + 31) // 32
+        d_all = [torch.full((words,), -1, dtype=torch.int32, device=torch.device("cuda", d)) for d in range(n_dev)]
+        for d in range(n_dev):
+            torch.cuda.synchronize(d)
+        mask, flags = rc.check_multi(ctxs, confs, want_flags=True, d_bitmask_all=d_all)
+        assert np.array_equal(flags, want)
+        assert np.array_equal(np.unpackbits(mask.view(np.uint8), bitorder="little")[:n], want)
+        for t in d_all:
+            assert np.array_equal(t.cpu().numpy().view(np.uint32), mask)
+    finally:
+        for c in ctxs:
+            c.close()

@@ -140,6 +140,39 @@ def test_descent_scheduling_variants_equal_brute(rc, meshes, knobs, monkeypatch)
     assert st["broad_cleared"] + st["sphere_cleared"] + st["narrow_valid"] + st["narrow_invalid"] == len(confs)
 
 
+@pytest.mark.parametrize("n_ctx,n", [(1, 5000), (2, 40001), (3, 64), (4, 100000), (4, 70)])
+def test_check_multi_single_process(rc, ctx, meshes, n_ctx, n):
+    """rc_check_multi: contiguous shards of whole bitmask words, every context checks its
+    shard, the host gets the full bitmask and flags, and every device buffer the full bitmask (peer
+    copies).  Several contexts on one device stand in for several devices here; the same call with
+    one context per GPU runs in tests/test_gpu_multi.py."""
+    torch = _torch()
+    confs = np.concatenate([rc.createAlphaBotConfigurations(n - n // 4, True, 91),
+                            rc.createAlphaBotConfigurations(n // 4, False, 92)])
+    confs = confs[np.random.default_rng(5).permutation(n)]
+    want = run_check(ctx, confs, rc.RC_MODE_CULLED)
+    ctxs = [rc.Context(meshes[0], meshes[1], device=0) for _ in range(n_ctx)]
+    try:
+        per = rc.lib().rc_shard_size(n, n_ctx)
+        assert per % 32 == 0 and per * n_ctx >= n
+        words = (n + 31) // 32
+        d_all = [torch.full((words,), -1, dtype=torch.int32, device="cuda") for _ in range(n_ctx)]
+        torch.cuda.synchronize()
+        mask, flags = rc.check_multi(ctxs, confs, want_flags=True, d_bitmask_all=d_all)
+        bits = np.unpackbits(mask.view(np.uint8), bitorder="little")[:n]
+        assert np.array_equal(flags, want)
+        assert np.array_equal(bits, want)
+        for t in d_all:
+            got = np.unpackbits(t.cpu().numpy().view(np.uint8), bitorder="little")[:n]
+            assert np.array_equal(got, want)
+        # bitmask only, no device buffers
+        mask2 = rc.check_multi(ctxs, confs)
+        assert np.array_equal(mask2, mask)
+    finally:
+        for c in ctxs:
+            c.close()
+
+
 # ---- stage API -------------------------------------------------------------------------------
 def test_transform_bit_exact_vs_oracle(rc, ctx, po, omeshes):
     torch = _torch()

@@ -175,3 +175,22 @@ def test_sharding_partition():
     assert w.dtype == np.uint32 and len(w) == 3
     assert np.array_equal(sh.unpack_bitmask(w, 77), flags)
     assert (int(w[0]) >> 3) & 1 == 1 and (int(w[0]) >> 4) & 1 == 0
+
+
+def test_shard_size_and_multi_argument_checks(rc):
+    """rc_shard_size: shards of whole bitmask words that cover n; rc_check_multi rejects
+    bad arguments with a status instead of touching a device."""
+    lib = rc.lib()
+    for n, g in ((0, 1), (1, 1), (100_000, 8), (10_000_000, 8), (1_000_000, 3), (33, 4), (31, 2)):
+        per = lib.rc_shard_size(n, g)
+        assert per % 32 == 0 and per * g >= n and (per == 0) == (n == 0)
+        if n:
+            assert (per - 32) * g < n + 32 * g   # no more than one word of slack per shard
+    assert lib.rc_shard_size(100_000, 8) == 12512
+    assert lib.rc_shard_size(5, 0) == rc.RC_ERR_INVALID and lib.rc_shard_size(-1, 2) == rc.RC_ERR_INVALID
+    assert lib.rc_check_multi(None, 2, None, 10, None, None, None) == rc.RC_ERR_INVALID
+    import ctypes
+    handles = (ctypes.c_void_p * 2)(None, None)
+    confs = np.zeros((4, 6), dtype=np.float32)
+    mask = np.zeros(1, dtype=np.uint32)
+    assert lib.rc_check_multi(handles, 2, confs.ctypes.data, 4, mask.ctypes.data, None, None) == rc.RC_ERR_INVALID
