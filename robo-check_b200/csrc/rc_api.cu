@@ -32,7 +32,7 @@ namespace {
 // culling boxes are inflated by this much on each side (scene extent is ~90 units)
 constexpr float kBoxMargin = 1e-3f;
 // groups of robot vertices whose rotated boxes bound the vertex AABB in classify_kernel
-constexpr int kBoundBoxes = 64;
+constexpr int kBoundBoxes = 32;  // = rc::kClassifyBoxes (rc_culled.cuh)
 
 template <class T>
 cudaError_t dev_alloc(rc_ctx *ctx, T **p, size_t count)
@@ -352,8 +352,14 @@ int rc_create(rc_ctx **out, const float *rob_x, const float *rob_y, const float 
 
         const size_t rt_pad = (size_t)n_rob_t + (n_rob_t & 1);
         const std::vector<float4> bound = vertex_bound_boxes(rob_x, rob_y, rob_z, n_rob_v, kBoundBoxes);
-        t.n_rob_bound = (int)(bound.size() / 2);
-        if ((e = upload(ctx, &t.rob_bound, bound)) || (e = upload(ctx, &t.rob_v, rv)) || (e = upload(ctx, &t.rob_aos, raos)) ||
+        // fewer groups than boxes (tiny meshes): repeat the first one, the union does not change
+        t.n_rob_bound = bound.empty() ? 0 : kBoundBoxes;
+        for (int q = 0; q < kBoundBoxes && !bound.empty(); q++) {
+            const size_t src = (size_t)q < bound.size() / 2 ? (size_t)q : 0;
+            t.h_rob_bound[2 * q] = bound[2 * src];
+            t.h_rob_bound[2 * q + 1] = bound[2 * src + 1];
+        }
+        if ((e = upload(ctx, &t.rob_v, rv)) || (e = upload(ctx, &t.rob_aos, raos)) ||
             (e = upload(ctx, &t.rob_t, rt, rt_pad)) || (e = upload(ctx, &t.rob_t_sorted, rts, rt_pad)) ||
             (e = upload(ctx, &t.rob_bvh, rbn)) || (e = upload(ctx, &t.obs_bvh, obn)) ||
             (e = dev_alloc(ctx, &ctx->d_counters, RC_NUM_COUNTERS)) ||

@@ -25,13 +25,19 @@
 
 namespace rc {
 
-constexpr int kCulledWarpsDefault = 24;  // warps per CTA (one CTA per SM); 16/20/24 instantiated
-constexpr int kStackCap = 1024;  // node pairs per warp; overflow falls back to the exhaustive sweep
+constexpr int kCulledWarpsDefault = 32;  // warps per CTA (one CTA per SM); 16/20/24/28/32 instantiated
+constexpr int kStackCap = 1024;  // node pairs per warp (fewer with more warps per CTA); overflow falls back to the exhaustive sweep
 constexpr int kLeafQCap = 64;
 constexpr int kTailQCap = 160;   // pairs that passed both plane tests, finished 32 at a time
 constexpr int kStackCapGlobal = 1536;  // obstacle tables in global memory: deeper trees
+// the deepest stack seen on alpha1.0 is ~200 pairs, so more warps per CTA can live with smaller stacks
+__host__ __device__ constexpr int stack_cap_of(int warps, bool gobs)
+{
+    return gobs ? (warps > 24 ? 1024 : kStackCapGlobal) : (warps > 28 ? 512 : warps > 24 ? 768 : kStackCap);
+}
 constexpr float kTriMargin = 2e-3f;  // triangle-box clearance, same as the two inflated tree boxes
 constexpr int kLeafTrisDev = 4;  // must match rc::kLeafTris of the host builder (rc_bvh.h)
+constexpr int kClassifyBoxes = 32;  // vertex groups of the robot bounded in classify_kernel
 constexpr int kMailSlots = 16;   // per CTA (capacity; a.mail_slots are used): pieces of a deep descent handed to warps without work
 constexpr int kDonateMin = 64;   // node pairs on a warp's stack before it hands 32 of them out
 constexpr uint32_t kPendHit = 0x80000000u;
@@ -138,8 +144,9 @@ struct ClassifyArgs {
     rc_aabb obs_box;
     float sph_x, sph_y, sph_z, sph_r;
     float box_cx, box_cy, box_cz, box_ex, box_ey, box_ez;
-    const float4 *bound;  // (centre, half extent) of the vertex groups, local frame
-    int n_bound;
+    float4 bound[2 * 32];  // (centre, half extent) of the vertex groups, local frame: kernel parameter =
+                           // constant bank, the unrolled loop reads them as instruction operands
+    int n_bound;           // kClassifyBoxes, or 0 to skip them
     uint32_t *work_idx;
     float4 *work_mat;
     long work_cap;
@@ -148,7 +155,7 @@ struct ClassifyArgs {
 };
 
 template <bool STATS>
-__global__ void __launch_bounds__(256) classify_kernel(const ClassifyArgs a)
+__global__ void __launch_bounds__(64) classify_kernel(const __grid_constant__ ClassifyArgs a)
 {
     // the descent kernel is launched with programmatic stream serialisation: let its CTAs start
     // staging the mesh tables while this grid is still running (they wait before reading the list)
@@ -186,7 +193,7 @@ __global__ void __launch_bounds__(256) classify_kernel(const ClassifyArgs a)
                     cz - gz > a.obs_box.z_max || cz + gz < a.obs_box.z_min;
         }
         int inside = 0;  // vertex groups whose box meets the obstacle AABB: the cost class of the descent
-        if (!clear && a.n_bound > 1) {
+        if (!clear && a.n_bound == kClassifyBoxes) {
             // ... and inside the union of the rotated boxes of its vertex groups: close to the exact
             // vertex AABB, so all but a thin band of the configurations the reference's broad phase
             // clears are decided here, by one thread, without transforming a single vertex.
@@ -194,8 +201,9 @@ __global__ void __launch_bounds__(256) classify_kernel(const ClassifyArgs a)
             const float ax = fabsf(m.r00), ay = fabsf(m.r01), az = fabsf(m.r02);
             const float bx = fabsf(m.r10), by = fabsf(m.r11), bz = fabsf(m.r12);
             const float cx = fabsf(m.r20), cy = fabsf(m.r21), cz = fabsf(m.r22);
-            for (int r = 0; r < a.n_bound; r++) {
-                const float4 bc = __ldg(a.bound + 2 * r), be = __ldg(a.bound + 2 * r + 1);
+#pragma unroll
+            for (int r = 0; r < kClassifyBoxes; r++) {
+                const float4 bc = a.bound[2 * r], be = a.bound[2 * r + 1];
                 const float px = fmaf(m.r02, bc.z, fmaf(m.r01, bc.y, fmaf(m.r00, bc.x, m.tx)));
                 const float py = fmaf(m.r12, bc.z, fmaf(m.r11, bc.y, fmaf(m.r10, bc.x, m.ty)));
                 const float pz = fmaf(m.r22, bc.z, fmaf(m.r21, bc.y, fmaf(m.r20, bc.x, m.tz)));
@@ -225,7 +233,7 @@ __global__ void __launch_bounds__(256) classify_kernel(const ClassifyArgs a)
         if (mw) {
             // cost class from the share of the robot inside the obstacle AABB (edges ~ 1/64, 3/64, 7/64,
             // 13/64, 21/64, 31/64, 43/64 of the groups), one list per class, warp-aggregated append
-            const int f = a.n_bound > 0 ? inside * 64 / a.n_bound : 0;
+            const int f = inside * (64 / kClassifyBoxes);
             const int bin = (f >= 1) + (f >= 3) + (f >= 7) + (f >= 13) + (f >= 21) + (f >= 31) + (f >= 43);
             const unsigned peers = __match_any_sync(kFull, work ? bin : kWorkBins);
             if (work) {
@@ -252,7 +260,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
 {
     constexpr int SH = GOBS ? 21 : 16;
     constexpr uint32_t LOW = (1u << SH) - 1u;
-    constexpr int kStack = GOBS ? kStackCapGlobal : kStackCap;
+    constexpr int kStack = stack_cap_of(WARPS, GOBS);
     constexpr int kWarpWork = kStack + kLeafQCap + kTailQCap;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const CheckArgs &c = a.c;
@@ -746,7 +754,7 @@ static size_t culled_smem_bytes(const DeviceTables &t, int warps, bool gobs)
                (size_t)(t.n_rob_t + (t.n_rob_t & 1)) * 8;
     if (!gobs)
         b += (size_t)t.n_obs_nodes * 32 + (size_t)t.n_obs_t * 48 + (size_t)pad4(t.n_obs_t) * 4;
-    b += (size_t)warps * ((gobs ? kStackCapGlobal : kStackCap) + kLeafQCap + kTailQCap) * 4;
+    b += (size_t)warps * (stack_cap_of(warps, gobs) + kLeafQCap + kTailQCap) * 4;
     b = (b + 15) / 16 * 16 + kMailSlots * sizeof(Mail) + ((size_t)warps + 4 + kWorkBins + 1) * 4;  // + s_pend, s_idle, s_t0, s_bin
     return b;
 }
@@ -756,6 +764,8 @@ static void (*pick_culled(int warps, int want_stats))(const CulledArgs)
 {
     if (warps == 16) return want_stats ? check_culled_kernel<true, 16, GOBS> : check_culled_kernel<false, 16, GOBS>;
     if (warps == 20) return want_stats ? check_culled_kernel<true, 20, GOBS> : check_culled_kernel<false, 20, GOBS>;
+    if (warps == 28) return want_stats ? check_culled_kernel<true, 28, GOBS> : check_culled_kernel<false, 28, GOBS>;
+    if (warps == 32) return want_stats ? check_culled_kernel<true, 32, GOBS> : check_culled_kernel<false, 32, GOBS>;
     return want_stats ? check_culled_kernel<true, 24, GOBS> : check_culled_kernel<false, 24, GOBS>;
 }
 
@@ -765,7 +775,7 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
 {
     const DeviceTables &t = ctx->t;
     int warps = ctx->knob_warps;
-    if (warps != 16 && warps != 20 && warps != 24) warps = kCulledWarpsDefault;
+    if (warps != 16 && warps != 20 && warps != 24 && warps != 28 && warps != 32) warps = kCulledWarpsDefault;
     // Obstacle tables go to shared memory when everything fits with at least 16 warps per CTA;
     // otherwise they stay in global memory (any obstacle size, robot tables must still fit).
     bool gobs = ctx->knob_global_obstacle;
@@ -801,7 +811,7 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
     const int sd = ctx->knob_seed_depth < 0 ? 2 : min(3, ctx->knob_seed_depth);
     a.n_seed_r = t.n_seed_r[sd]; a.n_seed_o = t.n_seed_o[sd];
     for (int q = 0; q < 8; q++) { a.seed_r[q] = t.seed_r[sd][q]; a.seed_o[q] = t.seed_o[sd][q]; }
-    a.stack_cap = gobs ? kStackCapGlobal : kStackCap;
+    a.stack_cap = stack_cap_of(warps, gobs);
     if (ctx->knob_stack_cap > 0) a.stack_cap = max(64, min(a.stack_cap, ctx->knob_stack_cap));
     if (ctx->knob_tail > 0) a.tail_thresh = min(32, ctx->knob_tail);
     if (ctx->knob_leaf > 0) a.leaf_thresh = min(8, ctx->knob_leaf);
@@ -819,16 +829,18 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
     k.sph_x = a.sph_x; k.sph_y = a.sph_y; k.sph_z = a.sph_z; k.sph_r = a.sph_r;
     k.box_cx = a.box_cx; k.box_cy = a.box_cy; k.box_cz = a.box_cz;
     k.box_ex = a.box_ex; k.box_ey = a.box_ey; k.box_ez = a.box_ez;
-    k.bound = t.rob_bound; k.n_bound = ctx->knob_bound ? t.n_rob_bound : 0;
+    for (int q = 0; q < 2 * kClassifyBoxes; q++) k.bound[q] = t.h_rob_bound[q];
+    k.n_bound = ctx->knob_bound ? t.n_rob_bound : 0;
     k.work_idx = ctx->d_work_idx; k.work_mat = ctx->d_work_mat; k.work_count = ctx->d_work_count;
     k.work_cap = ctx->work_cap;
     k.counters = ctx->d_counters;
     void (*kern)(const CulledArgs) = gobs ? pick_culled<true>(warps, want_stats) : pick_culled<false>(warps, want_stats);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const int cgrid = (int)min((n + 255) / 256, (long)ctx->sm_count * 64);
-    if (want_stats) classify_kernel<true><<<cgrid, 256, 0, stream>>>(k);
-    else classify_kernel<false><<<cgrid, 256, 0, stream>>>(k);
+    // small blocks: 100,000 configurations are only 21 warps per SM, spread them evenly
+    const int cgrid = (int)min((n + 63) / 64, (long)ctx->sm_count * 256);
+    if (want_stats) classify_kernel<true><<<cgrid, 64, 0, stream>>>(k);
+    else classify_kernel<false><<<cgrid, 64, 0, stream>>>(k);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
 
     // step 2: the remaining configurations, one warp each; programmatic dependent launch, so the

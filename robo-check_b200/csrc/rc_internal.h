@@ -41,8 +41,8 @@ struct DeviceTables {
     float rob_box_c[3], rob_box_e[3];
     // boxes (local frame) of a k-d partition of ALL robot vertices: a much tighter outer bound of
     // the exact vertex AABB than the single rotated box; two float4 (centre, half extent) each
-    float4 *rob_bound = nullptr;
-    int n_rob_bound = 0;
+    float4 h_rob_bound[2 * 32];                // passed to classify_kernel by value (constant bank)
+    int n_rob_bound = 0;                       // 32, or 0 if the mesh is empty
     // traversal seeds: node cuts at depth 0..3 of both trees (<= 8 nodes each)
     uint32_t seed_r[4][8], seed_o[4][8];
     int n_seed_r[4], n_seed_o[4];  // robot local AABB: centre and half extent (rounded up)

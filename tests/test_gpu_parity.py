@@ -112,6 +112,7 @@ def test_culled_equals_brute_large(rc, ctx):
     {"RC_BOUND": "0"},                                        # one cost class, no vertex-group bound
     {"RC_PDL": "1"},                                          # programmatic dependent launch
     {"RC_CULLED_WARPS": "16"},
+    {"RC_CULLED_WARPS": "24"},
 ])
 def test_descent_scheduling_variants_equal_brute(rc, meshes, knobs, monkeypatch):
     """How the descent is scheduled (cost classes, hand-over of pieces between the warps of a CTA,
