@@ -258,7 +258,7 @@ int rc_create(rc_ctx **out, const float *rob_x, const float *rob_y, const float 
         ctx->knob_stack_cap = knob("RC_STACK_CAP", 0);
         ctx->knob_global_obstacle = getenv("RC_FORCE_GLOBAL_OBSTACLE") != nullptr;
         ctx->knob_share = knob("RC_SHARE", 1);
-        ctx->knob_pdl = knob("RC_PDL", 0);
+        ctx->knob_pdl = knob("RC_PDL", 1);
         ctx->knob_bound = knob("RC_BOUND", 1);
         ctx->knob_mail_slots = knob("RC_MAIL_SLOTS", 4);
         ctx->knob_donate_min = knob("RC_DONATE_MIN", 40);

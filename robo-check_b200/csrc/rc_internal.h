@@ -96,7 +96,7 @@ struct rc_ctx {
     int knob_warps = 0, knob_seed_depth = -1, knob_tail = 0, knob_leaf = 0, knob_chunk = 0;
     int knob_stack_cap = 0;  // RC_STACK_CAP: shrink the pair stack to exercise the overflow fallback
     bool knob_global_obstacle = false;
-    int knob_pdl = 0;        // RC_PDL=1: programmatic dependent launch of the descent step
+    int knob_pdl = 1;        // RC_PDL=0: no programmatic dependent launch of the descent step
     int knob_bound = 1;      // RC_BOUND=0: classify without the vertex-group boxes
     int knob_mail_slots = 4, knob_donate_min = 40;  // RC_MAIL_SLOTS, RC_DONATE_MIN
     int knob_share = 1;      // RC_SHARE=0: warps of a CTA do not hand pieces of a deep descent to each other

@@ -110,7 +110,7 @@ def test_culled_equals_brute_large(rc, ctx):
     {"RC_DONATE_MIN": "200", "RC_MAIL_SLOTS": "1"},           # one slot, rare hand-overs
     {"RC_SHARE": "0"},                                        # no hand-over at all
     {"RC_BOUND": "0"},                                        # one cost class, no vertex-group bound
-    {"RC_PDL": "1"},                                          # programmatic dependent launch
+    {"RC_PDL": "0"},                                          # plain stream order instead of the programmatic dependent launch
     {"RC_CULLED_WARPS": "16"},
     {"RC_CULLED_WARPS": "24"},
 ])
