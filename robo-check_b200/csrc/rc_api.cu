@@ -832,6 +832,11 @@ int rc_set_robot_spheres(rc_ctx *ctx, const float *xyzr, int n)
         r2 = std::max(r2, std::sqrt(d2) + (double)s[4 * k + 3]);
     }
     t.sph_bound[3] = (float)(r2 * (1.0 + 1e-6)) + 1e-4f;
+    for (int q = 0; q < 3; q++) {
+        t.sph_box_c[q] = t.sph_bound[q];
+        const double e = std::max(bhi[q] - (double)t.sph_box_c[q], (double)t.sph_box_c[q] - blo[q]);
+        t.sph_box_e[q] = (float)(e * (1.0 + 1e-6)) + 1e-4f;
+    }
     cudaError_t e;
     cudaDeviceSynchronize();  // an earlier asynchronous check may still read the old tables
     if ((e = upload(ctx, &t.sph, sorted)) || (e = upload(ctx, &t.sph_bvh, nodes)))
@@ -861,11 +866,15 @@ int rc_check_spheres(rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_v
         if (rcode != RC_OK) return rcode;
     }
     cudaSetDevice(ctx->device);
+    {
+        const int rcode = ensure_work_list(ctx, n);
+        if (rcode != RC_OK) return rcode;
+    }
     cudaError_t e = launch_check_spheres(ctx, d_confs, n, d_valid, d_bitmask, ctx->stats_on,
                                          stream_of(ctx, stream), nullptr);
     if (e == cudaErrorInvalidConfiguration)
         return set_error(ctx, RC_ERR_UNSUPPORTED, "sphere / obstacle tables do not fit");
-    ctx->launches++;
+    ctx->launches += 2;  // classify + sphere descent
     return check_cuda(ctx, e, "rc_check_spheres launch");
 }
 

@@ -32,6 +32,7 @@ struct DeviceTables {
     float4 *sph = nullptr, *sph_bvh = nullptr;
     int n_sph = 0, n_sph_nodes = 0;
     float sph_bound[4] = {0, 0, 0, 0};  // bounding sphere of the set, local frame
+    float sph_box_c[3] = {0, 0, 0}, sph_box_e[3] = {0, 0, 0};  // its local AABB (radii included), rounded up
     int n_rob_v = 0, n_rob_t = 0, n_obs_v = 0, n_obs_t = 0;
     int n_rob_nodes = 0, n_obs_nodes = 0;
     int n_rob_v_pad = 0;        // n_rob_v rounded up to 32 (padding repeats vertex 0)

@@ -27,7 +27,11 @@ struct SphereArgs {
     uint32_t *bitmask;
     unsigned long long *counters, *queue;
     long tail_begin;
-    int chunk;
+    // work list written by classify_kernel (cost class 0 only): configurations the bounding sphere /
+    // bounding box of the set could not clear, with their matrices
+    const uint32_t *work_idx;
+    const float4 *work_mat;
+    unsigned long long *work_count;
 };
 
 constexpr int kSphereWarps = 24;
@@ -80,32 +84,31 @@ __global__ void __launch_bounds__(kSphereWarps * 32, 1) check_spheres_kernel(con
     const unsigned lt = (1u << lane) - 1u;
     uint32_t *stack = s_work + warp * kWarpWork;
     uint32_t *leafq = stack + kStack;
-    unsigned long long st_clear = 0, st_valid = 0, st_invalid = 0, st_nodes = 0, st_leaves = 0,
+    unsigned long long st_valid = 0, st_invalid = 0, st_nodes = 0, st_leaves = 0,
                        st_tris = 0, st_over = 0;
+    const long n_work = (long)__ldcg(a.work_count);
+    const int chunk = (int)max(1L, min(16L, n_work / ((long)gridDim.x * kSphereWarps * 32)));
     long seen = 0;
     for (;;) {
-        const int take = (seen + a.tail_begin < a.n) ? a.chunk : 1;
+        const int take = (seen + a.tail_begin < n_work) ? chunk : 1;
         long base = 0;
-        if (lane == 0) base = (long)atomicAdd(a.queue, (unsigned long long)take);
+        if (lane == 0) base = (long)atomicAdd(a.work_count + kWorkBins, (unsigned long long)take);
         base = __shfl_sync(kFull, base, 0);
-        if (base >= a.n) break;
+        if (base >= n_work) break;
         seen = base;
-        const long end = min(base + (long)take, a.n);
-        for (long i = base; i < end; i++) {
-            const Mat34 m = load_matrix(a.confs, i);
-            bool hit = false, done = false;
-            {   // the whole set lies inside its bounding sphere
-                const float sx = fmaf(m.r02, a.bs_z, fmaf(m.r01, a.bs_y, fmaf(m.r00, a.bs_x, m.tx)));
-                const float sy = fmaf(m.r12, a.bs_z, fmaf(m.r11, a.bs_y, fmaf(m.r10, a.bs_x, m.ty)));
-                const float sz = fmaf(m.r22, a.bs_z, fmaf(m.r21, a.bs_y, fmaf(m.r20, a.bs_x, m.tz)));
-                const float gx = a.bs_r + 0.01f + 4e-6f * (fabsf(sx) + a.bs_r);
-                const float gy = a.bs_r + 0.01f + 4e-6f * (fabsf(sy) + a.bs_r);
-                const float gz = a.bs_r + 0.01f + 4e-6f * (fabsf(sz) + a.bs_r);
-                done = sx - gx > a.obs_box.x_max || sx + gx < a.obs_box.x_min ||
-                       sy - gy > a.obs_box.y_max || sy + gy < a.obs_box.y_min ||
-                       sz - gz > a.obs_box.z_max || sz + gz < a.obs_box.z_min;
-                if (STATS && done) st_clear++;
+        const long end = min(base + (long)take, n_work);
+        for (long w = base; w < end; w++) {
+            const long i = (long)__ldcg(a.work_idx + w);
+            Mat34 m;
+            {
+                const float4 q0 = __ldcg(a.work_mat + 3 * i), q1 = __ldcg(a.work_mat + 3 * i + 1),
+                             q2 = __ldcg(a.work_mat + 3 * i + 2);
+                m.r00 = q0.x; m.r01 = q0.y; m.r02 = q0.z; m.tx = q0.w;
+                m.r10 = q1.x; m.r11 = q1.y; m.r12 = q1.z; m.ty = q1.w;
+                m.r20 = q2.x; m.r21 = q2.y; m.r22 = q2.z; m.tz = q2.w;
             }
+            bool hit = false;
+            const bool done = false;  // step 1 (classify_kernel) has cleared what the bounds can clear
             if (!done) {
                 int sp = 1, lq = 0;
                 bool overflow = false;
@@ -211,7 +214,6 @@ __global__ void __launch_bounds__(kSphereWarps * 32, 1) check_spheres_kernel(con
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) st_tris += __shfl_xor_sync(kFull, st_tris, o);
         if (lane == 0) {
-            atomicAdd(a.counters + CNT_SPHERE_CLEARED, st_clear);
             atomicAdd(a.counters + CNT_NARROW_VALID, st_valid);
             atomicAdd(a.counters + CNT_NARROW_INVALID, st_invalid);
             atomicAdd(a.counters + CNT_NODE_PAIRS, st_nodes);
@@ -219,6 +221,13 @@ __global__ void __launch_bounds__(kSphereWarps * 32, 1) check_spheres_kernel(con
             atomicAdd(a.counters + CNT_TRI_PAIRS, st_tris);
             atomicAdd(a.counters + CNT_OVERFLOW, st_over);
         }
+    }
+    // the last CTA to finish leaves the list counters at zero for the next call (as the mesh path does)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(a.work_count + kWorkBins + 1, 1ULL) == (unsigned long long)gridDim.x - 1ULL)
+            for (int q = 0; q < kWorkBins + 2; q++) a.work_count[q] = 0;
     }
 }
 
@@ -231,9 +240,7 @@ cudaError_t launch_check_spheres(const rc_ctx *ctx, const rc_config *d_confs, lo
     if (t.n_sph <= 0) return cudaErrorInvalidConfiguration;
     cudaError_t e;
     if (!queue) queue = ctx->d_counters + CNT_QUEUE;
-    if ((e = cudaMemsetAsync(queue, 0, sizeof(unsigned long long), stream)) != cudaSuccess) return e;
-    if (d_bitmask && (e = cudaMemsetAsync(d_bitmask, 0, (size_t)((n + 31) / 32) * 4, stream)) != cudaSuccess)
-        return e;
+    if (!ctx->d_work_idx || ctx->work_cap < n) return cudaErrorMemoryAllocation;  // rc_check_spheres sizes it
     auto smem_bytes = [&](bool gobs) {
         size_t b = 16 + (size_t)t.n_sph * 16 + (size_t)t.n_sph_nodes * 32;
         if (!gobs) b += (size_t)t.n_obs_nodes * 32 + (size_t)t.n_obs_t * 48;
@@ -256,7 +263,22 @@ cudaError_t launch_check_spheres(const rc_ctx *ctx, const rc_config *d_confs, lo
     a.confs = d_confs; a.n = n; a.valid = d_valid; a.bitmask = d_bitmask;
     a.counters = ctx->d_counters; a.queue = queue;
     const int grid = ctx->sm_count;
-    a.chunk = (int)max(1L, min(16L, n / ((long)grid * kSphereWarps * 32)));
+    a.work_idx = ctx->d_work_idx; a.work_mat = ctx->d_work_mat; a.work_count = ctx->d_work_count;
+    // step 1: the per-thread classify kernel of the mesh path with the bounds of the sphere set
+    // (bounding sphere, rotated local box; no vertex groups, so everything lands in cost class 0);
+    // it writes the flags and whole bitmask words of the configurations it clears
+    ClassifyArgs k{};
+    k.confs = d_confs; k.n = n; k.valid = d_valid; k.bitmask = d_bitmask; k.obs_box = t.obs_box;
+    k.sph_x = a.bs_x; k.sph_y = a.bs_y; k.sph_z = a.bs_z; k.sph_r = a.bs_r;
+    k.box_cx = t.sph_box_c[0]; k.box_cy = t.sph_box_c[1]; k.box_cz = t.sph_box_c[2];
+    k.box_ex = t.sph_box_e[0]; k.box_ey = t.sph_box_e[1]; k.box_ez = t.sph_box_e[2];
+    k.n_bound = 0;
+    k.work_idx = ctx->d_work_idx; k.work_mat = ctx->d_work_mat; k.work_cap = ctx->work_cap;
+    k.work_count = ctx->d_work_count; k.counters = ctx->d_counters;
+    const int cgrid = (int)min((n + 63) / 64, (long)ctx->sm_count * 256);
+    if (want_stats) classify_kernel<true><<<cgrid, 64, 0, stream>>>(k);
+    else classify_kernel<false><<<cgrid, 64, 0, stream>>>(k);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
     a.tail_begin = (long)grid * kSphereWarps * 4;
     void (*kern)(const SphereArgs) =
         gobs ? (want_stats ? check_spheres_kernel<true, true> : check_spheres_kernel<false, true>)
@@ -264,7 +286,9 @@ cudaError_t launch_check_spheres(const rc_ctx *ctx, const rc_config *d_confs, lo
     if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
         return e;
     kern<<<grid, kSphereWarps * 32, smem, stream>>>(a);
-    return cudaGetLastError();
+    if ((e = cudaGetLastError()) != cudaSuccess)  // nobody will reset the list counters step 1 filled
+        cudaMemsetAsync(ctx->d_work_count, 0, kWorkCounters * sizeof(unsigned long long), stream);
+    return e;
 }
 
 }  // namespace rc
