@@ -42,7 +42,7 @@ for name, m in (("valid", v[listed] == 1), ("colliding", v[listed] == 0)):
     print(f"  {name:9s} {m.sum():6d}: mean {cc.mean():.0f} p99 {np.percentile(cc, 99):.0f} max {cc.max()}")
 print(f"last decision {fin.max():.1f} us after the first; 50/90/99/99.9 % decided after "
       + "/".join(f"{np.percentile(fin, q):.1f}" for q in (50, 90, 99, 99.9)) + " us")
-warps = 148 * 24
+warps = 148 * 32
 print(f"sum of cycles / {warps} warps = {c.sum() / warps:.0f} cycles = {c.sum() / warps / 1.965e3:.1f} us at 1965 MHz; "
       f"longest single configuration {c.max() / 1.965e3:.1f} us")
 order = np.argsort(fin)[-10:]
