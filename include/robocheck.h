@@ -97,6 +97,8 @@ int rc_check_host(rc_ctx *ctx, const rc_config *h_confs, long n, uint8_t *h_vali
  * (Multi-process callers -- one rank per GPU -- use rc_check + ncclAllGather on the bitmask
  * instead, see robo-check_b200/sharding.py and bench.py.) */
 int rc_shard_size(long n, int n_gpus);
+/* CUDA devices visible to this process (0 and RC_ERR_NO_DEVICE when there is none). */
+int rc_device_count(int *count);
 int rc_check_multi(rc_ctx **ctxs, int n_gpus, const rc_config *h_confs, long n, uint32_t *h_bitmask,
                    uint8_t *h_valid, uint32_t **d_bitmask_all);
 

@@ -57,6 +57,7 @@ ABI = [
     ("rc_check", _i, [_vp, _vp, _l, _vp, _vp, _i, _vp]),
     ("rc_check_host", _i, [_vp, _vp, _l, _vp, _i]),
     ("rc_shard_size", _i, [_l, _i]),
+    ("rc_device_count", _i, [C.POINTER(_i)]),
     ("rc_check_multi", _i, [_vp, _i, _vp, _l, _vp, _vp, _vp]),
     ("rc_transform_aos", _i, [_vp, _vp, _l, _vp, _i, _vp, _vp]),
     ("rc_generate_aabb", _i, [_vp, _vp, _u, _u, _vp, _vp]),

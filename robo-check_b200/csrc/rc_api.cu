@@ -502,6 +502,19 @@ int rc_check_host(rc_ctx *ctx, const rc_config *h_confs, long n, uint8_t *h_vali
     return RC_OK;
 }
 
+int rc_device_count(int *count)
+{
+    if (!count) return RC_ERR_INVALID;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        *count = 0;
+        return RC_ERR_NO_DEVICE;
+    }
+    *count = n;
+    return RC_OK;
+}
+
 int rc_shard_size(long n, int n_gpus)
 {
     if (n < 0 || n_gpus <= 0) return RC_ERR_INVALID;

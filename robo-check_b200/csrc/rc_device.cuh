@@ -27,12 +27,9 @@ struct Mat34 {  // rows of [R | t]; the 4th matrix row (0,0,0,1) is never used
 
 // createTransformationMatrix, broad-phase-fused.cu:26-55 (A = yaw, B = pitch, C = roll).
 // sinf/cosf are the same libdevice routines the reference inlines.
-__device__ __forceinline__ Mat34 make_matrix(float x, float y, float z, float pitch, float yaw,
-                                             float roll)
+__device__ __forceinline__ Mat34 matrix_from_trig(float x, float y, float z, float sA, float cA, float sB,
+                                                  float cB, float sC, float cC)
 {
-    const float cB = cosf(pitch), sB = sinf(pitch);
-    const float cA = cosf(yaw), sA = sinf(yaw);
-    const float cC = cosf(roll), sC = sinf(roll);
     const float cAsB = __fmul_rn(cA, sB);
     const float sAsB = __fmul_rn(sA, sB);
     Mat34 m;
@@ -49,6 +46,29 @@ __device__ __forceinline__ Mat34 make_matrix(float x, float y, float z, float pi
     m.r22 = __fmul_rn(cB, cC);
     m.tz = z;
     return m;
+}
+
+__device__ __forceinline__ Mat34 make_matrix(float x, float y, float z, float pitch, float yaw,
+                                             float roll)
+{
+    const float cB = cosf(pitch), sB = sinf(pitch);
+    const float cA = cosf(yaw), sA = sinf(yaw);
+    const float cC = cosf(roll), sC = sinf(roll);
+    return matrix_from_trig(x, y, z, sA, cA, sB, cB, sC, cC);
+}
+
+// The same matrix for a whole warp working on ONE configuration: lanes 0, 1, 2 evaluate the sine and
+// cosine of yaw, pitch, roll (the other lanes repeat roll), six shuffles hand them round -- a third
+// of the trigonometry of make_matrix in every lane, same values bit for bit.
+__device__ __forceinline__ Mat34 make_matrix_warp(float x, float y, float z, float pitch, float yaw,
+                                                  float roll, int lane)
+{
+    const float ang = lane == 0 ? yaw : lane == 1 ? pitch : roll;
+    const float s = sinf(ang), c = cosf(ang);
+    const float sA = __shfl_sync(0xffffffffu, s, 0), cA = __shfl_sync(0xffffffffu, c, 0);
+    const float sB = __shfl_sync(0xffffffffu, s, 1), cB = __shfl_sync(0xffffffffu, c, 1);
+    const float sC = __shfl_sync(0xffffffffu, s, 2), cC = __shfl_sync(0xffffffffu, c, 2);
+    return matrix_from_trig(x, y, z, sA, cA, sB, cB, sC, cC);
 }
 
 // transformVector(Vector3f, Matrix4f), broad-phase-fused.cu:84-105: each row accumulates

@@ -72,6 +72,14 @@ __device__ __forceinline__ Mat34 load_matrix(const rc_config *confs, long i)
     return make_matrix(a.x, a.y, b.x, b.y, c.x, c.y);
 }
 
+// one configuration per warp (all lanes call it with the same i)
+__device__ __forceinline__ Mat34 load_matrix_warp(const rc_config *confs, long i, int lane)
+{
+    const float2 *p = reinterpret_cast<const float2 *>(confs + i);
+    const float2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    return make_matrix_warp(a.x, a.y, b.x, b.y, c.x, c.y, lane);
+}
+
 // Transform every robot vertex of one configuration with the lanes striding over the
 // (padded) vertex table, reduce the AABB with warp shuffles.  All lanes return the box.
 __device__ __forceinline__ void warp_aabb(const Mat34 &m, const float4 *__restrict__ s_rob_v,

@@ -38,11 +38,12 @@ __global__ void __launch_bounds__(kStageThreads) transform_soa_kernel(
                      ((reinterpret_cast<uintptr_t>(oy) & 15) == 0) &&
                      ((reinterpret_cast<uintptr_t>(oz) & 15) == 0);
     for (long i = warp; i < n; i += n_warps) {
-        const Mat34 m = load_matrix(confs, i);
+        const Mat34 m = load_matrix_warp(confs, i, lane);
         float lx = FLT_MAX, ly = FLT_MAX, lz = FLT_MAX, hx = -FLT_MAX, hy = -FLT_MAX, hz = -FLT_MAX;
         const size_t row = (size_t)i * n_v;
         if (vec) {
-            for (int v = 4 * lane; v < n_v; v += 128) {
+            const int n_full = n_v & ~127;  // whole groups of 128 vertices: four per lane
+            for (int v = 4 * lane; v < n_full; v += 128) {
                 const float4 X = *reinterpret_cast<const float4 *>(sx + v);
                 const float4 Y = *reinterpret_cast<const float4 *>(sy + v);
                 const float4 Z = *reinterpret_cast<const float4 *>(sz + v);
@@ -60,6 +61,16 @@ __global__ void __launch_bounds__(kStageThreads) transform_soa_kernel(
                 hy = fmaxf(hy, fmaxf(fmaxf(wy.x, wy.y), fmaxf(wy.z, wy.w)));
                 lz = fminf(lz, fminf(fminf(wz.x, wz.y), fminf(wz.z, wz.w)));
                 hz = fmaxf(hz, fmaxf(fmaxf(wz.x, wz.y), fmaxf(wz.z, wz.w)));
+            }
+            // the rest (24 of 792 vertices) one per lane: a quarter of the instructions of another
+            // four-per-lane step in which six lanes would work
+            for (int v = n_full + lane; v < n_v; v += 32) {
+                float x, y, z;
+                xform(m, sx[v], sy[v], sz[v], x, y, z);
+                __stcs(ox + row + v, x); __stcs(oy + row + v, y); __stcs(oz + row + v, z);
+                lx = fminf(lx, x); hx = fmaxf(hx, x);
+                ly = fminf(ly, y); hy = fmaxf(hy, y);
+                lz = fminf(lz, z); hz = fmaxf(hz, z);
             }
         } else {
             for (int v = lane; v < n_v; v += 32) {
@@ -130,7 +141,7 @@ __global__ void __launch_bounds__(kStageThreads) transform_aos_kernel(
     float *of = reinterpret_cast<float *>(out);
     const bool vec = (n_v % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     for (long i = warp; i < n; i += n_warps) {
-        const Mat34 m = load_matrix(confs, i);
+        const Mat34 m = load_matrix_warp(confs, i, lane);
         float *row = of + 3 * (size_t)i * n_v;
         for (int v0 = 0; v0 < n_v; v0 += 128) {
             const int v = v0 + 4 * lane;

@@ -452,6 +452,13 @@ def test_cpp_harness_end_to_end(rc, golden, tmp_path):
                               os.path.join(rc.ASSET_DIR, "obstacle.g")], capture_output=True, text=True)
         assert out.returncode == 0, out.stdout + out.stderr
         assert f"{n_valid} valid" in out.stdout and "0 disagreements" in out.stdout
+        # the same program through rc_check_multi of the C ABI (three contexts, device index modulo
+        # the devices present)
+        out = subprocess.run([cli, conf, os.path.join(rc.ASSET_DIR, "robot.g"),
+                              os.path.join(rc.ASSET_DIR, "obstacle.g"), "--gpus", "3"], capture_output=True, text=True)
+        assert out.returncode == 0, out.stdout + out.stderr
+        assert "rc_check_multi over 3 contexts" in out.stdout
+        assert f"{n_valid} valid" in out.stdout and "0 disagreements" in out.stdout
 
 
 # ---- sphere-approximated robot (BASELINE config 3; this repo's own definition) -----------------
