@@ -47,7 +47,16 @@ typedef struct { float x_min, y_min, z_min, x_max, y_max, z_max; } rc_aabb;     
 typedef struct rc_ctx rc_ctx;
 typedef struct rc_mesh rc_mesh;
 
-/* rc_check modes */
+/* rc_check modes.
+ * RC_MODE_BRUTE decides every pair the reference decides: its flags equal the reference's on any
+ * input.  RC_MODE_CULLED never looks at a pair whose triangles are separated by more than 2e-3 (an
+ * ancestor box pair is disjoint).  The reference's arithmetic agrees with that on well-conditioned
+ * pairs, and on the alpha1.0 scene always (0 of 86,410 reported pairs were box-disjoint; 0 flag
+ * differences on 600,000 configurations against the reference pipeline).  It does NOT
+ * agree for nearly coplanar triangle pairs: there the reference's intersection line is rounding
+ * noise and it can report two triangles that lie far apart inside their common plane
+ * (tests/coplanar_scene.py has one such configuration in 3,000).  RC_MODE_CULLED calls such a
+ * configuration valid, i.e. where the two modes differ the culled answer is the geometric one. */
 #define RC_MODE_CULLED 0 /* BVH-culled fused kernel (default, fastest)                        */
 #define RC_MODE_BRUTE 1  /* fused kernel, all n_rob_t x n_obs_t pairs: the reference's sweep  */
 
@@ -171,6 +180,22 @@ int rc_set_robot_spheres(rc_ctx *ctx, const float *xyzr, int n);
 int rc_robot_spheres(const rc_ctx *ctx, float *xyzr_out, int *n); /* xyzr_out may be NULL */
 int rc_check_spheres(rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_valid,
                      uint32_t *d_bitmask, void *stream);
+
+/* ---- coplanar pairs -----------------------------------------------------------
+ * A pair that passes both plane tests and whose planes is_coplanar_sep calls proportional
+ * (narrow-phase/narrow-phase.cu:297-338) is not decided by the reference kernel: it sets
+ * req_coplanar, prints "Error: require coplanar intersection" and goes on (:647-652, :680), so
+ * such a pair never makes a configuration invalid.  RC_COPLANAR_SKIP (default) reproduces that,
+ * flags stay bit-identical to the reference pipeline.  RC_COPLANAR_DECIDE decides the pair in the
+ * common plane the way the reference's design model does (python/narrow.py:98-177: edge-edge
+ * intersections, then containment): both triangles are projected along the dominant axis of the
+ * robot triangle's normal, the nine edge pairs are tested (touching counts), then one vertex of
+ * each triangle for containment in the other.  Applies to rc_check (both modes), rc_check_host,
+ * rc_check_multi, rc_megakernel and rc_narrow_phase of this context; not to rc_check_spheres. */
+#define RC_COPLANAR_SKIP 0
+#define RC_COPLANAR_DECIDE 1
+int rc_set_coplanar_mode(rc_ctx *ctx, int mode);
+int rc_coplanar_mode(const rc_ctx *ctx);
 
 /* ---- measurement ------------------------------------------------------------------------- */
 typedef struct {

@@ -8,6 +8,11 @@ extern "C" {
 
 #define RCO_VARIANT_GPU 0  /* broadPhaseFusedKernel_sep + narrowPhaseKernel_coarse */
 #define RCO_VARIANT_HOST 1 /* narrowPhaseBaseline (reference CPU brute force)       */
+/* or-ed into a variant: pairs the reference leaves undecided for coplanarity
+ * (narrow-phase.cu:647-652) are decided in the common plane (python/narrow.py:98-177);
+ * mirrors RC_COPLANAR_DECIDE of the product.  Not reference behaviour: parity of this
+ * mode is pinned only against the product's own definition.                          */
+#define RCO_FLAG_COPLANAR 0x10
 
 typedef struct { float x, y, z, pitch, yaw, roll; } rco_config;            /* Utils_rai.h:51-58 */
 typedef struct { float x_min, y_min, z_min, x_max, y_max, z_max; } rco_aabb_t; /* Utils_rai.h:87-95 */
@@ -42,6 +47,7 @@ void rco_canonicalize(const float d[3], int idx[3]);
 float rco_param(const float v0[3], const float v1[3], float d0, float d1, const float D[3],
                 const float O[3], int fused);
 int rco_is_coplanar(const float N1[3], float d1, const float N2[3], float d2);
+int rco_coplanar_overlap(const float r[9], const float o[9], const float Nr[3]);
 int rco_pair_hits(const float r[9], const float o[9], int variant, int *coplanar);
 
 int rco_check(const rco_mesh *rob, const rco_mesh *obs, const rco_config *confs, long n,

@@ -10,6 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "liboracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libref.so")
 VARIANT_GPU, VARIANT_HOST = 0, 1
+FLAG_COPLANAR = 0x10  # or-ed into a variant: decide coplanar pairs in the plane (RC_COPLANAR_DECIDE)
 
 
 class rco_mesh(C.Structure):
@@ -116,6 +117,10 @@ def pair_hits(r9, o9, variant=VARIANT_GPU):
     cop = C.c_int()
     h = lib().rco_pair_hits(_p(_f(r9)), _p(_f(o9)), variant, C.byref(cop))
     return int(h), int(cop.value)
+
+
+def coplanar_overlap(r9, o9, normal3):
+    return int(lib().rco_coplanar_overlap(_p(_f(r9)), _p(_f(o9)), _p(_f(normal3))))
 
 
 def check_spheres(spheres, obs, confs, nthreads=None):

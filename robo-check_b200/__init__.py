@@ -22,6 +22,7 @@ RC_OK = 0
 RC_ERR_INVALID, RC_ERR_CUDA, RC_ERR_NOMEM, RC_ERR_IO = -1, -2, -3, -4
 RC_ERR_FORMAT, RC_ERR_UNSUPPORTED, RC_ERR_NO_DEVICE = -5, -6, -7
 RC_MODE_CULLED, RC_MODE_BRUTE = 0, 1
+RC_COPLANAR_SKIP, RC_COPLANAR_DECIDE = 0, 1
 
 # Configuration = 6 x f32 (x, y, z, pitch, yaw, roll), Utils_rai.h:51-58
 CONFIG_DTYPE = np.dtype(np.float32)
@@ -74,6 +75,8 @@ ABI = [
     ("rc_set_robot_spheres", _i, [_vp, _vp, _i]),
     ("rc_robot_spheres", _i, [_vp, _vp, C.POINTER(_i)]),
     ("rc_check_spheres", _i, [_vp, _vp, _l, _vp, _vp, _vp]),
+    ("rc_set_coplanar_mode", _i, [_vp, _i]),
+    ("rc_coplanar_mode", _i, [_vp]),
     ("rc_stats_enable", _i, [_vp, _i]),
     ("rc_stats_read", _i, [_vp, C.POINTER(rc_stats), _i]),
     ("rc_stats_trace", _i, [_vp, _vp]),
@@ -424,6 +427,14 @@ class Context:
     def check_spheres(self, d_confs, n, d_valid=None, d_bitmask=None, stream=None):
         _check(_lib.rc_check_spheres(self._h, _ptr(d_confs), int(n), _ptr(d_valid), _ptr(d_bitmask),
                                      _stream_ptr(stream)), self._h)
+
+    # coplanar pairs ------------------------------------------------------------------
+    def set_coplanar_mode(self, mode):
+        """RC_COPLANAR_SKIP (reference behaviour, narrow-phase.cu:647-652,680) or RC_COPLANAR_DECIDE."""
+        _check(_lib.rc_set_coplanar_mode(self._h, int(mode)), self._h)
+
+    def coplanar_mode(self):
+        return int(_lib.rc_coplanar_mode(self._h))
 
     # measurement -----------------------------------------------------------------------------------
     def stats_enable(self, on=True):

@@ -893,6 +893,19 @@ int rc_check_spheres(rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_v
     return check_cuda(ctx, e, "rc_check_spheres launch");
 }
 
+// ---- coplanar pairs ------------------------------------------------------------
+
+int rc_set_coplanar_mode(rc_ctx *ctx, int mode)
+{
+    if (!ctx) return RC_ERR_INVALID;
+    if (mode != RC_COPLANAR_SKIP && mode != RC_COPLANAR_DECIDE)
+        return set_error(ctx, RC_ERR_INVALID, "coplanar mode must be RC_COPLANAR_SKIP or RC_COPLANAR_DECIDE");
+    ctx->coplanar_mode = mode;
+    return RC_OK;
+}
+
+int rc_coplanar_mode(const rc_ctx *ctx) { return ctx ? ctx->coplanar_mode : RC_ERR_INVALID; }
+
 // ---- measurement --------------------------------------------------------------------------
 
 int rc_stats_enable(rc_ctx *ctx, int on)

@@ -104,6 +104,7 @@ __device__ __forceinline__ bool boxes_overlap(const Mat34 &m, const float4 r0, c
 
 // Exhaustive sweep for one configuration, used only when the pair stack overflows (never
 // observed); kept small on purpose: lane = robot triangle, obstacle triangles broadcast.
+template <bool COP>
 __device__ __noinline__ bool narrow_exhaustive(const Mat34 m, const float4 *s_rob_v,
                                                const uint2 *s_rob_t, int n_rob_t,
                                                const float4 *s_obs_a, const float4 *s_obs_b,
@@ -123,7 +124,7 @@ __device__ __noinline__ bool narrow_exhaustive(const Mat34 m, const float4 *s_ro
             const float4 oa = s_obs_a[k], ob = s_obs_b[k], oc = s_obs_c[k];
             const Tri o = {oa.x, oa.y, oa.z, ob.x, ob.y, ob.z, oc.x, oc.y, oc.z};
             const Plane po = {oa.w, ob.w, oc.w, s_obs_d[k]};
-            if (pair_hits(r, pr, o, po)) hit = true;
+            if (pair_hits<COP>(r, pr, o, po)) hit = true;
         }
         hit = __any_sync(kFull, hit);
     }
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(64) classify_kernel(const __grid_constant__ Cl
 // GOBS = obstacle tables (BVH + triangles) stay in global memory (L2-resident) instead of being
 // staged into shared memory: meshes of any size (BASELINE config 5, the subdivided obstacle).
 // Pair encodings then use 11 bits for the robot side and 21 bits for the obstacle side.
-template <bool STATS, int WARPS, bool GOBS>
+template <bool STATS, int WARPS, bool GOBS, bool COP>
 __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const CulledArgs a)
 {
     constexpr int SH = GOBS ? 21 : 16;
@@ -586,7 +587,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
                             dO2 = sdist(pr, o.cx, o.cy, o.cz);
                 const float dR0 = sdist(po, r.ax, r.ay, r.az), dR1 = sdist(po, r.bx, r.by, r.bz),
                             dR2 = sdist(po, r.cx, r.cy, r.cz);
-                const bool h = act && pair_tail(r, pr, dR0, dR1, dR2, o, po, dO0, dO1, dO2);
+                const int verdict = act ? pair_tail(r, pr, dR0, dR1, dR2, o, po, dO0, dO1, dO2) : kPairMiss;
+                bool h = verdict == kPairHit;
+                if constexpr (COP) {  // RC_COPLANAR_DECIDE: the undecided pairs are decided in the common plane
+                    if (verdict == kPairCoplanar) h = coplanar_overlap(r, o, pr);
+                }
                 if (STATS) { st_tails += cnt; st_tr++; tr_tails++; }
                 if (__any_sync(kFull, h)) { hit = true; break; }
                 __syncwarp();
@@ -690,10 +695,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
         if (overflow) {
             if (STATS) st_over++;
             if constexpr (GOBS)
-                hit = narrow_exhaustive(m, s_rob_v, s_rob_t, c.n_rob_t, c.obs_a, c.obs_b, c.obs_c,
+                hit = narrow_exhaustive<COP>(m, s_rob_v, s_rob_t, c.n_rob_t, c.obs_a, c.obs_b, c.obs_c,
                                         c.obs_d, c.n_obs_t, lane);
             else
-                hit = narrow_exhaustive(m, s_rob_v, s_rob_t, c.n_rob_t, s_obs_a, s_obs_b, s_obs_c,
+                hit = narrow_exhaustive<COP>(m, s_rob_v, s_rob_t, c.n_rob_t, s_obs_a, s_obs_b, s_obs_c,
                                         s_obs_d, c.n_obs_t, lane);
         }
         __syncwarp();
@@ -767,14 +772,14 @@ static size_t culled_smem_bytes(const DeviceTables &t, int warps, bool gobs)
     return b;
 }
 
-template <bool GOBS>
+template <bool GOBS, bool COP>
 static void (*pick_culled(int warps, int want_stats))(const CulledArgs)
 {
-    if (warps == 16) return want_stats ? check_culled_kernel<true, 16, GOBS> : check_culled_kernel<false, 16, GOBS>;
-    if (warps == 20) return want_stats ? check_culled_kernel<true, 20, GOBS> : check_culled_kernel<false, 20, GOBS>;
-    if (warps == 28) return want_stats ? check_culled_kernel<true, 28, GOBS> : check_culled_kernel<false, 28, GOBS>;
-    if (warps == 32) return want_stats ? check_culled_kernel<true, 32, GOBS> : check_culled_kernel<false, 32, GOBS>;
-    return want_stats ? check_culled_kernel<true, 24, GOBS> : check_culled_kernel<false, 24, GOBS>;
+    if (warps == 16) return want_stats ? check_culled_kernel<true, 16, GOBS, COP> : check_culled_kernel<false, 16, GOBS, COP>;
+    if (warps == 20) return want_stats ? check_culled_kernel<true, 20, GOBS, COP> : check_culled_kernel<false, 20, GOBS, COP>;
+    if (warps == 28) return want_stats ? check_culled_kernel<true, 28, GOBS, COP> : check_culled_kernel<false, 28, GOBS, COP>;
+    if (warps == 32) return want_stats ? check_culled_kernel<true, 32, GOBS, COP> : check_culled_kernel<false, 32, GOBS, COP>;
+    return want_stats ? check_culled_kernel<true, 24, GOBS, COP> : check_culled_kernel<false, 24, GOBS, COP>;
 }
 
 cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, long n,
@@ -843,7 +848,11 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
     k.work_idx = ctx->d_work_idx; k.work_mat = ctx->d_work_mat; k.work_count = ctx->d_work_count;
     k.work_cap = ctx->work_cap;
     k.counters = ctx->d_counters;
-    void (*kern)(const CulledArgs) = gobs ? pick_culled<true>(warps, want_stats) : pick_culled<false>(warps, want_stats);
+    void (*kern)(const CulledArgs);
+    if (ctx->coplanar_mode)
+        kern = gobs ? pick_culled<true, true>(warps, want_stats) : pick_culled<false, true>(warps, want_stats);
+    else
+        kern = gobs ? pick_culled<true, false>(warps, want_stats) : pick_culled<false, false>(warps, want_stats);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     // small blocks: 100,000 configurations are only 21 warps per SM, spread them evenly

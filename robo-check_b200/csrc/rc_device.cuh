@@ -219,11 +219,87 @@ __device__ __forceinline__ void tri_interval(const Tri &t, float d0, float d1, f
 
 // Everything after the two plane tests of narrowPhaseKernel_coarse (:639-670):
 // coplanarity skip, intersection line, canonical order, parametric intervals, interval test.
-// Returns true when the pair makes the configuration invalid.
-__device__ __noinline__ bool pair_tail(const Tri r, const Plane pr, float dR0, float dR1, float dR2,
-                                       const Tri o, const Plane po, float dO0, float dO1, float dO2)
+// ---- optional decision of coplanar pairs ----------------------------------------
+// The reference's kernel only prints "Error: require coplanar intersection" for a pair whose planes
+// is_coplanar_sep calls proportional and moves on (narrow-phase.cu:647-652, :680); its Python design
+// model decides such pairs in the common plane (python/narrow.py:98-177: edge-edge intersections,
+// then containment).  With coplanar mode 1 the pair is decided here the same way -- both triangles
+// projected along the dominant axis of the robot triangle's normal, the nine edge pairs tested for
+// intersection (orientation signs, touching counts), then containment of a vertex of one triangle in
+// the other (done exactly; the model's box comparison is only a sketch).  Every operation is rounded
+// individually so that the CPU checker reproduces the decision bit for bit.  Default mode 0 = the
+// reference's behaviour: flags are unchanged.
+__device__ __forceinline__ float orient2(float ax, float ay, float bx, float by, float cx, float cy)
 {
-    if (is_coplanar(pr, po)) return false;
+    return __fsub_rn(__fmul_rn(__fsub_rn(bx, ax), __fsub_rn(cy, ay)),
+                     __fmul_rn(__fsub_rn(by, ay), __fsub_rn(cx, ax)));
+}
+__device__ __forceinline__ bool on_seg2(float ax, float ay, float bx, float by, float px, float py)
+{
+    return fminf(ax, bx) <= px && px <= fmaxf(ax, bx) && fminf(ay, by) <= py && py <= fmaxf(ay, by);
+}
+__device__ __forceinline__ bool seg_meet2(float p1x, float p1y, float p2x, float p2y, float p3x, float p3y,
+                                          float p4x, float p4y)
+{
+    const float d1 = orient2(p3x, p3y, p4x, p4y, p1x, p1y), d2 = orient2(p3x, p3y, p4x, p4y, p2x, p2y);
+    const float d3 = orient2(p1x, p1y, p2x, p2y, p3x, p3y), d4 = orient2(p1x, p1y, p2x, p2y, p4x, p4y);
+    if (((d1 > 0.f && d2 < 0.f) || (d1 < 0.f && d2 > 0.f)) && ((d3 > 0.f && d4 < 0.f) || (d3 < 0.f && d4 > 0.f)))
+        return true;
+    if (d1 == 0.f && on_seg2(p3x, p3y, p4x, p4y, p1x, p1y)) return true;
+    if (d2 == 0.f && on_seg2(p3x, p3y, p4x, p4y, p2x, p2y)) return true;
+    if (d3 == 0.f && on_seg2(p1x, p1y, p2x, p2y, p3x, p3y)) return true;
+    if (d4 == 0.f && on_seg2(p1x, p1y, p2x, p2y, p4x, p4y)) return true;
+    return false;
+}
+__device__ __forceinline__ bool inside2(const float t[6], float px, float py)
+{
+    const float o1 = orient2(t[0], t[1], t[2], t[3], px, py), o2 = orient2(t[2], t[3], t[4], t[5], px, py),
+                o3 = orient2(t[4], t[5], t[0], t[1], px, py);
+    return (o1 >= 0.f && o2 >= 0.f && o3 >= 0.f) || (o1 <= 0.f && o2 <= 0.f && o3 <= 0.f);
+}
+__device__ __noinline__ bool coplanar_overlap(const Tri r, const Tri o, const Plane pr)
+{
+    const float ax = fabsf(pr.nx), ay = fabsf(pr.ny), az = fabsf(pr.nz);
+    const int drop = (az >= ax && az >= ay) ? 2 : (ay >= ax ? 1 : 0);
+    float a[6], b[6];
+    if (drop == 2) {
+        a[0] = r.ax; a[1] = r.ay; a[2] = r.bx; a[3] = r.by; a[4] = r.cx; a[5] = r.cy;
+        b[0] = o.ax; b[1] = o.ay; b[2] = o.bx; b[3] = o.by; b[4] = o.cx; b[5] = o.cy;
+    } else if (drop == 1) {
+        a[0] = r.ax; a[1] = r.az; a[2] = r.bx; a[3] = r.bz; a[4] = r.cx; a[5] = r.cz;
+        b[0] = o.ax; b[1] = o.az; b[2] = o.bx; b[3] = o.bz; b[4] = o.cx; b[5] = o.cz;
+    } else {
+        a[0] = r.ay; a[1] = r.az; a[2] = r.by; a[3] = r.bz; a[4] = r.cy; a[5] = r.cz;
+        b[0] = o.ay; b[1] = o.az; b[2] = o.by; b[3] = o.bz; b[4] = o.cy; b[5] = o.cz;
+    }
+    // rare path: rolled loops over arrays in local memory keep the register footprint (which every
+    // caller of pair_tail pays for around the call) small
+#pragma unroll 1
+    for (int i = 0; i < 3; i++) {
+        const int i2 = (i + 1) % 3;
+#pragma unroll 1
+        for (int k = 0; k < 3; k++) {
+            const int k2 = (k + 1) % 3;
+            if (seg_meet2(a[2 * i], a[2 * i + 1], a[2 * i2], a[2 * i2 + 1], b[2 * k], b[2 * k + 1], b[2 * k2],
+                          b[2 * k2 + 1]))
+                return true;
+        }
+    }
+    return inside2(b, a[0], a[1]) || inside2(a, b[0], b[1]);
+}
+
+// Verdict of pair_tail.  kPairCoplanar: is_coplanar_sep calls the two planes proportional; the
+// reference leaves such a pair undecided (no collision, narrow-phase.cu:647-652), and so does every
+// caller here unless the context is in RC_COPLANAR_DECIDE mode, in which case the caller runs
+// coplanar_overlap on the pair.  The kernels carry the mode as a template parameter (COP): the
+// descent kernel is register-bound (64 registers at 1,024 threads), any code added to its default
+// instantiation costs spills, so the default build contains none of this.
+constexpr int kPairMiss = 0, kPairHit = 1, kPairCoplanar = 2;
+
+__device__ __noinline__ int pair_tail(const Tri r, const Plane pr, float dR0, float dR1, float dR2,
+                                      const Tri o, const Plane po, float dO0, float dO1, float dO2)
+{
+    if (is_coplanar(pr, po)) return kPairCoplanar;
 
     // compute_intersect_line_sep(N1 = Nr, d1 = dr, N2 = No, d2 = do): Dx, Dz are two rounded
     // products and a subtraction (shared with la_solve's A2A3 - A1A4); Dy is fused.
@@ -248,13 +324,14 @@ __device__ __noinline__ bool pair_tail(const Tri r, const Plane pr, float dR0, f
     tri_interval(r, dR0, dR1, dR2, Dx, Dy, Dz, Ox, Oy, Oz, tr01, tr12);
     tri_interval(o, dO0, dO1, dO2, Dx, Dy, Dz, Ox, Oy, Oz, to01, to12);
     // :659-670 -- `>=`; a NaN makes both comparisons false, i.e. a collision, as in the reference
-    if (fminf(tr01, tr12) >= fmaxf(to01, to12)) return false;
-    if (fminf(to01, to12) >= fmaxf(tr01, tr12)) return false;
-    return true;
+    if (fminf(tr01, tr12) >= fmaxf(to01, to12)) return kPairMiss;
+    if (fminf(to01, to12) >= fmaxf(tr01, tr12)) return kPairMiss;
+    return kPairHit;
 }
 
 // One (robot triangle, obstacle triangle) decision given both planes (the obstacle plane is
 // configuration independent, so the context precomputes it with the same arithmetic).
+template <bool COP>
 __device__ __forceinline__ bool pair_hits(const Tri &r, const Plane &pr, const Tri &o, const Plane &po)
 {
     const float dO0 = sdist(pr, o.ax, o.ay, o.az), dO1 = sdist(pr, o.bx, o.by, o.bz),
@@ -263,7 +340,11 @@ __device__ __forceinline__ bool pair_hits(const Tri &r, const Plane &pr, const T
     const float dR0 = sdist(po, r.ax, r.ay, r.az), dR1 = sdist(po, r.bx, r.by, r.bz),
                 dR2 = sdist(po, r.cx, r.cy, r.cz);
     if (!straddles(dR0, dR1, dR2)) return false;
-    return pair_tail(r, pr, dR0, dR1, dR2, o, po, dO0, dO1, dO2);
+    const int verdict = pair_tail(r, pr, dR0, dR1, dR2, o, po, dO0, dO1, dO2);
+    if constexpr (COP) {
+        if (verdict == kPairCoplanar) return coplanar_overlap(r, o, pr);
+    }
+    return verdict == kPairHit;
 }
 
 // ---- small PTX wrappers: mbarrier + TMA bulk copy (global -> shared) -------------------

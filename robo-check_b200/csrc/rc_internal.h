@@ -70,6 +70,7 @@ struct rc_ctx {
     unsigned long long *d_counters = nullptr;  // [RC_NUM_COUNTERS] work queue + statistics
     rc_aabb *d_obs_box = nullptr;              // obstacle AABB on the device (broad-phase stage)
     int stats_on = 0;
+    int coplanar_mode = 0;                     // rc_set_coplanar_mode: 0 = skip like the reference, 1 = decide in the plane
     uint32_t *d_trace = nullptr;               // rc_stats_trace (caller's memory)
     unsigned long long launches = 0;           // kernels launched through this context
     rc_config *d_stage_confs = nullptr;        // device staging for rc_check_host

@@ -130,7 +130,7 @@ __device__ __forceinline__ void publish(const CheckArgs &a, long i, bool valid, 
 // the end re-test the last triangle (a duplicate cannot change "some pair hits").  The later
 // stages run at most once per lane and triangle between two warp-wide flushes, so the rare path
 // executes with several lanes instead of one.  `load_tri(j)` yields the world-space triangle.
-template <class LoadTri>
+template <bool COP, class LoadTri>
 __device__ __forceinline__ bool exhaustive_sweep(LoadTri load_tri, int n_rob_t,
                                                  const float4 *__restrict__ s_obs_a,
                                                  const float4 *__restrict__ s_obs_b,
@@ -155,7 +155,11 @@ __device__ __forceinline__ bool exhaustive_sweep(LoadTri load_tri, int n_rob_t,
                 tails++;
                 const float dO0 = sdist(pr, o.ax, o.ay, o.az), dO1 = sdist(pr, o.bx, o.by, o.bz),
                             dO2 = sdist(pr, o.cx, o.cy, o.cz);
-                if (pair_tail(r, pr, dR0, dR1, dR2, o, po, dO0, dO1, dO2)) hit = true;
+                const int verdict = pair_tail(r, pr, dR0, dR1, dR2, o, po, dO0, dO1, dO2);
+                if (verdict == kPairHit) hit = true;
+                if constexpr (COP) {  // RC_COPLANAR_DECIDE
+                    if (verdict == kPairCoplanar && coplanar_overlap(r, o, pr)) hit = true;
+                }
             }
         };
 
@@ -201,7 +205,7 @@ __device__ __forceinline__ bool exhaustive_sweep(LoadTri load_tri, int n_rob_t,
 // ------------------------------------------------------------------------------------------
 // Brute-force fused kernel.
 
-template <bool STATS>
+template <bool STATS, bool COP>
 __global__ void __launch_bounds__(kThreads, 2) check_brute_kernel(const CheckArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -263,8 +267,8 @@ __global__ void __launch_bounds__(kThreads, 2) check_brute_kernel(const CheckArg
                 xform(m, C.x, C.y, C.z, r.cx, r.cy, r.cz);
                 return r;
             };
-            const bool hit = exhaustive_sweep(load_tri, a.n_rob_t, s_obs_a, s_obs_b, s_obs_c, s_obs_d,
-                                              a.n_obs_t, lane, st_tail);
+            const bool hit = exhaustive_sweep<COP>(load_tri, a.n_rob_t, s_obs_a, s_obs_b, s_obs_c, s_obs_d,
+                                                   a.n_obs_t, lane, st_tail);
             publish(a, i, !hit, lane);
             if (STATS) { if (hit) st_invalid++; else st_valid++; }
         }
@@ -331,7 +335,9 @@ cudaError_t launch_check(const rc_ctx *ctx, const rc_config *d_confs, long n, ui
         const int grid = ctx->sm_count * ctas_per_sm;
         const long warps = (long)grid * kWarpsPerCta;
         a.chunk = (int)max(1L, min(8L, n / (warps * 16)));
-        auto kern = want_stats ? check_brute_kernel<true> : check_brute_kernel<false>;
+        void (*kern)(const CheckArgs);
+        if (ctx->coplanar_mode) kern = want_stats ? check_brute_kernel<true, true> : check_brute_kernel<false, true>;
+        else kern = want_stats ? check_brute_kernel<true, false> : check_brute_kernel<false, false>;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem)) != cudaSuccess)
             return e;

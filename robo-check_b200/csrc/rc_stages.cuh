@@ -334,6 +334,7 @@ cudaError_t launch_broad(long n, const rc_aabb *d_robots, const rc_aabb *d_obsta
 // valid[] is in/out: entries that are already 1 are skipped (:578).  One warp per remaining
 // configuration, lane = robot triangle (vertices gathered from the SoA rows), obstacle triangles
 // broadcast from shared memory, exhaustive like the reference.
+template <bool COP>
 __global__ void __launch_bounds__(kThreads, 2) narrow_soa_kernel(const CheckArgs a,
                                                                  const float *__restrict__ px,
                                                                  const float *__restrict__ py,
@@ -379,8 +380,8 @@ __global__ void __launch_bounds__(kThreads, 2) narrow_soa_kernel(const CheckArgs
                        __ldg(z + vb), __ldg(x + vc), __ldg(y + vc), __ldg(z + vc)};
         };
         unsigned long long tails = 0;
-        const bool hit = exhaustive_sweep(load_tri, a.n_rob_t, s_obs_a, s_obs_b, s_obs_c, s_obs_d,
-                                          a.n_obs_t, lane, tails);
+        const bool hit = exhaustive_sweep<COP>(load_tri, a.n_rob_t, s_obs_a, s_obs_b, s_obs_c, s_obs_d,
+                                               a.n_obs_t, lane, tails);
         if (lane == 0) a.valid[i] = hit ? 0 : 1;
     }
 }
@@ -402,11 +403,11 @@ cudaError_t launch_narrow_soa(const rc_ctx *ctx, const float *d_x, const float *
     const size_t smem = 16 + (size_t)t.n_obs_t * 48 + (size_t)pad4(t.n_obs_t) * 4 +
                         (size_t)(t.n_rob_t + (t.n_rob_t & 1)) * 8;
     if (smem > (size_t)ctx->max_smem_optin) return cudaErrorInvalidConfiguration;
-    e = cudaFuncSetAttribute(narrow_soa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = ctx->coplanar_mode ? narrow_soa_kernel<true> : narrow_soa_kernel<false>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int ctas_per_sm = (2 * smem + 2048 <= (size_t)ctx->max_smem_optin) ? 2 : 1;
-    narrow_soa_kernel<<<ctx->sm_count * ctas_per_sm, kThreads, smem, stream>>>(a, d_x, d_y, d_z,
-                                                                             t.n_rob_v);
+    kern<<<ctx->sm_count * ctas_per_sm, kThreads, smem, stream>>>(a, d_x, d_y, d_z, t.n_rob_v);
     return cudaGetLastError();
 }
 

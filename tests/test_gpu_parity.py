@@ -571,3 +571,79 @@ def test_tiny_meshes_all_paths(rc, po, shape):
         assert np.array_equal(d_valid.cpu().numpy(), po.check_spheres(c.robot_spheres(), po.OracleMesh(*obs.arrays()), confs))
     finally:
         c.close()
+
+
+def _only_disjoint_pairs_hit(po, rob_a, obs_a, conf, variant, clearance=2e-3):
+    """True iff every pair the reference arithmetic reports for `conf` has bounding boxes more than
+    `clearance` apart (the triangles are disjoint; the report is a rounding artefact)."""
+    wx, wy, wz = po.transform(conf[None, :], *rob_a[:3])
+    w = np.stack([wx[0], wy[0], wz[0]], 1)
+    ov = np.stack(obs_a[:3], 1)
+    hits = 0
+    for a, b, c3 in zip(*rob_a[3:]):
+        r = w[[a, b, c3]]
+        for e, f, g in zip(*obs_a[3:]):
+            o = ov[[e, f, g]]
+            if po.pair_hits(r.reshape(-1), o.reshape(-1), variant)[0]:
+                hits += 1
+                if np.maximum(r.min(0) - o.max(0), o.min(0) - r.max(0)).max() <= clearance:
+                    return False
+    return hits > 0
+
+
+def test_coplanar_mode_all_paths(rc, po):
+    """RC_COPLANAR_SKIP reproduces the reference (undecided pairs never collide,
+    narrow-phase.cu:647-652,:680), RC_COPLANAR_DECIDE decides them in the common plane; both modes
+    bit-equal to the oracle in the exhaustive and stage-wise paths, on a scene where the option
+    changes more than 100 flags (tests/coplanar_scene.py).
+
+    The scene is made of large triangles lying in one plane, which is also where the reference's
+    arithmetic breaks down: for nearly parallel planes its intersection line is rounding noise and it
+    reports some pairs whose triangles are far apart inside the plane (configuration 16: boxes 0.39
+    apart).  The tree-culled kernel never looks at such a pair (culling safety), so for
+    RC_MODE_CULLED the assertion is: any flag that differs is valid-here / invalid-there, and every
+    pair the oracle reports for that configuration has boxes more than the culling clearance apart."""
+    torch = _torch()
+    from tests import coplanar_scene
+    rob_a, obs_a, confs = coplanar_scene.build(po)
+    R, O = po.OracleMesh(*rob_a), po.OracleMesh(*obs_a)
+    variant = {rc.RC_COPLANAR_SKIP: po.VARIANT_GPU, rc.RC_COPLANAR_DECIDE: po.VARIANT_GPU | po.FLAG_COPLANAR}
+    want = {m: po.check(R, O, confs, v) for m, v in variant.items()}
+    assert int((want[0] != want[1]).sum()) > 100
+    c = rc.Context(rc.Mesh.from_arrays(*rob_a), rc.Mesh.from_arrays(*obs_a), device=0)
+    try:
+        assert c.coplanar_mode() == rc.RC_COPLANAR_SKIP  # the default is the reference's behaviour
+        with pytest.raises(rc.RoboCheckError):
+            c.set_coplanar_mode(7)
+        n, nv = len(confs), len(rob_a[0])
+        d_confs = torch.from_numpy(confs).cuda()
+        s = torch.cuda.current_stream()
+        for mode in (rc.RC_COPLANAR_DECIDE, rc.RC_COPLANAR_SKIP):
+            c.set_coplanar_mode(mode)
+            assert c.coplanar_mode() == mode
+            got, bits = run_check(c, confs, rc.RC_MODE_BRUTE, bitmask=True)
+            assert np.array_equal(got, want[mode]), (mode, int((got != want[mode]).sum()))
+            assert np.array_equal(bits, want[mode])
+            dx, dy, dz = (torch.zeros(n * nv, dtype=torch.float32, device="cuda") for _ in range(3))
+            d_valid = torch.zeros(n, dtype=torch.uint8, device="cuda")
+            c.broad_fused(d_confs, n, dx, dy, dz, None, d_valid, s)
+            c.narrow_phase(dx, dy, dz, n, d_valid, s)
+            torch.cuda.synchronize()
+            assert np.array_equal(d_valid.cpu().numpy(), want[mode])
+            # tree-culled kernel, with and without statistics, and through the host entry point
+            culled, bits = run_check(c, confs, rc.RC_MODE_CULLED, bitmask=True)
+            assert np.array_equal(bits, culled)
+            differ = np.nonzero(culled != want[mode])[0]
+            assert len(differ) <= 3 and np.all(culled[differ] == 1)
+            for i in differ:
+                assert _only_disjoint_pairs_hit(po, rob_a, obs_a, confs[i], variant[mode])
+            # the coplanar decisions themselves all survive the culling
+            changed = want[0] != want[1]
+            assert np.array_equal(culled[changed], want[mode][changed])
+            c.stats_enable(True)
+            again = run_check(c, confs, rc.RC_MODE_CULLED)
+            c.stats_enable(False)
+            assert np.array_equal(again, culled) and c.stats(reset=True)["watchdog"] == 0
+            assert np.array_equal(np.asarray(c.check_host(confs)), culled)
+    finally:
+        c.close()
