@@ -396,6 +396,31 @@ def main():
         del dx, dy, dz
         from oracle import pyoracle as po
         out["cpu_baseline"], _, _ = cpu_reference_throughput(rc, po, confs, seconds=12.0)
+        # second same-box comparator: tree-culled CPU checker with the reference's per-pair
+        # arithmetic, the stand-in for FCL's BVH path (FCL is not installable here); it finishes the
+        # whole workload, so it also checks every flag of the timed steps
+        rob_m, obs_m = rc.alpha_meshes()
+        orob, oobs = po.OracleMesh(*rob_m.arrays()), po.OracleMesh(*obs_m.arrays())
+        threads = os.cpu_count() or 1
+        po.check_bvh(orob, oobs, confs[:2048], po.VARIANT_GPU, threads)  # warm-up
+        t0 = time.perf_counter()
+        cpu_flags = po.check_bvh(orob, oobs, confs, po.VARIANT_GPU, threads)
+        dt_all = time.perf_counter() - t0
+        n1 = min(n, 20000)
+        t0 = time.perf_counter()
+        po.check_bvh(orob, oobs, confs[:n1], po.VARIANT_GPU, 1)
+        dt_one = time.perf_counter() - t0
+        out["cpu_baseline_tree"] = {
+            "value": n / dt_all, "unit": "configs/s", "cores": threads, "kind": "port",
+            "sample": f"all {n} workload configurations, {dt_all:.2f} s; oracle/oracle_bvh.c: dual-tree "
+                      "descent + the reference's per-pair arithmetic (stand-in for FCL's BVH path)",
+            "single_core_value": n1 / dt_one,
+            "single_core_sample": f"first {n1} configurations, {dt_one:.2f} s"}
+        ctx.check(d_confs, n, d_valid, d_mask, rc.RC_MODE_CULLED, stream); torch.cuda.synchronize()
+        gpu_flags = d_valid.cpu().numpy()
+        out["parity"] = {"checker": "oracle/oracle_bvh.c (CPU), every configuration of the workload",
+                         "configs": n, "flag_mismatches": int((gpu_flags != cpu_flags).sum()),
+                         "e2e_flag_mismatches": int((np_valid != cpu_flags).sum())}
 
     emit(out)
 

@@ -52,6 +52,11 @@ int rco_pair_hits(const float r[9], const float o[9], int variant, int *coplanar
 
 int rco_check(const rco_mesh *rob, const rco_mesh *obs, const rco_config *confs, long n,
               int variant, int nthreads, int early_exit, uint8_t *valid, rco_stats *stats);
+/* Same flags as rco_check (early exit), pairs enumerated by a dual-tree descent (oracle_bvh.c):
+ * whole BASELINE-size sets in seconds.  In its statistics pairs_stage1 counts box pairs tested
+ * and pairs_full triangle pairs decided. */
+int rco_check_bvh(const rco_mesh *rob, const rco_mesh *obs, const rco_config *confs, long n,
+                  int variant, int nthreads, uint8_t *valid, rco_stats *stats);
 int rco_narrow(const rco_mesh *rob, const rco_mesh *obs, const float *px, const float *py,
                const float *pz, long n, int variant, uint8_t *valid);
 

@@ -73,6 +73,21 @@ def check(rob, obs, confs, variant=VARIANT_GPU, nthreads=None, early_exit=True, 
     return valid
 
 
+def check_bvh(rob, obs, confs, variant=VARIANT_GPU, nthreads=None, want_stats=False):
+    """Same flags as check(), pairs enumerated by a dual-tree descent (oracle_bvh.c): fast enough for
+    the full BASELINE sizes."""
+    confs = _f(confs).reshape(-1, 6)
+    valid = np.zeros(len(confs), np.uint8)
+    st = rco_stats()
+    nthreads = nthreads or os.cpu_count() or 1
+    rc = lib().rco_check_bvh(C.byref(rob.c), C.byref(obs.c), _p(confs), C.c_long(len(confs)), variant,
+                             nthreads, _p(valid), C.byref(st))
+    assert rc == 0
+    if want_stats:
+        return valid, {k: getattr(st, k) for k, _ in rco_stats._fields_}
+    return valid
+
+
 def transform(confs, x, y, z):
     confs = _f(confs).reshape(-1, 6)
     x, y, z = _f(x), _f(y), _f(z)

@@ -647,3 +647,20 @@ def test_coplanar_mode_all_paths(rc, po):
             assert np.array_equal(np.asarray(c.check_host(confs)), culled)
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("workload", ["C2_hard_100k", "C4_uniform_1M", "hard_1M"])
+def test_full_size_workloads_every_flag(rc, ctx, po, omeshes, workload):
+    """BASELINE.json's sizes, every flag checked: the tree-culled CPU checker (oracle_bvh.c, pinned
+    against the exhaustive oracle in tests/test_oracle.py) decides all of the bench workload
+    (configs[1], seed 508), all of configs[3] (1M of the reference's sampler) and 1M hard ones."""
+    n, hard, seed = {"C2_hard_100k": (100_000, True, 508), "C4_uniform_1M": (1_000_000, False, 510),
+                     "hard_1M": (1_000_003, True, 511)}[workload]
+    confs = rc.createAlphaBotConfigurations(n, hard, seed)
+    want, st = po.check_bvh(omeshes[0], omeshes[1], confs, po.VARIANT_GPU, want_stats=True)
+    got, bits = run_check(ctx, confs, rc.RC_MODE_CULLED, bitmask=True)
+    assert np.array_equal(got, want), int((got != want).sum())
+    assert np.array_equal(bits, want)
+    assert st["narrow_invalid"] > 0 and st["broad_cleared"] > 0
+    host = ctx.check_host(confs)
+    assert np.array_equal(host, want)
