@@ -664,3 +664,24 @@ def test_full_size_workloads_every_flag(rc, ctx, po, omeshes, workload):
     assert st["narrow_invalid"] > 0 and st["broad_cleared"] > 0
     host = ctx.check_host(confs)
     assert np.array_equal(host, want)
+
+
+@pytest.mark.parametrize("levels,n", [(2, 200_000), (5, 100_000)])
+def test_subdivided_obstacle_full_size_every_flag(rc, po, meshes, levels, n):
+    """BASELINE configs[4] at its real obstacle sizes (16,128 and 1,032,192 triangles, tables in
+    global memory), "easy" configurations with the 10 % "hard" admixture of SURVEY 8(d): every flag
+    against the tree-culled CPU checker."""
+    rob, obs = meshes[0], meshes[1].subdivide(levels)
+    assert obs.n_t == 1008 * 4 ** levels
+    confs = np.concatenate([rc.createAlphaBotConfigurations(n * 9 // 10, False, 511),
+                            rc.createAlphaBotConfigurations(n // 10, True, 512)]).astype(np.float32)
+    want, st = po.check_bvh(po.OracleMesh(*rob.arrays()), po.OracleMesh(*obs.arrays()), confs,
+                            po.VARIANT_GPU, want_stats=True)
+    assert st["narrow_invalid"] > 1000 and st["narrow_valid"] > 1000
+    c = rc.Context(rob, obs, device=0)
+    try:
+        got, bits = run_check(c, confs, rc.RC_MODE_CULLED, bitmask=True)
+        assert np.array_equal(got, want), int((got != want).sum())
+        assert np.array_equal(bits, want)
+    finally:
+        c.close()
