@@ -260,8 +260,6 @@ int rc_create(rc_ctx **out, const float *rob_x, const float *rob_y, const float 
         ctx->knob_share = knob("RC_SHARE", 1);
         ctx->knob_pdl = knob("RC_PDL", 1);
         ctx->knob_bound = knob("RC_BOUND", 1);
-        ctx->knob_poll_ns = knob("RC_POLL_NS", 2048);
-        ctx->knob_check_mask = knob("RC_CHECK_MASK", 3);
         ctx->knob_mail_slots = knob("RC_MAIL_SLOTS", 4);
         ctx->knob_donate_min = knob("RC_DONATE_MIN", 40);
     }

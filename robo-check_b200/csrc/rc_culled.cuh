@@ -41,7 +41,7 @@ constexpr int kClassifyBoxes = 32;  // vertex groups of the robot bounded in cla
 constexpr int kMailSlots = 16;   // per CTA (capacity; a.mail_slots are used): pieces of a deep descent handed to warps without work
 constexpr int kDonateMin = 64;   // node pairs on a warp's stack before it hands 32 of them out
 constexpr uint32_t kPendHit = 0x80000000u;
-constexpr uint32_t kWatchdogSpins = 1u << 21;  // x 2 us: a few seconds
+constexpr uint32_t kWatchdogSpins = 1u << 22;  // x 256 ns: about a second
 constexpr uint32_t kAbortTicks = 8192;          // x 2^20 SM cycles: about four seconds after the CTA started
 
 struct __align__(16) Mail {
@@ -69,7 +69,6 @@ struct CulledArgs {
     int tail_thresh, leaf_thresh;
     int stack_cap;                                         // <= compiled capacity (smaller only in tests)
     int share;                                             // 0: no hand-over between the warps of a CTA
-    int poll_max_ns, check_mask;                           // serve-loop back-off cap; idle flag looked at when (round & mask) == 0
     int mail_slots, donate_min;                            // hand-over tuning (<= kMailSlots; node pairs kept before giving)
     // work list written by classify_kernel: configurations the cheap tests could not clear
     const uint32_t *work_idx;                              // [kWorkBins][work_cap] configuration indices
@@ -350,8 +349,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
     const uint32_t chunk = max(1u, min(16u, n_work / (gridDim.x * WARPS * 32u)));
     uint32_t w_next = 0, w_end = 0;
     bool dry = false;
-    bool idle_known = false;  // some warp of this CTA has run out of configurations (sticky)
-    uint32_t rounds = 0;
     for (;;) {
         if (!dry && w_next >= w_end) {
             const uint32_t take = ((unsigned long long)w_end + a.tail_begin < n_work) ? chunk : 1u;
@@ -360,7 +357,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
             base = __shfl_sync(kFull, base, 0);
             if (base >= n_work) {
                 dry = true;
-                idle_known = a.share != 0;
                 if (lane == 0) atomicAdd(s_idle, 1u);
             } else {
                 w_next = (uint32_t)base;
@@ -407,7 +403,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
                 }
                 k = __shfl_sync(kFull, k, 0);
                 if (k != -1) break;
-                __nanosleep(min((uint32_t)a.poll_max_ns, 128u << min(spins, 4u)));  // back off: idle warps must not eat issue slots
+                __nanosleep(256);
             }
             if (k == -2) break;
             __threadfence_block();
@@ -491,18 +487,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
                              : lq >= 16 ? 1 : sp >= a.donate_min ? 0 : -1;
             // What other warps publish is agreed on by the whole warp (vote / broadcast: two lanes
             // reading the same word at different moments could otherwise take different branches of
-            // this loop).  s_idle only ever grows: until some warp of the CTA is known to be idle it is
-            // looked at in every fourth round that has something to give, afterwards never again; the
-            // hit bit of the other pieces and the time limit are read only while pieces are out (or
-            // every 64th round).
+            // this loop), and only in rounds where it matters: something to give, or pieces of this
+            // configuration are out.  s_idle only ever grows, so the common case is one shared-memory
+            // read and one vote.
             uint32_t seen = 0;
-            rounds++;
-            if (!idle_known && kind >= 0 && (rounds & (uint32_t)a.check_mask) == 0u)
-                idle_known = __any_sync(kFull, ld_volatile(s_idle) != 0u);
-            if (idle_known && (kind >= 0 || sharing)) {
-                seen = 1u;
-                if (sharing || (rounds & 63u) == 0u) {
+            if (kind >= 0 || sharing) {
+                if (__any_sync(kFull, ld_volatile(s_idle) != 0u)) {
                     if (lane == 0) {
+                        seen = 1u;
                         if (sharing && (ld_volatile(&s_pend[pend_slot]) & kPendHit) != 0u) seen = 3u;
                         if ((uint32_t)(clock64() >> 20) - *s_t0 > kAbortTicks) seen = 4u;
                     }
@@ -829,7 +821,6 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
     if (ctx->knob_tail > 0) a.tail_thresh = min(32, ctx->knob_tail);
     if (ctx->knob_leaf > 0) a.leaf_thresh = min(8, ctx->knob_leaf);
     a.share = ctx->knob_share;
-    a.poll_max_ns = max(64, ctx->knob_poll_ns); a.check_mask = max(0, ctx->knob_check_mask);
     a.mail_slots = max(1, min(kMailSlots, ctx->knob_mail_slots));
     a.donate_min = max(40, ctx->knob_donate_min);
     a.trace = want_stats ? ctx->d_trace : nullptr;
