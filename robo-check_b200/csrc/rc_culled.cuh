@@ -103,6 +103,36 @@ __device__ __forceinline__ bool boxes_overlap(const Mat34 &m, const float4 r0, c
 
 // Exhaustive sweep for one configuration, used only when the pair stack overflows (never
 // observed); kept small on purpose: lane = robot triangle, obstacle triangles broadcast.
+// Exact broad-phase flag of the reference (broad-phase-fused.cu:186-200), one warp.  If ANY
+// exactly-transformed robot vertex lies inside the obstacle AABB, the two AABBs overlap on every
+// axis (robot.min <= v <= obstacle.max, obstacle.min <= v <= robot.max), so the broad phase cannot
+// clear the configuration: 32 probe vertices are tried first.  Otherwise the lanes transform all
+// vertices and reduce the exact AABB.  Not inlined, and the matrix is read again from the work list
+// (L2) instead of being passed: the call sits between two configurations and must not weigh on the
+// register allocation of the descent loop (passing the matrix made ptxas keep it in local memory).
+__device__ __noinline__ bool exact_broad_clears(const float4 *work_mat, long i, const float4 *s_rob_v,
+                                                int n_rob_v_pad, int probe_stride, const rc_aabb obs_box,
+                                                int lane)
+{
+    Mat34 m;
+    {
+        const float4 q0 = __ldcg(work_mat + 3 * i), q1 = __ldcg(work_mat + 3 * i + 1), q2 = __ldcg(work_mat + 3 * i + 2);
+        m.r00 = q0.x; m.r01 = q0.y; m.r02 = q0.z; m.tx = q0.w;
+        m.r10 = q1.x; m.r11 = q1.y; m.r12 = q1.z; m.ty = q1.w;
+        m.r20 = q2.x; m.r21 = q2.y; m.r22 = q2.z; m.tz = q2.w;
+    }
+    const float4 p = s_rob_v[lane * probe_stride];
+    float x, y, z;
+    xform(m, p.x, p.y, p.z, x, y, z);
+    const bool inside = obs_box.x_min <= x && x <= obs_box.x_max && obs_box.y_min <= y &&
+                        y <= obs_box.y_max && obs_box.z_min <= z && z <= obs_box.z_max;
+    if (__any_sync(kFull, inside)) return false;
+    float box[6];
+    warp_aabb(m, s_rob_v, n_rob_v_pad, lane, box);
+    return broad_valid(box[0], box[1], box[2], box[3], box[4], box[5], obs_box.x_min, obs_box.y_min,
+                       obs_box.z_min, obs_box.x_max, obs_box.y_max, obs_box.z_max);
+}
+
 template <bool COP>
 __device__ __noinline__ bool narrow_exhaustive(const Mat34 m, const float4 *s_rob_v,
                                                const uint2 *s_rob_t, int n_rob_t,
@@ -438,29 +468,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
                 m.r20 = q2.x; m.r21 = q2.y; m.r22 = q2.z; m.tz = q2.w;
             }
 
-            // A: exact broad-phase flag.  If ANY exactly-transformed robot vertex lies inside the
-            // obstacle AABB, the two AABBs overlap on every axis (robot.min <= v <= obstacle.max,
-            // obstacle.min <= v <= robot.max), so the broad phase cannot clear the configuration:
-            // 32 probe vertices are tried first.  Otherwise the lanes transform all vertices and
-            // reduce the exact AABB.
-            bool certain_overlap;
-            {
-                const float4 p = s_rob_v[lane * a.probe_stride];
-                float x, y, z;
-                xform(m, p.x, p.y, p.z, x, y, z);
-                const bool inside = c.obs_box.x_min <= x && x <= c.obs_box.x_max &&
-                                    c.obs_box.y_min <= y && y <= c.obs_box.y_max &&
-                                    c.obs_box.z_min <= z && z <= c.obs_box.z_max;
-                certain_overlap = __any_sync(kFull, inside);
-            }
-            if (!certain_overlap) {
-                float box[6];
-                warp_aabb(m, s_rob_v, c.n_rob_v_pad, lane, box);
-                if (broad_valid(box[0], box[1], box[2], box[3], box[4], box[5], c.obs_box.x_min,
-                                c.obs_box.y_min, c.obs_box.z_min, c.obs_box.x_max, c.obs_box.y_max,
-                                c.obs_box.z_max)) {
+            // A: exact broad-phase flag (exact_broad_clears).  The flag of a configuration is "the
+            // broad phase clears it, or the narrow phase finds no hit", so the exact robot AABB only
+            // matters when the descent DOES report a hit: the production build runs the descent
+            // first and settles the broad phase afterwards, for colliding configurations only (a
+            // configuration the broad phase clears usually ends after the 16 seed pairs).  The
+            // statistics build keeps the reference's order, because it reports the two kinds of
+            // valid configurations separately.
+            if constexpr (STATS) {
+                if (exact_broad_clears(a.work_mat, i, s_rob_v, c.n_rob_v_pad, a.probe_stride, c.obs_box, lane)) {
                     publish(c, i, true, lane);
-                    if (STATS) st_broad++;
+                    st_broad++;
                     trace();
                     continue;
                 }
@@ -720,6 +738,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
             }
             v = __shfl_sync(kFull, v, 0);
             hit = hit || (v & kPendHit) != 0u;
+        }
+        if constexpr (!STATS) {
+            // the reference's broad phase comes first: what it clears is valid whatever the narrow
+            // phase would say
+            if (hit && exact_broad_clears(a.work_mat, i, s_rob_v, c.n_rob_v_pad, a.probe_stride, c.obs_box, lane)) hit = false;
         }
         publish(c, i, !hit, lane);
         if (STATS) { if (hit) st_invalid++; else st_valid++; }
