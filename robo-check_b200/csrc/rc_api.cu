@@ -258,6 +258,7 @@ int rc_create(rc_ctx **out, const float *rob_x, const float *rob_y, const float 
         ctx->knob_stack_cap = knob("RC_STACK_CAP", 0);
         ctx->knob_global_obstacle = getenv("RC_FORCE_GLOBAL_OBSTACLE") != nullptr;
         ctx->knob_share = knob("RC_SHARE", 1);
+        ctx->knob_host_direct = knob("RC_HOST_DIRECT", 1);
         ctx->knob_pdl = knob("RC_PDL", 1);
         ctx->knob_bound = knob("RC_BOUND", 1);
         ctx->knob_mail_slots = knob("RC_MAIL_SLOTS", 4);
@@ -480,19 +481,32 @@ int rc_check_host(rc_ctx *ctx, const rc_config *h_confs, long n, uint8_t *h_vali
         src = ctx->h_pinned_confs;
     }
     uint8_t *dst = out_pinned ? h_valid : ctx->h_pinned_valid;
+    // Flags go straight into the page-locked host buffer: the kernels store one byte per
+    // configuration through the mapped address (posted PCIe writes spread over the run), which
+    // saves the device-to-host copy and its completion latency at the end (RC_HOST_DIRECT=0: copy).
+    uint8_t *d_out = ctx->d_stage_valid;
+    bool direct = false;
+    if (ctx->knob_host_direct) {
+        void *mapped = nullptr;
+        if (cudaHostGetDevicePointer(&mapped, dst, 0) == cudaSuccess && mapped) {
+            d_out = static_cast<uint8_t *>(mapped);
+            direct = true;
+        }
+        cudaGetLastError();
+    }
     if ((e = cudaMemcpyAsync(ctx->d_stage_confs, src, (size_t)n * sizeof(rc_config),
                              cudaMemcpyHostToDevice, s)))
         return check_cuda(ctx, e, "H2D configurations");
     cudaEventRecord(ctx->ev0, s);
     if (mode == RC_MODE_CULLED && (rcode = ensure_work_list(ctx, n)) != RC_OK) return rcode;
-    e = launch_check(ctx, ctx->d_stage_confs, n, ctx->d_stage_valid, nullptr, mode, ctx->stats_on, s,
+    e = launch_check(ctx, ctx->d_stage_confs, n, d_out, nullptr, mode, ctx->stats_on, s,
                      ctx->d_queues);
     if (e == cudaErrorInvalidConfiguration)
         return set_error(ctx, RC_ERR_UNSUPPORTED, "mesh tables do not fit in shared memory");
     if (e) return check_cuda(ctx, e, "rc_check_host launch");
     ctx->launches += mode == RC_MODE_CULLED ? 2 : 1;
     cudaEventRecord(ctx->ev1, s);
-    if ((e = cudaMemcpyAsync(dst, ctx->d_stage_valid, (size_t)n, cudaMemcpyDeviceToHost, s)) ||
+    if ((!direct && (e = cudaMemcpyAsync(dst, ctx->d_stage_valid, (size_t)n, cudaMemcpyDeviceToHost, s))) ||
         (e = cudaStreamSynchronize(s)))
         return check_cuda(ctx, e, "D2H flags");
     cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev0, ctx->ev1);
