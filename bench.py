@@ -38,6 +38,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--confs", type=int, default=N_CONFS, help=argparse.SUPPRESS)
+    ap.add_argument("--gather", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N>1: bitmask all-gather fused behind the check over peer-mapped memory "
+                         "(rc_check_gather), or the NCCL all-gather; auto = peer when available")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip cpu_baseline / brute / stage rooflines (used by the ncu passes)")
     return ap.parse_args()
@@ -212,10 +215,34 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
 
+    # N>1: the all-gather of the bitmask fused behind the check over peer-mapped memory (NVLink),
+    # falling back to the NCCL all-gather when symmetric memory is not available on the box
+    pg, gather_note = None, "none"
+    if world > 1:
+        gather_note = "all_gather of the validity bitmask (NCCL)"
+        if args.gather != "nccl":
+            try:
+                from robocheck_b200 import sharding as sh
+                pg = sh.PeerGather(rc, dist, dev, words)
+            except Exception as exc:
+                pg = None
+                print(f"[bench] rank {rank}: peer gather unavailable ({type(exc).__name__}: {exc})", file=sys.stderr)
+            okf = torch.tensor([1 if pg is not None else 0], device=dev)
+            dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+            if int(okf.item()) == 0:
+                assert args.gather != "peer", "--gather peer: symmetric memory not available"
+                pg = None
+            else:
+                gather_note = ("bitmask words stored into the peers' buffers over NVLink by a kernel behind the "
+                               "check (rc_check_gather, torch symmetric memory), no communicator call")
+
     def step():
+        if pg is not None:
+            return pg.check(ctx, d_confs, n, d_valid, stream)
         ctx.check(d_confs, n, d_valid, d_mask, rc.RC_MODE_CULLED, stream)
         if world > 1:
             dist.all_gather_into_tensor(d_gather, d_mask)
+        return d_gather
 
     def barrier():
         if world > 1:
@@ -224,6 +251,24 @@ def main():
 
     for _ in range(max(args.warmup, 3)):  # never fewer than three warm-up steps
         step()
+    # untimed, before the timed steps: the gathered bitmask of one step against an NCCL all-gather of the
+    # same words; a peer gather that disagrees (or whose wait gave up) is not used for the timed steps
+    gather_check = None
+    if world > 1:
+        got = step().clone()
+        ctx.check(d_confs, n, d_valid, d_mask, rc.RC_MODE_CULLED, stream)
+        dist.all_gather_into_tensor(d_gather, d_mask)
+        torch.cuda.synchronize()
+        good = torch.equal(got, d_gather) and ctx.stats()["watchdog"] == 0
+        same = torch.tensor([int(good)], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        if int(same.item()) == 0 and pg is not None:
+            assert args.gather != "peer", "peer gather disagrees with the NCCL all-gather"
+            pg, gather_note = None, "all_gather of the validity bitmask (NCCL; the peer gather failed its check)"
+            gather_check = "NCCL"
+        else:
+            assert int(same.item()) == 1
+            gather_check = "gathered bitmask == NCCL all-gather on every rank"
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -244,8 +289,8 @@ def main():
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
     value = world * n * args.steps / (total_ms * 1e-3)
-    launches = 2 * args.steps  # two kernels of ours per step: classify + descent (memsets and NCCL are not ours)
-
+    # kernels of ours per step: classify + descent (+ the gather push at N>1); memsets and NCCL are not ours
+    launches = (3 if pg is not None else 2) * args.steps
     # ---- end to end: host buffers in, host flags out, through the public host call ---------------
     h_confs = torch.from_numpy(confs).pin_memory()
     h_valid = torch.zeros(n, dtype=torch.uint8).pin_memory()
@@ -343,7 +388,7 @@ def main():
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "configs_per_gpu": n, "mode": "culled fused kernel",
                    "l2": "flushed before every timed step (256 MiB fill, outside the event pair)",
-                   "collective": "all_gather of the validity bitmask (NCCL)" if world > 1 else "none"},
+                   "collective": gather_note, "collective_check": gather_check},
         "e2e": {"value": e2e_value, "unit": "configs/s", "h2d_bytes_per_step": n * 24,
                 "d2h_bytes_per_step": n, "api": "rc_check_host (pinned host buffers)",
                 "timing": "median of 3 runs of K synchronous steps each (wall clock, max over ranks)",

@@ -170,6 +170,26 @@ int rc_conf_generate_device(rc_ctx *ctx, rc_config *d_out, long n, float x_min, 
 int rc_compact(rc_ctx *ctx, const uint8_t *d_valid, const uint32_t *d_bitmask, long n, int want,
                uint32_t *d_indices, unsigned long long *d_count, void *stream);
 
+/* ---- one process per GPU: check + all-gather of the bitmask in one call -----------
+ * The reference is single-GPU.  north_star shards the configurations over the GPUs of a box and
+ * gathers only the validity bitmask (ncclAllGather); here the gather is fused behind the check and
+ * runs over peer-mapped memory (NVLink / NVSwitch) without a communicator call: every rank owns one
+ * buffer of rc_gather_buffer_words(world, words_per_rank) 32-bit words, ZEROED once, mapped into the
+ * address space of every rank (torch.distributed._symmetric_memory, cudaIpcOpenMemHandle, ...);
+ * peer_buffers[r] is rank r's buffer as seen from the calling process (peer_buffers[rank] = the own
+ * one).  rc_check_gather checks the rank's n configurations (n <= 32 * words_per_rank, mode
+ * RC_MODE_CULLED) with the bitmask going straight into the rank's slot, stores the slot into every
+ * peer's buffer, signals, and waits for the peers' slots.  All ranks must call it the same number of
+ * times with the same world / words_per_rank (a collective).  After the call, in stream order,
+ * *d_result points at world * words_per_rank words inside the own buffer: the bitmask of all ranks
+ * (rank r's configurations start at bit 32 * words_per_rank * r).  It stays valid until the second
+ * next call.  A peer that never arrives is counted in rc_stats.watchdog after 4 s instead of
+ * hanging the device.  d_valid (optional) receives the rank's own flag bytes. */
+long rc_gather_buffer_words(int world, long words_per_rank);
+int rc_check_gather(rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_valid,
+                    void *const *peer_buffers, int rank, int world, long words_per_rank,
+                    uint32_t **d_result, void *stream);
+
 /* ---- sphere-approximated robot (BASELINE config 3) -----------------------------
  * The reference has no such path (test/CPU-Sphere-Test.cpp:8-18 only collides two unit spheres
  * with FCL), so the semantics are this library's: the robot is a set of spheres (x, y, z, r) in

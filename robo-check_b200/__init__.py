@@ -60,6 +60,8 @@ ABI = [
     ("rc_shard_size", _i, [_l, _i]),
     ("rc_device_count", _i, [C.POINTER(_i)]),
     ("rc_check_multi", _i, [_vp, _i, _vp, _l, _vp, _vp, _vp]),
+    ("rc_gather_buffer_words", _l, [_i, _l]),
+    ("rc_check_gather", _i, [_vp, _vp, _l, _vp, _vp, _i, _i, _l, _vp, _vp]),
     ("rc_transform_aos", _i, [_vp, _vp, _l, _vp, _i, _vp, _vp]),
     ("rc_generate_aabb", _i, [_vp, _vp, _u, _u, _vp, _vp]),
     ("rc_generate_aabb_host", _i, [_vp, _vp, _u, _u, _vp]),
@@ -351,6 +353,17 @@ class Context:
     def check(self, d_confs, n, d_valid=None, d_bitmask=None, mode=RC_MODE_CULLED, stream=None):
         _check(_lib.rc_check(self._h, _ptr(d_confs), int(n), _ptr(d_valid), _ptr(d_bitmask), mode,
                              _stream_ptr(stream)), self._h)
+
+    def check_gather(self, d_confs, n, d_valid, peer_ptrs, rank, words_per_rank, stream=None):
+        """Check this rank's n configurations and all-gather the bitmask through the peer-mapped buffers
+        `peer_ptrs` (device addresses of every rank's buffer, see rc_check_gather in robocheck.h).
+        Returns the word offset of the gathered bitmask inside the own buffer."""
+        world = len(peer_ptrs)
+        arr = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in peer_ptrs])
+        res = C.c_void_p()
+        _check(_lib.rc_check_gather(self._h, _ptr(d_confs), int(n), _ptr(d_valid), arr, int(rank), world,
+                                    int(words_per_rank), C.byref(res), _stream_ptr(stream)), self._h)
+        return (int(res.value) - int(peer_ptrs[rank])) // 4
 
     def check_host(self, confs, mode=RC_MODE_CULLED):
         confs = np.ascontiguousarray(confs, dtype=np.float32).reshape(-1, 6)

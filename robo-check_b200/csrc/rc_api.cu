@@ -459,6 +459,55 @@ int rc_check(rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_valid, ui
     return check_cuda(ctx, e, "rc_check launch");
 }
 
+long rc_gather_buffer_words(int world, long words_per_rank)
+{
+    if (world <= 0 || world > rc::kMaxGatherRanks || words_per_rank <= 0) return RC_ERR_INVALID;
+    return 2L * world * words_per_rank + world;
+}
+
+int rc_check_gather(rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_valid,
+                    void *const *peer_buffers, int rank, int world, long words_per_rank,
+                    uint32_t **d_result, void *stream)
+{
+    if (!ctx || n < 0 || (n > 0 && !d_confs) || !peer_buffers || world <= 0 ||
+        world > rc::kMaxGatherRanks || rank < 0 || rank >= world || words_per_rank <= 0 ||
+        (n + 31) / 32 > words_per_rank || words_per_rank > 0x7fffffffL / 4)
+        return RC_ERR_INVALID;
+    for (int r = 0; r < world; r++)
+        if (!peer_buffers[r]) return RC_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = stream_of(ctx, stream);
+    const uint32_t call = ++ctx->gather_calls;
+    const long area = (long)(call & 1u) * world * words_per_rank;  // the two gather areas alternate
+    uint32_t *mine = static_cast<uint32_t *>(peer_buffers[rank]);
+    uint32_t *slot = mine + area + (long)rank * words_per_rank;
+    if (d_result) *d_result = mine + area;
+    const long used = (n + 31) / 32;
+    cudaError_t e;
+    // words of the slot past the last configuration (short or empty last shards) are defined as 0
+    if (used < words_per_rank &&
+        (e = cudaMemsetAsync(slot + used, 0, (size_t)(words_per_rank - used) * 4, s)) != cudaSuccess)
+        return check_cuda(ctx, e, "rc_check_gather memset");
+    if (n > 0) {
+        const int rcode = rc_check(ctx, d_confs, n, d_valid, slot, RC_MODE_CULLED, stream);
+        if (rcode != RC_OK) return rcode;
+    }
+    rc::GatherArgs a{};
+    a.src = slot;
+    for (int r = 0; r < world; r++) {
+        uint32_t *base = static_cast<uint32_t *>(peer_buffers[r]);
+        a.peer_slot[r] = base + area + (long)rank * words_per_rank;
+        a.peer_signal[r] = base + 2L * world * words_per_rank + rank;
+    }
+    a.my_signal = mine + 2L * world * words_per_rank;
+    a.rank = rank; a.world = world; a.words = (int)words_per_rank; a.call = call;
+    a.counters = ctx->d_counters;
+    a.timeout_ns = 4000000000ULL;
+    e = rc::launch_gather_push(ctx, a, s);
+    if (world > 1) ctx->launches += 1;
+    return check_cuda(ctx, e, "rc_check_gather push");
+}
+
 int rc_check_host(rc_ctx *ctx, const rc_config *h_confs, long n, uint8_t *h_valid, int mode)
 {
     if (!ctx || n < 0 || (n > 0 && (!h_confs || !h_valid))) return RC_ERR_INVALID;

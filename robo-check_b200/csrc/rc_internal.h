@@ -70,6 +70,7 @@ struct rc_ctx {
     unsigned long long *d_counters = nullptr;  // [RC_NUM_COUNTERS] work queue + statistics
     rc_aabb *d_obs_box = nullptr;              // obstacle AABB on the device (broad-phase stage)
     int stats_on = 0;
+    uint32_t gather_calls = 0;                 // rc_check_gather calls so far (all ranks call in lock-step)
     int coplanar_mode = 0;                     // rc_set_coplanar_mode: 0 = skip like the reference, 1 = decide in the plane
     uint32_t *d_trace = nullptr;               // rc_stats_trace (caller's memory)
     unsigned long long launches = 0;           // kernels launched through this context
@@ -145,6 +146,19 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
 cudaError_t launch_check_spheres(const rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_valid,
                                  uint32_t *d_bitmask, int want_stats, cudaStream_t stream,
                                  unsigned long long *queue);
+// all-gather of the bitmask through peer-mapped buffers (rc_gather.cuh)
+constexpr int kMaxGatherRanks = 16;
+struct GatherArgs {
+    const uint32_t *src;                     // this rank's slot in its own buffer
+    uint32_t *peer_slot[kMaxGatherRanks];    // the same slot inside every rank's buffer
+    uint32_t *peer_signal[kMaxGatherRanks];  // word [rank] of every rank's signal row
+    const uint32_t *my_signal;               // this rank's signal row
+    int rank, world, words;
+    uint32_t call;                           // 1, 2, 3, ...
+    unsigned long long *counters;
+    unsigned long long timeout_ns;
+};
+cudaError_t launch_gather_push(const rc_ctx *ctx, const GatherArgs &a, cudaStream_t stream);
 cudaError_t launch_fma_peak(float *d_out, int grid, int iters, cudaStream_t stream);
 cudaError_t launch_conf_generate(rc_config *d_out, long n, const float box[6], uint64_t seed,
                                  cudaStream_t stream);

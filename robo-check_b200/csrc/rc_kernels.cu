@@ -296,6 +296,7 @@ __global__ void __launch_bounds__(kThreads, 2) check_brute_kernel(const CheckArg
 #include "rc_culled.cuh"
 #include "rc_spheres.cuh"
 #include "rc_stages.cuh"
+#include "rc_gather.cuh"
 
 namespace rc {
 

@@ -45,3 +45,33 @@ def check_sharded(check_local, confs, dist, device=None):
     check_local(confs[lo:hi], mine)
     dist.all_gather_into_tensor(gather, mine.clone() if device is None else mine)
     return unpack_bitmask(gather.cpu().numpy(), world * per)[:n] if world * per >= n else None
+
+
+class PeerGather:
+    """The all-gather of the bitmask fused behind the check (rc_check_gather in robocheck.h): one
+    symmetric buffer per rank, mapped into every rank of the group with
+    torch.distributed._symmetric_memory, so that a small kernel behind the two check kernels stores
+    the rank's bitmask words straight into the peers' buffers over NVLink and waits for theirs -- no
+    communicator call in the step.  Raises if the symmetric allocation or the rendezvous is not
+    available; callers then fall back to check_sharded (NCCL all-gather)."""
+
+    def __init__(self, rc, dist, device, words_per_rank):
+        import torch
+        import torch.distributed._symmetric_memory as symm
+        self.world, self.rank, self.words = dist.get_world_size(), dist.get_rank(), int(words_per_rank)
+        total = int(rc.lib().rc_gather_buffer_words(self.world, self.words))
+        if total <= 0:
+            raise ValueError("world size / shard size not supported by rc_check_gather")
+        self.buf = symm.empty(total, dtype=torch.int32, device=device)
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, dist.group.WORLD)
+        self.ptrs = [int(self.hdl.get_buffer(r, (total,), torch.int32).data_ptr()) for r in range(self.world)]
+        assert self.ptrs[self.rank] == self.buf.data_ptr()
+        torch.cuda.synchronize(device)
+        dist.barrier()  # every buffer is zeroed before anybody delivers into it
+
+    def check(self, ctx, d_confs, n, d_valid=None, stream=None):
+        """Returns the gathered bitmask of this call: a view of world * words int32 words inside the
+        own buffer, valid (in stream order) until the second next call."""
+        off = ctx.check_gather(d_confs, n, d_valid, self.ptrs, self.rank, self.words, stream)
+        return self.buf[off:off + self.world * self.words]

@@ -38,8 +38,37 @@ def _worker(rank, world, port, n, q):
 
     flags = sh.check_sharded(check_local, confs, dist, device=torch.device("cuda", rank))
     single = ctx.check_host(confs)
+    ok = bool(np.array_equal(flags, single)) and len(flags) == n
+    # the same gather fused behind the check, over peer-mapped memory (rc_check_gather): three calls in
+    # a row (both gather areas, call numbers), ragged sizes incl. a short last shard
+    fused = "skipped"
+    try:
+        pg = sh.PeerGather(rc, dist, torch.device("cuda", rank), sh.words_per_shard(n, world))
+    except Exception as exc:  # symmetric memory not available on this box: NCCL path only
+        pg, fused = None, f"unavailable: {type(exc).__name__}: {exc}"
+    if pg is not None:
+        fused = "ok"
+        for call, m in enumerate((n, n - 4097, 70)):
+            sub = confs[:m]
+            lo, hi, per = sh.shard_bounds(m, world, rank)
+            # a shard never exceeds the slot the buffer was sized for
+            lo, hi = min(m, rank * pg.words * 32), min(m, (rank + 1) * pg.words * 32)
+            d = torch.from_numpy(np.ascontiguousarray(sub[lo:hi])).cuda()
+            words = pg.check(ctx, d, hi - lo, None, torch.cuda.current_stream())
+            torch.cuda.synchronize()
+            got = sh.unpack_bitmask(words.cpu().numpy(), world * pg.words * 32)[:m]
+            if not np.array_equal(got, single[:m]):
+                ok, fused = False, f"call {call}: {int((got != single[:m]).sum())} flags differ"
+        if ctx.stats()["watchdog"] != 0:
+            ok, fused = False, "watchdog"
+    agree = torch.tensor([int(ok)], device="cuda")
+    dist.all_reduce(agree, op=dist.ReduceOp.MIN)
     if rank == 0:
-        q.put(bool(np.array_equal(flags, single)) and len(flags) == n)
+        out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+        if os.path.isdir(out):
+            with open(os.path.join(out, "fused_gather_status.txt"), "w") as f:
+                f.write(fused + "\n")
+        q.put(bool(agree.item()))
     dist.barrier()
     dist.destroy_process_group()
 
