@@ -194,3 +194,20 @@ def test_shard_size_and_multi_argument_checks(rc):
     confs = np.zeros((4, 6), dtype=np.float32)
     mask = np.zeros(1, dtype=np.uint32)
     assert lib.rc_check_multi(handles, 2, confs.ctypes.data, 4, mask.ctypes.data, None, None) == rc.RC_ERR_INVALID
+
+
+def test_gather_and_coplanar_argument_checks(rc):
+    """rc_gather_buffer_words sizes the peer buffer (two gather areas + a signal row); rc_check_gather
+    and rc_set_coplanar_mode reject bad arguments with a status, without touching a device."""
+    import ctypes
+    lib = rc.lib()
+    assert lib.rc_gather_buffer_words(8, 3125) == 2 * 8 * 3125 + 8
+    assert lib.rc_gather_buffer_words(1, 1) == 3
+    for world, words in ((0, 10), (17, 10), (2, 0), (-1, 5)):
+        assert lib.rc_gather_buffer_words(world, words) == rc.RC_ERR_INVALID
+    peers = (ctypes.c_void_p * 2)(None, None)
+    res = ctypes.c_void_p()
+    assert lib.rc_check_gather(None, None, 0, None, peers, 0, 2, 10, ctypes.byref(res), None) == rc.RC_ERR_INVALID
+    assert lib.rc_set_coplanar_mode(None, rc.RC_COPLANAR_DECIDE) == rc.RC_ERR_INVALID
+    assert lib.rc_coplanar_mode(None) == rc.RC_ERR_INVALID
+    assert (rc.RC_COPLANAR_SKIP, rc.RC_COPLANAR_DECIDE) == (0, 1)
