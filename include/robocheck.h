@@ -170,6 +170,19 @@ int rc_conf_generate_device(rc_ctx *ctx, rc_config *d_out, long n, float x_min, 
 int rc_compact(rc_ctx *ctx, const uint8_t *d_valid, const uint32_t *d_bitmask, long n, int want,
                uint32_t *d_indices, unsigned long long *d_count, void *stream);
 
+/* ---- pipelined host calls (planner loops) ---------------------------------------
+ * rc_check_host returns when the flags are in host memory, so the copy of the next batch cannot
+ * start before the kernels of this one have finished (the reference has the same shape, plus its
+ * 45-50 ms of per-call set-up, report 4.8).  rc_check_host_submit queues a batch and returns at
+ * once; up to two batches are in flight per context: the configurations of batch k+1 travel on a
+ * copy stream while the kernels of batch k run, the kernels of all batches run one after the other.
+ * rc_check_host_wait(ticket) returns when the flags of that batch are in h_valid.  Buffers must stay
+ * untouched between submit and wait; page-locked buffers are used in place, pageable ones are
+ * staged.  Submitting a third batch first completes the oldest one.  Tickets count up from 0. */
+int rc_check_host_submit(rc_ctx *ctx, const rc_config *h_confs, long n, uint8_t *h_valid, int mode,
+                         int *ticket);
+int rc_check_host_wait(rc_ctx *ctx, int ticket);
+
 /* ---- one process per GPU: check + all-gather of the bitmask in one call -----------
  * The reference is single-GPU.  north_star shards the configurations over the GPUs of a box and
  * gathers only the validity bitmask (ncclAllGather); here the gather is fused behind the check and

@@ -60,6 +60,8 @@ ABI = [
     ("rc_shard_size", _i, [_l, _i]),
     ("rc_device_count", _i, [C.POINTER(_i)]),
     ("rc_check_multi", _i, [_vp, _i, _vp, _l, _vp, _vp, _vp]),
+    ("rc_check_host_submit", _i, [_vp, _vp, _l, _vp, _i, C.POINTER(_i)]),
+    ("rc_check_host_wait", _i, [_vp, _i]),
     ("rc_gather_buffer_words", _l, [_i, _l]),
     ("rc_check_gather", _i, [_vp, _vp, _l, _vp, _vp, _i, _i, _l, _vp, _vp]),
     ("rc_transform_aos", _i, [_vp, _vp, _l, _vp, _i, _vp, _vp]),
@@ -370,6 +372,23 @@ class Context:
         valid = np.zeros(len(confs), np.uint8)
         _check(_lib.rc_check_host(self._h, _ptr(confs), len(confs), _ptr(valid), mode), self._h)
         return valid
+
+    def check_host_submit(self, confs, valid_out, mode=RC_MODE_CULLED):
+        """Queue a batch (rc_check_host_submit): `confs` float32 [n, 6] and `valid_out` uint8 [n], both
+        C-contiguous numpy arrays that stay untouched until check_host_wait(ticket) returns."""
+        assert confs.dtype == np.float32 and confs.flags.c_contiguous and valid_out.dtype == np.uint8
+        n = confs.shape[0]
+        assert valid_out.flags.c_contiguous and valid_out.size >= n
+        ticket = C.c_int(-1)
+        _check(_lib.rc_check_host_submit(self._h, _ptr(confs), n, _ptr(valid_out), mode, C.byref(ticket)), self._h)
+        if not hasattr(self, "_inflight"):
+            self._inflight = {}
+        self._inflight[ticket.value] = (confs, valid_out)  # keep the buffers alive
+        return ticket.value
+
+    def check_host_wait(self, ticket):
+        _check(_lib.rc_check_host_wait(self._h, int(ticket)), self._h)
+        return getattr(self, "_inflight", {}).pop(ticket, (None, None))[1]
 
     # stage API -----------------------------------------------------------------------------------
     def transform_aos(self, d_confs, n, d_out, d_base=None, n_v=0, stream=None):

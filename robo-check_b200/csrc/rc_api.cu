@@ -192,6 +192,49 @@ int ensure_staging(rc_ctx *ctx, long n)
     return RC_OK;
 }
 
+int ensure_lane(rc_ctx *ctx, PipeLane &l, long n)
+{
+    cudaError_t e;
+    if (!l.copied && ((e = cudaEventCreateWithFlags(&l.copied, cudaEventDisableTiming)) ||
+                      (e = cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming))))
+        return check_cuda(ctx, e, "pipeline events");
+    if (n <= l.cap) return RC_OK;
+    if (l.d_confs) cudaFree(l.d_confs);
+    if (l.d_valid) cudaFree(l.d_valid);
+    if (l.h_confs) cudaFreeHost(l.h_confs);
+    if (l.h_valid) cudaFreeHost(l.h_valid);
+    l.d_confs = nullptr; l.d_valid = nullptr; l.h_confs = nullptr; l.h_valid = nullptr; l.cap = 0;
+    const long cap = std::max(n, 1L << 16);
+    if ((e = cudaMalloc(&l.d_confs, (size_t)cap * sizeof(rc_config))) || (e = cudaMalloc(&l.d_valid, (size_t)cap)) ||
+        (e = cudaMallocHost(&l.h_confs, (size_t)cap * sizeof(rc_config))) ||
+        (e = cudaMallocHost(&l.h_valid, (size_t)cap)))
+        return check_cuda(ctx, e, "pipeline staging buffers");
+    l.cap = cap;
+    return RC_OK;
+}
+
+void free_lane(PipeLane &l)
+{
+    if (l.d_confs) cudaFree(l.d_confs);
+    if (l.d_valid) cudaFree(l.d_valid);
+    if (l.h_confs) cudaFreeHost(l.h_confs);
+    if (l.h_valid) cudaFreeHost(l.h_valid);
+    if (l.copied) cudaEventDestroy(l.copied);
+    if (l.done) cudaEventDestroy(l.done);
+    l = PipeLane();
+}
+
+int finish_lane(rc_ctx *ctx, PipeLane &l)
+{
+    if (!l.busy) return RC_OK;
+    const cudaError_t e = cudaEventSynchronize(l.done);
+    l.busy = false;
+    if (e != cudaSuccess) return check_cuda(ctx, e, "rc_check_host_wait");
+    if (l.user_valid) std::memcpy(l.user_valid, l.h_valid, (size_t)l.n);
+    l.user_valid = nullptr;
+    return RC_OK;
+}
+
 }  // namespace
 }  // namespace rc
 
@@ -416,6 +459,7 @@ void rc_destroy(rc_ctx *ctx)
     if (ctx->d_work_mat) cudaFree(ctx->d_work_mat);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    free_lane(ctx->pipe[0]); free_lane(ctx->pipe[1]);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->own_stream2) cudaStreamDestroy(ctx->own_stream2);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -561,6 +605,60 @@ int rc_check_host(rc_ctx *ctx, const rc_config *h_confs, long n, uint8_t *h_vali
     cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev0, ctx->ev1);
     if (!out_pinned) std::memcpy(h_valid, ctx->h_pinned_valid, (size_t)n);
     return RC_OK;
+}
+
+int rc_check_host_submit(rc_ctx *ctx, const rc_config *h_confs, long n, uint8_t *h_valid, int mode, int *ticket)
+{
+    if (!ctx || !ticket || n <= 0 || !h_confs || !h_valid) return RC_ERR_INVALID;
+    if (mode != RC_MODE_CULLED && mode != RC_MODE_BRUTE) return RC_ERR_INVALID;
+    if (n > 0xffffffffL) return RC_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    PipeLane &l = ctx->pipe[ctx->pipe_next & 1];
+    int rcode = finish_lane(ctx, l);  // the batch submitted two calls ago, if nobody has waited for it yet
+    if (rcode != RC_OK || (rcode = ensure_lane(ctx, l, n)) != RC_OK) return rcode;
+    if (mode == RC_MODE_CULLED && (rcode = ensure_work_list(ctx, n)) != RC_OK) return rcode;
+    cudaStream_t copy = ctx->own_stream2, compute = ctx->own_stream;
+    cudaPointerAttributes pa_in{}, pa_out{};
+    const bool in_pinned = cudaPointerGetAttributes(&pa_in, h_confs) == cudaSuccess && pa_in.type == cudaMemoryTypeHost;
+    const bool out_pinned = cudaPointerGetAttributes(&pa_out, h_valid) == cudaSuccess && pa_out.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    const rc_config *src = h_confs;
+    if (!in_pinned) {
+        std::memcpy(l.h_confs, h_confs, (size_t)n * sizeof(rc_config));
+        src = l.h_confs;
+    }
+    uint8_t *dst = out_pinned ? h_valid : l.h_valid;
+    void *mapped = nullptr;
+    const bool direct = ctx->knob_host_direct && cudaHostGetDevicePointer(&mapped, dst, 0) == cudaSuccess && mapped;
+    cudaGetLastError();
+    cudaError_t e;
+    // copy stream: the configurations; compute stream: the kernels of all batches, one after the other
+    // (one work list per context), each waiting only for its own copy
+    if ((e = cudaMemcpyAsync(l.d_confs, src, (size_t)n * sizeof(rc_config), cudaMemcpyHostToDevice, copy)) ||
+        (e = cudaEventRecord(l.copied, copy)) || (e = cudaStreamWaitEvent(compute, l.copied, 0)))
+        return check_cuda(ctx, e, "rc_check_host_submit copy");
+    e = launch_check(ctx, l.d_confs, n, direct ? static_cast<uint8_t *>(mapped) : l.d_valid, nullptr, mode,
+                     ctx->stats_on, compute, ctx->d_queues);
+    if (e == cudaErrorInvalidConfiguration)
+        return set_error(ctx, RC_ERR_UNSUPPORTED, "mesh tables do not fit in shared memory");
+    if (e) return check_cuda(ctx, e, "rc_check_host_submit launch");
+    ctx->launches += mode == RC_MODE_CULLED ? 2 : 1;
+    if ((!direct && (e = cudaMemcpyAsync(dst, l.d_valid, (size_t)n, cudaMemcpyDeviceToHost, compute))) ||
+        (e = cudaEventRecord(l.done, compute)))
+        return check_cuda(ctx, e, "rc_check_host_submit");
+    l.busy = true; l.n = n; l.user_valid = out_pinned ? nullptr : h_valid;
+    l.ticket = ctx->pipe_next;
+    *ticket = ctx->pipe_next++;
+    return RC_OK;
+}
+
+int rc_check_host_wait(rc_ctx *ctx, int ticket)
+{
+    if (!ctx || ticket < 0 || ticket >= ctx->pipe_next) return RC_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    PipeLane &l = ctx->pipe[ticket & 1];
+    if (l.ticket != ticket) return RC_OK;  // completed when its lane was taken over by a later batch
+    return finish_lane(ctx, l);
 }
 
 int rc_device_count(int *count)

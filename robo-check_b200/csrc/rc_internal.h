@@ -57,7 +57,23 @@ struct DeviceTables {
 constexpr int kWorkBins = 8;
 constexpr int kWorkCounters = 16;  // [0..7] entries per class, [8] next entry, [9] CTAs finished
 
+// one of the two batches rc_check_host_submit may have in flight
+struct PipeLane {
+    rc_config *d_confs = nullptr;   // device staging of the configurations
+    rc_config *h_confs = nullptr;   // page-locked staging for pageable callers
+    uint8_t *h_valid = nullptr;     // page-locked staging for pageable callers
+    uint8_t *d_valid = nullptr;     // device flags when the host buffer cannot be mapped
+    long cap = 0;
+    cudaEvent_t copied = nullptr, done = nullptr;
+    bool busy = false;
+    int ticket = -1;
+    uint8_t *user_valid = nullptr;  // where the flags go at rc_check_host_wait (nullptr: already there)
+    long n = 0;
+};
+
 struct rc_ctx {
+    PipeLane pipe[2];
+    int pipe_next = 0;
     int device = 0;
     int sm_count = 0;
     int max_smem_optin = 0;

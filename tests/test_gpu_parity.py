@@ -685,3 +685,35 @@ def test_subdivided_obstacle_full_size_every_flag(rc, po, meshes, levels, n):
         assert np.array_equal(bits, want)
     finally:
         c.close()
+
+
+def test_pipelined_host_calls(rc, ctx, po, omeshes):
+    """rc_check_host_submit / rc_check_host_wait: batches of different sizes in flight two at a time,
+    page-locked and pageable buffers, both kernels, waits in and out of order -- the flags equal the
+    synchronous call's (which equal the oracle's on the first batch)."""
+    torch = _torch()
+    sizes = [5000, 40001, 33, 70000, 1, 9999, 20000]
+    batches = [rc.createAlphaBotConfigurations(n, k % 3 != 2, 900 + k) for k, n in enumerate(sizes)]
+    want = [ctx.check_host(b) for b in batches]
+    assert np.array_equal(want[0], po.check_bvh(omeshes[0], omeshes[1], batches[0], po.VARIANT_GPU))
+    for pinned in (True, False):
+        if pinned:
+            ins = [torch.from_numpy(b).pin_memory().numpy() for b in batches]
+            outs = [torch.full((len(b),), 9, dtype=torch.uint8).pin_memory().numpy() for b in batches]
+        else:
+            ins = [b.copy() for b in batches]
+            outs = [np.full(len(b), 9, np.uint8) for b in batches]
+        tickets = []
+        for k in range(len(batches)):
+            mode = rc.RC_MODE_BRUTE if k == 2 else rc.RC_MODE_CULLED
+            tickets.append(ctx.check_host_submit(ins[k], outs[k], mode))
+            if k >= 1 and k % 2 == 1:
+                ctx.check_host_wait(tickets[k - 1])       # one behind: two batches in flight
+        for t in reversed(tickets):                        # the rest, newest first; finished ones are no-ops
+            ctx.check_host_wait(t)
+        assert tickets == sorted(tickets) and len(set(tickets)) == len(tickets)
+        for k in range(len(batches)):
+            assert np.array_equal(outs[k], want[k]), (pinned, k, int((outs[k] != want[k]).sum()))
+    with pytest.raises(rc.RoboCheckError):
+        ctx.check_host_wait(10 ** 6)
+    assert ctx.stats()["watchdog"] == 0
