@@ -118,7 +118,7 @@ struct rc_ctx {
     int knob_pdl = 1;        // RC_PDL=0: no programmatic dependent launch of the descent step
     int knob_bound = 1;      // RC_BOUND=0: classify without the vertex-group boxes
     int knob_mail_slots = 4, knob_donate_min = 40;  // RC_MAIL_SLOTS, RC_DONATE_MIN
-    int knob_host_direct = 1; // RC_HOST_DIRECT=0: rc_check_host copies the flags back instead of storing them into the pinned buffer
+    int knob_host_direct = 0; // RC_HOST_DIRECT=1: rc_check_host stores the flags into the pinned buffer from the kernels instead of copying them back
     int knob_share = 1;      // RC_SHARE=0: warps of a CTA do not hand pieces of a deep descent to each other
     std::string last_error;
     std::vector<void *> allocations;
