@@ -211,3 +211,48 @@ def test_gather_and_coplanar_argument_checks(rc):
     assert lib.rc_set_coplanar_mode(None, rc.RC_COPLANAR_DECIDE) == rc.RC_ERR_INVALID
     assert lib.rc_coplanar_mode(None) == rc.RC_ERR_INVALID
     assert (rc.RC_COPLANAR_SKIP, rc.RC_COPLANAR_DECIDE) == (0, 1)
+
+
+def test_host_io_properties(rc, tmp_path):
+    """Property checks of the loaders on generated input (hypothesis): polygons of any arity in any of
+    the OBJ token forms are fanned around their first corner (Utils_rai.cu:139-320), and a .conf file
+    written from what was read from a .conf file is read back bit for bit (6-digit text, :25-34)."""
+    from hypothesis import given, settings, strategies as st
+
+    coord = st.floats(min_value=-1e3, max_value=1e3, allow_nan=False, width=32)
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.lists(st.tuples(coord, coord, coord), min_size=3, max_size=24),
+           st.lists(st.tuples(st.integers(3, 7), st.integers(0, 2)), min_size=1, max_size=12), st.randoms())
+    def obj_case(verts, faces, rnd):
+        lines = ["# generated"] + [f"v {x!r} {y!r} {z!r}" for x, y, z in verts] + ["vn 0 0 1", "vt 0 0"]
+        want = []
+        for arity, form in faces:
+            idx = [rnd.randrange(len(verts)) for _ in range(arity)]
+            tok = {0: lambda i: f"{i + 1}", 1: lambda i: f"{i + 1}//1", 2: lambda i: f"{i + 1}/1/1"}[form]
+            lines.append("f " + " ".join(tok(i) for i in idx))
+            want += [(idx[0], idx[k], idx[k + 1]) for k in range(1, arity - 1)]
+        p = tmp_path / "h.obj"
+        p.write_text("\n".join(lines) + "\n")
+        x, y, z, v1, v2, v3 = rc.loadOBJFile(str(p))
+        assert np.array_equal(x, np.float32([v[0] for v in verts]))
+        assert np.array_equal(z, np.float32([v[2] for v in verts]))
+        assert list(zip(v1.tolist(), v2.tolist(), v3.tolist())) == want
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.lists(st.tuples(*([st.floats(min_value=-700, max_value=700, allow_nan=False, width=32)] * 6)),
+                    min_size=0, max_size=40), st.randoms())
+    def conf_case(rows, rnd):
+        confs = np.array(rows, np.float32).reshape(-1, 6)
+        tags = np.array([rnd.randrange(2) for _ in rows], np.uint8)
+        p = str(tmp_path / "h.conf")
+        rc.writeConfigurationToFileTagged(confs, tags, p)
+        once, t1 = rc.readConfigurationFromFileTagged(p)
+        assert once.shape == confs.shape and np.array_equal(t1, tags)
+        assert np.allclose(once, confs, rtol=1e-5, atol=1e-30)      # 6 significant digits
+        rc.writeConfigurationToFileTagged(once, t1, p)
+        twice, t2 = rc.readConfigurationFromFileTagged(p)
+        assert np.array_equal(twice.view(np.uint32), once.view(np.uint32)) and np.array_equal(t2, tags)
+
+    obj_case()
+    conf_case()
