@@ -16,7 +16,11 @@
  *  - `stream` is a cudaStream_t passed as void* (NULL = CUDA's legacy default stream, as in
  *    the runtime API); stage calls are asynchronous on it unless stated otherwise.  The *_host
  *    convenience calls use a private stream of the context and synchronise before returning.
- *  - one context per device; calls on one context are serialised by the caller.
+ *  - one context per device; calls on one context are serialised by the caller (host side).  Device
+ *    work the calls leave queued is ordered by the library: entry points of one context share its
+ *    scratch (work lists, about 80 bytes per configuration of the largest batch seen), and a launch
+ *    on another stream than the previous one first waits for it (an event), so rc_check on the
+ *    caller's stream followed by rc_check_host on the context's own stream is safe.
  *  - there is NO CPU fallback: without a usable CUDA device rc_create fails with
  *    RC_ERR_NO_DEVICE.
  */
@@ -47,16 +51,20 @@ typedef struct { float x_min, y_min, z_min, x_max, y_max, z_max; } rc_aabb;     
 typedef struct rc_ctx rc_ctx;
 typedef struct rc_mesh rc_mesh;
 
-/* rc_check modes.
- * RC_MODE_BRUTE decides every pair the reference decides: its flags equal the reference's on any
- * input.  RC_MODE_CULLED never looks at a pair whose triangles are separated by more than 2e-3 (an
- * ancestor box pair is disjoint).  The reference's arithmetic agrees with that on well-conditioned
- * pairs, and on the alpha1.0 scene always (0 of 86,410 reported pairs were box-disjoint; 0 flag
- * differences on 600,000 configurations against the reference pipeline).  It does NOT
- * agree for nearly coplanar triangle pairs: there the reference's intersection line is rounding
- * noise and it can report two triangles that lie far apart inside their common plane
- * (tests/coplanar_scene.py has one such configuration in 3,000).  RC_MODE_CULLED calls such a
- * configuration valid, i.e. where the two modes differ the culled answer is the geometric one. */
+/* rc_check modes -- the exactness contract.
+ * RC_MODE_BRUTE decides every pair the reference decides, with the reference's arithmetic: its
+ * flags are bit-identical to the reference pipeline on ANY input, by construction.
+ * RC_MODE_CULLED decides with the same arithmetic every pair it looks at, but never looks at a pair
+ * whose triangles are separated by more than twice the box margin (2e-3 on scenes up to 250 units,
+ * proportionally more beyond: an ancestor pair of inflated boxes is disjoint).  Its flags equal the
+ * reference's whenever the reference reports no such box-disjoint pair.  That is an EMPIRICAL
+ * property of the scene, not a theorem: for two nearly coplanar triangles the reference's
+ * intersection line is rounding noise and it can report a pair whose triangles lie far apart inside
+ * their common plane (tests/coplanar_scene.py: one configuration in 3,000).  RC_MODE_CULLED calls
+ * such a configuration valid, i.e. where the two modes differ the culled answer is the geometric
+ * one.  On alpha1.0 no such pair exists in any set examined (every BASELINE workload).
+ * rc_audit() below measures the property on the caller's own scene and configurations: flags AND
+ * per-configuration hitting-pair counts of the two modes side by side. */
 #define RC_MODE_CULLED 0 /* BVH-culled fused kernel (default, fastest)                        */
 #define RC_MODE_BRUTE 1  /* fused kernel, all n_rob_t x n_obs_t pairs: the reference's sweep  */
 
@@ -83,8 +91,8 @@ int rc_obstacle_aabb(const rc_ctx *ctx, rc_aabb *out);
  * Replaces  MegaKernel<<<>>> / CallMegaKernel (test/MegaKernel.hu:6-9) and the live pipeline
  * broadPhaseFused_sep = broadPhaseFusedKernel_sep + narrowPhaseKernel_coarse
  * (broad-phase-fused.cu:365-520).  One persistent kernel: SE(3) transform, warp-shuffle AABB,
- * broad phase, narrow phase with early exit.  Flags are bit-identical to the reference
- * pipeline.  d_valid (n bytes) and d_bitmask (ceil(n/32) words, bit i%32 of word i/32 = valid)
+ * broad phase, narrow phase with early exit.  Flags: see the exactness contract of the two modes
+ * above.  d_valid (n bytes) and d_bitmask (ceil(n/32) words, bit i%32 of word i/32 = valid)
  * are both optional but at least one must be given.  Unlike MegaKernel the outputs need no
  * pre-fill.  Asynchronous. */
 int rc_check(rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_valid, uint32_t *d_bitmask,
@@ -185,23 +193,41 @@ int rc_check_host_wait(rc_ctx *ctx, int ticket);
 
 /* ---- one process per GPU: check + all-gather of the bitmask in one call -----------
  * The reference is single-GPU.  north_star shards the configurations over the GPUs of a box and
- * gathers only the validity bitmask (ncclAllGather); here the gather is fused behind the check and
+ * gathers only the validity bitmask (ncclAllGather); here the gather is fused INTO the check and
  * runs over peer-mapped memory (NVLink / NVSwitch) without a communicator call: every rank owns one
  * buffer of rc_gather_buffer_words(world, words_per_rank) 32-bit words, ZEROED once, mapped into the
  * address space of every rank (torch.distributed._symmetric_memory, cudaIpcOpenMemHandle, ...);
  * peer_buffers[r] is rank r's buffer as seen from the calling process (peer_buffers[rank] = the own
  * one).  rc_check_gather checks the rank's n configurations (n <= 32 * words_per_rank, mode
- * RC_MODE_CULLED) with the bitmask going straight into the rank's slot, stores the slot into every
- * peer's buffer, signals, and waits for the peers' slots.  All ranks must call it the same number of
+ * RC_MODE_CULLED) with the bitmask going straight into the rank's slot; the last CTA of the check
+ * kernel to finish stores the slot into every peer's buffer, signals, and waits for the peers'
+ * slots -- two launches per call, the same as rc_check.  All ranks must call it the same number of
  * times with the same world / words_per_rank (a collective).  After the call, in stream order,
  * *d_result points at world * words_per_rank words inside the own buffer: the bitmask of all ranks
  * (rank r's configurations start at bit 32 * words_per_rank * r).  It stays valid until the second
- * next call.  A peer that never arrives is counted in rc_stats.watchdog after 4 s instead of
- * hanging the device.  d_valid (optional) receives the rank's own flag bytes. */
+ * next call.  The call numbering lives in the buffer, so contexts may come and go.  A peer that never
+ * arrives makes the wait give up after 4 s instead of hanging the device: the result is then
+ * incomplete, and the only way to know is rc_gather_status (sticky `timeouts` word; also counted
+ * in rc_stats.watchdog).  d_valid (optional) receives the rank's own flag bytes.
+ *
+ * Two-phase form: rc_check_gather_begin does everything but the wait (it returns, in stream order,
+ * once the own slot has been delivered and signalled), rc_gather_end enqueues the wait for the
+ * peers' slots of that call.  Work that does not need the peers' flags can sit between the two.
+ * (It is also how the multi-rank path is tested on ONE device: begin for every emulated rank, then
+ * end for every rank -- kernels that wait for each other must not share a GPU.) */
 long rc_gather_buffer_words(int world, long words_per_rank);
 int rc_check_gather(rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_valid,
                     void *const *peer_buffers, int rank, int world, long words_per_rank,
                     uint32_t **d_result, void *stream);
+int rc_check_gather_begin(rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_valid,
+                          void *const *peer_buffers, int rank, int world, long words_per_rank,
+                          uint32_t **d_result, void *stream);
+int rc_gather_end(rc_ctx *ctx, void *const *peer_buffers, int rank, int world, long words_per_rank,
+                  void *stream);
+/* Header words of the own gather buffer, read back synchronously: number of the last call this rank
+ * delivered, and how many waits have timed out since the buffer was zeroed (must be 0). */
+int rc_gather_status(rc_ctx *ctx, const void *own_buffer, int world, long words_per_rank,
+                     uint32_t *calls, uint32_t *timeouts);
 
 /* ---- sphere-approximated robot (BASELINE config 3) -----------------------------
  * The reference has no such path (test/CPU-Sphere-Test.cpp:8-18 only collides two unit spheres
@@ -230,13 +256,40 @@ int rc_check_spheres(rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_v
 int rc_set_coplanar_mode(rc_ctx *ctx, int mode);
 int rc_coplanar_mode(const rc_ctx *ctx);
 
+/* ---- audits (closing rule) ------------------------------------------------
+ * rc_hit_counts: the check of `mode` WITHOUT early exit; d_counts[i] = number of (robot triangle,
+ * obstacle triangle) pairs of configuration i that the reference arithmetic reports -- all n_rob_t x
+ * n_obs_t of them in RC_MODE_BRUTE, the ones the tree descent reaches in RC_MODE_CULLED; 0 for a
+ * configuration the broad phase clears; 0xffffffff if the descent fell back to the exhaustive sweep
+ * (pair stack overflow).  d_valid (optional) receives the flags.  Equal counts in both modes mean
+ * the culling skipped no reported pair; equal counts against an independent CPU sweep mean no
+ * compensating per-pair errors hide behind equal flags (a colliding alpha1.0 configuration has about
+ * 100 hitting pairs).  Asynchronous; slower than rc_check (statistics kernels, no early exit). */
+int rc_hit_counts(rc_ctx *ctx, const rc_config *d_confs, long n, int mode, uint8_t *d_valid,
+                  uint32_t *d_counts, void *stream);
+/* rc_audit: both modes on the same configurations; how many flags differ, how many hitting-pair
+ * counts differ, and the first `cap` indices where either does (ascending).  Blocking. */
+int rc_audit(rc_ctx *ctx, const rc_config *d_confs, long n, long *n_flags_differ, long *n_counts_differ,
+             uint32_t *h_indices, long cap);
+/* Device known-answer tests: the per-pair helpers the kernels are built from, run on n host-supplied
+ * (robot triangle, obstacle triangle) pairs of 9 floats each (the role of the reference's host-side
+ * unit tests, narrow-phase/test-narrow-phase.cu:7-626).  h_out32[32 * i ...]: 0-2 Nr, 3 dr, 4-6
+ * signed distances of the obstacle vertices, 7-9 No, 10 do, 11-13 signed distances of the robot
+ * vertices, 14-16 D, 17-19 O, 20-23 t_r01 t_r12 t_o01 t_o12 (14-23 only when both plane tests pass
+ * and the pair is not coplanar).  h_verdict[i] = plane test O | plane test R << 1 | tail << 2, tail:
+ * 0 miss, 1 hit, 2 coplanar.  rc_kat_la_solve: la_solve on (A1 A2 A3 A4 b1 b2) -> (x1 x2). */
+int rc_kat_pairs(rc_ctx *ctx, const float *h_rob9, const float *h_obs9, int n, float *h_out32, int *h_verdict);
+int rc_kat_la_solve(rc_ctx *ctx, const float *h_in6, int n, float *h_out2);
+
 /* ---- measurement ------------------------------------------------------------------------- */
 typedef struct {
     unsigned long long broad_cleared, sphere_cleared, narrow_valid, narrow_invalid;
     unsigned long long node_pairs, leaf_pairs, tri_pairs, tail_pairs, overflow, launches;
     unsigned long long node_rounds, leaf_rounds, tail_rounds; /* warp steps of each phase */
     unsigned long long shared_pieces;  /* parts of a descent one warp handed to another */
-    unsigned long long watchdog, watchdog_where; /* hand-over waits that gave up: must be 0 */
+    unsigned long long watchdog, watchdog_where; /* waits that gave up: must be 0.  Inside the check kernels a
+                                                  * give-up costs parallelism only, never a flag; a gather wait
+                                                  * that gave up (bit 3) left *d_result incomplete */
 } rc_stats;
 /* Statistics of rc_check calls since the last reset; counting is off by default. */
 int rc_stats_enable(rc_ctx *ctx, int on);
@@ -274,6 +327,33 @@ const int *rc_mesh_v3(const rc_mesh *m);
 int rc_mesh_subdivide(const rc_mesh *m, int levels, rc_mesh **out);
 int rc_mesh_aabb(const rc_mesh *m, rc_aabb *out);
 void rc_mesh_free(rc_mesh *m);
+
+/* .env / .query of the motion-planning benchmark the meshes come from (models/alpha1.0/alpha.env,
+ * alpha.query).  The environment file names the bodies and places the passive ones in the world
+ * (alpha.env:13 puts the obstacle at 11.0899 9.00906 3.24427, no rotation); the query file holds
+ * start and goal.  The reference ignores both and checks the OBJ files as they are, so the default
+ * everywhere in this library is the unplaced mesh; a caller who wants the benchmark's world frame
+ * reads the file and applies the placement with rc_mesh_place before rc_create_from_meshes.
+ * Rotations of a placement are degrees about x, y, z (applied as Rz Ry Rx, the reference's own
+ * matrix); the query's three rotations are fractions of a full turn (-> roll, pitch, yaw). */
+#define RC_ENV_MAX_BODIES 16
+typedef struct {
+    char file[256];        /* geometry file as written, relative to the .env file      */
+    int active;            /* 1 = robot (movable body), 0 = passive obstacle             */
+    float color[4];        /* -c(r g b a); 0 0 0 1 when absent                           */
+    int has_placement;     /* passive bodies: x y z rx ry rz follow the file name        */
+    float x, y, z, rx, ry, rz;
+} rc_env_body;
+typedef struct {
+    int has_box;           /* "Boundary Box [lo:hi ; lo:hi ; lo:hi]" present            */
+    float box_lo[3], box_hi[3];
+    int n_bodies;
+    rc_env_body bodies[RC_ENV_MAX_BODIES];
+} rc_env;
+int rc_env_read(const char *path, rc_env *out);
+int rc_query_read(const char *path, rc_config **confs, long *n); /* free *confs with rc_free */
+int rc_mesh_place(const rc_mesh *m, float x, float y, float z, float rx_deg, float ry_deg, float rz_deg,
+                  rc_mesh **out);
 
 /* .conf: one header line, then `x y z pitch yaw roll tag` per line
  * (readConfigurationFromFile / writeConfigurationToFileTagged, Utils_rai.cu:11-97).

@@ -55,6 +55,9 @@ void generateAABBBaseline(std::vector<float> &x, std::vector<float> &y, std::vec
 void generateAABBBaseline(Vector3f *vertices, unsigned int numVertices, unsigned int numConfigs, AABB *botBounds);
 // broad-phase/broad-phase.hu:13 -- device pointers, asynchronous on the default stream
 void broadPhase(int num_confs, const AABB *robots, const AABB *obstacle, bool *valid_conf);
+// broad-phase/broad-phase.hu:17 -- host pointers.  The reference declares it and never defines it;
+// here it is the inclusive per-axis overlap test of the kernel (broad-phase.cu:10-28) on the host.
+void broadPhaseBaseline(int num_confs, const AABB *robots, const AABB *obstacle, bool *valid_conf);
 // narrow-phase/narrow-phase.hu:22-33 -- host pointers, valid_conf in/out (true entries skipped)
 void narrowPhase(int num_confs, int num_rob_trs, int num_rob_pts, int num_obs_trs, int num_obs_pts,
                  const Triangle *rob_trs, const Vector3f *rob_pts, const Triangle *obs_trs,
@@ -62,3 +65,14 @@ void narrowPhase(int num_confs, int num_rob_trs, int num_rob_pts, int num_obs_tr
 void narrowPhase_unopt(int num_confs, int num_rob_trs, int num_rob_pts, int num_obs_trs, int num_obs_pts,
                        const Triangle *rob_trs, const Vector3f *rob_pts, const Triangle *obs_trs,
                        const Vector3f *obs_pts, bool *valid_conf);
+// narrow-phase/narrow-phase.hu:37 -- the reference's CPU baseline: writes EVERY valid_conf[i] (no
+// in/out skipping, narrow-phase.cu:346-423).  There is no CPU path in this library, so the call
+// runs the exhaustive GPU sweep on all configurations.  The arithmetic is the live CUDA kernel's,
+// which differs from the reference's host code in four documented places (FMA
+// contraction, the float/double threshold of no_overlap, coplanarity tested after the second plane
+// test, `>=` instead of `>` in the interval test); on alpha1.0 the two agree on every configuration
+// of the golden sets.  Coplanar pairs are skipped silently (the reference prints a line per
+// configuration, :419-420).
+void narrowPhaseBaseline(int num_confs, int num_rob_trs, int num_rob_pts, int num_obs_trs, int num_obs_pts,
+                         const Triangle *rob_trs, const Vector3f *rob_pts, const Triangle *obs_trs,
+                         const Vector3f *obs_pts, bool *valid_conf);

@@ -15,7 +15,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "librobocheck.so")
+# RC_LIB: another build of the same library (A/B runs of two source trees in profiles/tools)
+LIB_PATH = os.environ.get("RC_LIB") or os.path.join(_HERE, "librobocheck.so")
 ASSET_DIR = os.path.join(REPO_ROOT, "assets", "alpha1.0")
 
 RC_OK = 0
@@ -34,6 +35,20 @@ class RoboCheckError(RuntimeError):
         self.code = code
         msg = _lib.rc_strerror(code).decode() if _lib is not None else str(code)
         super().__init__(f"robocheck error {code}: {msg}" + (f" ({detail})" if detail else ""))
+
+
+RC_ENV_MAX_BODIES = 16
+
+
+class rc_env_body(C.Structure):
+    _fields_ = [("file", C.c_char * 256), ("active", C.c_int), ("color", C.c_float * 4),
+                ("has_placement", C.c_int), ("x", C.c_float), ("y", C.c_float), ("z", C.c_float),
+                ("rx", C.c_float), ("ry", C.c_float), ("rz", C.c_float)]
+
+
+class rc_env(C.Structure):
+    _fields_ = [("has_box", C.c_int), ("box_lo", C.c_float * 3), ("box_hi", C.c_float * 3),
+                ("n_bodies", C.c_int), ("bodies", rc_env_body * RC_ENV_MAX_BODIES)]
 
 
 class rc_stats(C.Structure):
@@ -64,6 +79,13 @@ ABI = [
     ("rc_check_host_wait", _i, [_vp, _i]),
     ("rc_gather_buffer_words", _l, [_i, _l]),
     ("rc_check_gather", _i, [_vp, _vp, _l, _vp, _vp, _i, _i, _l, _vp, _vp]),
+    ("rc_check_gather_begin", _i, [_vp, _vp, _l, _vp, _vp, _i, _i, _l, _vp, _vp]),
+    ("rc_gather_end", _i, [_vp, _vp, _i, _i, _l, _vp]),
+    ("rc_gather_status", _i, [_vp, _vp, _i, _l, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    ("rc_hit_counts", _i, [_vp, _vp, _l, _i, _vp, _vp, _vp]),
+    ("rc_audit", _i, [_vp, _vp, _l, C.POINTER(_l), C.POINTER(_l), _vp, _l]),
+    ("rc_kat_pairs", _i, [_vp, _vp, _vp, _i, _vp, _vp]),
+    ("rc_kat_la_solve", _i, [_vp, _vp, _i, _vp]),
     ("rc_transform_aos", _i, [_vp, _vp, _l, _vp, _i, _vp, _vp]),
     ("rc_generate_aabb", _i, [_vp, _vp, _u, _u, _vp, _vp]),
     ("rc_generate_aabb_host", _i, [_vp, _vp, _u, _u, _vp]),
@@ -97,6 +119,9 @@ ABI = [
     ("rc_mesh_subdivide", _i, [_vp, _i, _pp]),
     ("rc_mesh_aabb", _i, [_vp, _vp]),
     ("rc_mesh_free", None, [_vp]),
+    ("rc_env_read", _i, [C.c_char_p, _vp]),
+    ("rc_query_read", _i, [C.c_char_p, _pp, C.POINTER(_l)]),
+    ("rc_mesh_place", _i, [_vp] + [_f] * 6 + [_pp]),
     ("rc_conf_read", _i, [C.c_char_p, _pp, _pp, C.POINTER(_l)]),
     ("rc_conf_write", _i, [C.c_char_p, _vp, _vp, _l]),
     ("rc_free", None, [_vp]),
@@ -249,6 +274,12 @@ class Mesh:
         _check(_lib.rc_mesh_subdivide(self._h, int(levels), C.byref(h)))
         return Mesh(h)
 
+    def place(self, x=0.0, y=0.0, z=0.0, rx=0.0, ry=0.0, rz=0.0):
+        """The mesh moved to its place in the world (.env placement: translation, degrees about x, y, z)."""
+        h = C.c_void_p()
+        _check(_lib.rc_mesh_place(self._h, float(x), float(y), float(z), float(rx), float(ry), float(rz), C.byref(h)))
+        return Mesh(h)
+
     def save_obj(self, path):
         _check(_lib.rc_mesh_save_obj(self._h, os.fsencode(path)))
 
@@ -266,6 +297,31 @@ def alpha_meshes():
     ROB_FILE / OBS_FILE = models/alpha1.0/{robot,obstacle}.obj, Utils_rai.h:18-19)."""
     return (Mesh.from_byu(os.path.join(ASSET_DIR, "robot.g")),
             Mesh.from_byu(os.path.join(ASSET_DIR, "obstacle.g")))
+
+
+# ---- .env / .query ------------------------------------------------------------------------------
+def readEnvironment(path):
+    """models/alpha1.0/alpha.env -> {"box": (lo, hi) or None, "bodies": [{file, active, color, placement}]}."""
+    e = rc_env()
+    _check(_lib.rc_env_read(os.fsencode(path), C.byref(e)))
+    bodies = []
+    for k in range(e.n_bodies):
+        b = e.bodies[k]
+        bodies.append({"file": b.file.decode(), "active": bool(b.active), "color": tuple(b.color),
+                       "placement": (b.x, b.y, b.z, b.rx, b.ry, b.rz) if b.has_placement else None})
+    box = (tuple(e.box_lo), tuple(e.box_hi)) if e.has_box else None
+    return {"box": box, "bodies": bodies}
+
+
+def readQuery(path):
+    """models/alpha1.0/alpha.query -> configurations float32 [n, 6] (x y z pitch yaw roll): start, goal."""
+    pc, n = C.c_void_p(), C.c_long()
+    _check(_lib.rc_query_read(os.fsencode(path), C.byref(pc), C.byref(n)))
+    try:
+        a = np.ctypeslib.as_array(C.cast(pc, C.POINTER(C.c_float)), shape=(max(n.value, 1) * 6,))
+        return a[: n.value * 6].reshape(n.value, 6).copy()
+    finally:
+        _lib.rc_free(pc)
 
 
 # ---- .conf files and configuration sets ---------------------------------------------------------
@@ -366,6 +422,54 @@ class Context:
         _check(_lib.rc_check_gather(self._h, _ptr(d_confs), int(n), _ptr(d_valid), arr, int(rank), world,
                                     int(words_per_rank), C.byref(res), _stream_ptr(stream)), self._h)
         return (int(res.value) - int(peer_ptrs[rank])) // 4
+
+    def check_gather_begin(self, d_confs, n, d_valid, peer_ptrs, rank, words_per_rank, stream=None):
+        """rc_check_gather_begin: like check_gather without the wait for the peers (pair with gather_end)."""
+        world = len(peer_ptrs)
+        arr = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in peer_ptrs])
+        res = C.c_void_p()
+        _check(_lib.rc_check_gather_begin(self._h, _ptr(d_confs), int(n), _ptr(d_valid), arr, int(rank), world,
+                                          int(words_per_rank), C.byref(res), _stream_ptr(stream)), self._h)
+        return (int(res.value) - int(peer_ptrs[rank])) // 4
+
+    def gather_end(self, peer_ptrs, rank, words_per_rank, stream=None):
+        world = len(peer_ptrs)
+        arr = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in peer_ptrs])
+        _check(_lib.rc_gather_end(self._h, arr, int(rank), world, int(words_per_rank), _stream_ptr(stream)), self._h)
+
+    def gather_status(self, own_ptr, world, words_per_rank):
+        calls, timeouts = C.c_uint32(), C.c_uint32()
+        _check(_lib.rc_gather_status(self._h, C.c_void_p(int(own_ptr)), int(world), int(words_per_rank),
+                                     C.byref(calls), C.byref(timeouts)), self._h)
+        return calls.value, timeouts.value
+
+    # audits ----------------------------------------------------------------------------------------
+    def hit_counts(self, d_confs, n, d_counts, mode=RC_MODE_BRUTE, d_valid=None, stream=None):
+        """rc_hit_counts: hitting pairs per configuration, no early exit (d_counts: n uint32/int32)."""
+        _check(_lib.rc_hit_counts(self._h, _ptr(d_confs), int(n), mode, _ptr(d_valid), _ptr(d_counts),
+                                  _stream_ptr(stream)), self._h)
+
+    def audit(self, d_confs, n, cap=64):
+        """rc_audit: (flags that differ, hit-pair counts that differ, first indices) culled vs brute."""
+        nf, nc = C.c_long(), C.c_long()
+        idx = np.zeros(max(cap, 1), np.uint32)
+        _check(_lib.rc_audit(self._h, _ptr(d_confs), int(n), C.byref(nf), C.byref(nc), _ptr(idx), int(cap)), self._h)
+        return nf.value, nc.value, idx[: min(cap, max(nf.value, nc.value))]
+
+    def kat_pairs(self, rob9, obs9):
+        """rc_kat_pairs: per-pair intermediates of the device helpers -> (float32 [n, 32], int32 [n])."""
+        rob9 = np.ascontiguousarray(rob9, dtype=np.float32).reshape(-1, 9)
+        obs9 = np.ascontiguousarray(obs9, dtype=np.float32).reshape(-1, 9)
+        n = len(rob9)
+        out, verdict = np.zeros((n, 32), np.float32), np.zeros(n, np.int32)
+        _check(_lib.rc_kat_pairs(self._h, _ptr(rob9), _ptr(obs9), n, _ptr(out), _ptr(verdict)), self._h)
+        return out, verdict
+
+    def kat_la_solve(self, in6):
+        in6 = np.ascontiguousarray(in6, dtype=np.float32).reshape(-1, 6)
+        out = np.zeros((len(in6), 2), np.float32)
+        _check(_lib.rc_kat_la_solve(self._h, _ptr(in6), len(in6), _ptr(out)), self._h)
+        return out
 
     def check_host(self, confs, mode=RC_MODE_CULLED):
         confs = np.ascontiguousarray(confs, dtype=np.float32).reshape(-1, 6)

@@ -151,6 +151,36 @@ int upload_obstacle(rc_ctx *ctx, const GatheredTris &g, float4 **a, float4 **b, 
 // context's private stream: work must land on the stream the caller times and orders.
 cudaStream_t stream_of(rc_ctx *, void *stream) { return static_cast<cudaStream_t>(stream); }
 
+// shared argument check of the entry points that launch a check
+int check_args(rc_ctx *ctx, long n, const void *confs, int mode)
+{
+    if (!ctx || n < 0 || (n > 0 && !confs)) return RC_ERR_INVALID;
+    if (mode != RC_MODE_CULLED && mode != RC_MODE_BRUTE)
+        return set_error(ctx, RC_ERR_INVALID, "mode must be RC_MODE_CULLED or RC_MODE_BRUTE");
+    if (n > 0xffffffffL) return set_error(ctx, RC_ERR_INVALID, "more than 2^32 - 1 configurations in one call");
+    return RC_OK;
+}
+
+// The scratch of a context (work lists, their self-resetting counters, the queue word) is shared by
+// every entry point, and entry points enqueue on different streams (the caller's, or the context's
+// own).  Device work of one call must not overlap the next call's on another stream: every launch
+// that touches the scratch records an event behind itself, and a launch on a different stream waits
+// for it first.  Calls on one stream pay one cudaEventRecord (about a microsecond of host time).
+int scratch_acquire(rc_ctx *ctx, cudaStream_t s)
+{
+    if (ctx->scratch_used && ctx->scratch_stream != s) {
+        const cudaError_t e = cudaStreamWaitEvent(s, ctx->ev_scratch, 0);
+        if (e != cudaSuccess) return check_cuda(ctx, e, "scratch hand-over between streams");
+    }
+    return RC_OK;
+}
+void scratch_release(rc_ctx *ctx, cudaStream_t s)
+{
+    cudaEventRecord(ctx->ev_scratch, s);
+    ctx->scratch_stream = s;
+    ctx->scratch_used = true;
+}
+
 int ensure_work_list(rc_ctx *ctx, long n)
 {
     if (n <= ctx->work_cap) return RC_OK;
@@ -306,6 +336,9 @@ int rc_create(rc_ctx **out, const float *rob_x, const float *rob_y, const float 
         ctx->knob_bound = knob("RC_BOUND", 1);
         ctx->knob_mail_slots = knob("RC_MAIL_SLOTS", 4);
         ctx->knob_donate_min = knob("RC_DONATE_MIN", 40);
+        ctx->knob_split_max = knob("RC_SPLIT_MAX", 16);
+        ctx->knob_split_load = knob("RC_SPLIT_LOAD", 8);
+        ctx->knob_host_chunks = knob("RC_HOST_CHUNKS", 0);
     }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
@@ -328,7 +361,8 @@ int rc_create(rc_ctx **out, const float *rob_x, const float *rob_y, const float 
         if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) ||
             (e = cudaStreamCreateWithFlags(&ctx->own_stream2, cudaStreamNonBlocking)) ||
             (e = cudaEventCreate(&ctx->ev0)) || (e = cudaEventCreate(&ctx->ev1)) ||
-            (e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming))) {
+            (e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) ||
+            (e = cudaEventCreateWithFlags(&ctx->ev_scratch, cudaEventDisableTiming))) {
             rcode = check_cuda(ctx, e, "stream/event");
             break;
         }
@@ -375,9 +409,23 @@ int rc_create(rc_ctx **out, const float *rob_x, const float *rob_y, const float 
         std::vector<uint2> rt((size_t)n_rob_t);
         for (int k = 0; k < n_rob_t; k++)
             rt[k] = make_uint2((uint32_t)rob_v1[k] | ((uint32_t)rob_v2[k] << 16), (uint32_t)rob_v3[k]);
-        // BVHs
-        const Bvh rb = build_bvh(rob_x, rob_y, rob_z, rob_v1, rob_v2, rob_v3, n_rob_t, kBoxMargin);
-        const Bvh ob = build_bvh(obs_x, obs_y, obs_z, obs_v1, obs_v2, obs_v3, n_obs_t, kBoxMargin);
+        // BVHs.  Every tree box is inflated by box_margin; a pair of boxes is culled only when it is
+        // separated on an axis after that inflation, so the margin has to stay well above the rounding
+        // of the box test itself, which grows with the size of the coordinates: about 5e-7 x |coordinate|
+        // (four FMAs on values of that size, boxes stored in float).  Near-contact configurations -- the
+        // only ones whose pairs are ever looked at -- keep the robot within its own diameter of the
+        // obstacle, hence the scene extent below.  kBoxMargin (1e-3) holds up to extents of 250 units
+        // (alpha1.0: about 130); larger scenes get a proportionally larger margin.
+        {
+            double ext = 0;
+            for (int v = 0; v < n_obs_v; v++)
+                ext = std::max(ext, (double)std::max(std::fabs(obs_x[v]), std::max(std::fabs(obs_y[v]), std::fabs(obs_z[v]))));
+            ext += 2.0 * (double)t.rob_radius;
+            for (int k = 0; k < 3; k++) ext = std::max(ext, (double)std::fabs(t.rob_center[k]) + t.rob_radius);
+            t.box_margin = std::max(kBoxMargin, (float)(4e-6 * ext));
+        }
+        const Bvh rb = build_bvh(rob_x, rob_y, rob_z, rob_v1, rob_v2, rob_v3, n_rob_t, t.box_margin);
+        const Bvh ob = build_bvh(obs_x, obs_y, obs_z, obs_v1, obs_v2, obs_v3, n_obs_t, t.box_margin);
         t.n_rob_nodes = rb.n_nodes; t.n_obs_nodes = ob.n_nodes;
         for (int d = 0; d < 4; d++) {
             const std::vector<int> cr = rb.cut(d), co = ob.cut(d);
@@ -424,9 +472,7 @@ int rc_create(rc_ctx **out, const float *rob_x, const float *rob_y, const float 
             break;
     } while (0);
 
-    if (rcode != RC_OK) {
-        // keep the message readable through rc_strerror; the context itself is discarded
-        fprintf(stderr, "rc_create: %s\n", ctx->last_error.c_str());
+    if (rcode != RC_OK) {  // the context is discarded; the code says what failed (never prints)
         rc_destroy(ctx);
         return rcode;
     }
@@ -461,6 +507,7 @@ void rc_destroy(rc_ctx *ctx)
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     free_lane(ctx->pipe[0]); free_lane(ctx->pipe[1]);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->ev_scratch) cudaEventDestroy(ctx->ev_scratch);
     if (ctx->own_stream2) cudaStreamDestroy(ctx->own_stream2);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -483,35 +530,46 @@ int rc_obstacle_aabb(const rc_ctx *ctx, rc_aabb *out)
     return RC_OK;
 }
 
-int rc_check(rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_valid, uint32_t *d_bitmask,
-             int mode, void *stream)
+static int check_on_stream(rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_valid, uint32_t *d_bitmask,
+                           int mode, cudaStream_t s, const rc::CheckExtras *extras, const char *what)
 {
-    if (!ctx || n < 0 || (n > 0 && !d_confs) || (!d_valid && !d_bitmask)) return RC_ERR_INVALID;
-    if (mode != RC_MODE_CULLED && mode != RC_MODE_BRUTE) return RC_ERR_INVALID;
-    if (n == 0) return RC_OK;
-    if (n > 0xffffffffL) return RC_ERR_INVALID;
-    cudaSetDevice(ctx->device);
     if (mode == RC_MODE_CULLED) {
         const int rcode = ensure_work_list(ctx, n);
         if (rcode != RC_OK) return rcode;
     }
-    cudaError_t e = launch_check(ctx, d_confs, n, d_valid, d_bitmask, mode, ctx->stats_on,
-                                 stream_of(ctx, stream), nullptr);
+    int rcode = scratch_acquire(ctx, s);
+    if (rcode != RC_OK) return rcode;
+    const int stats = ctx->stats_on || (extras && extras->hit_counts);
+    cudaError_t e = launch_check(ctx, d_confs, n, d_valid, d_bitmask, mode, stats, s, nullptr, extras);
+    scratch_release(ctx, s);
     if (e == cudaErrorInvalidConfiguration)
         return set_error(ctx, RC_ERR_UNSUPPORTED, "mesh tables do not fit in shared memory");
-    ctx->launches += mode == RC_MODE_CULLED ? 2 : 1;
-    return check_cuda(ctx, e, "rc_check launch");
+    if (e == cudaSuccess) ctx->launches += mode == RC_MODE_CULLED ? 2 : 1;
+    return check_cuda(ctx, e, what);
+}
+
+int rc_check(rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_valid, uint32_t *d_bitmask,
+             int mode, void *stream)
+{
+    const int rcode = check_args(ctx, n, d_confs, mode);
+    if (rcode != RC_OK) return rcode;
+    if (!d_valid && !d_bitmask) return RC_ERR_INVALID;
+    if (n == 0) return RC_OK;
+    cudaSetDevice(ctx->device);
+    return check_on_stream(ctx, d_confs, n, d_valid, d_bitmask, mode, stream_of(ctx, stream), nullptr,
+                           "rc_check launch");
 }
 
 long rc_gather_buffer_words(int world, long words_per_rank)
 {
     if (world <= 0 || world > rc::kMaxGatherRanks || words_per_rank <= 0) return RC_ERR_INVALID;
-    return 2L * world * words_per_rank + world;
+    return 2L * world * words_per_rank + world + rc::kGatherHeaderWords;
 }
 
-int rc_check_gather(rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_valid,
-                    void *const *peer_buffers, int rank, int world, long words_per_rank,
-                    uint32_t **d_result, void *stream)
+// wait = 1: one-call form (the last CTA of the descent also waits for the peers); 0: push only
+static int check_gather(rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_valid,
+                        void *const *peer_buffers, int rank, int world, long words_per_rank,
+                        uint32_t **d_result, void *stream, int wait)
 {
     if (!ctx || n < 0 || (n > 0 && !d_confs) || !peer_buffers || world <= 0 ||
         world > rc::kMaxGatherRanks || rank < 0 || rank >= world || words_per_rank <= 0 ||
@@ -521,21 +579,24 @@ int rc_check_gather(rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_va
         if (!peer_buffers[r]) return RC_ERR_INVALID;
     cudaSetDevice(ctx->device);
     cudaStream_t s = stream_of(ctx, stream);
-    const uint32_t call = ++ctx->gather_calls;
-    const long area = (long)(call & 1u) * world * words_per_rank;  // the two gather areas alternate
     uint32_t *mine = static_cast<uint32_t *>(peer_buffers[rank]);
-    uint32_t *slot = mine + area + (long)rank * words_per_rank;
-    if (d_result) *d_result = mine + area;
-    const long used = (n + 31) / 32;
+    uint32_t *row = mine + 2L * world * words_per_rank;
     cudaError_t e;
-    // words of the slot past the last configuration (short or empty last shards) are defined as 0
-    if (used < words_per_rank &&
-        (e = cudaMemsetAsync(slot + used, 0, (size_t)(words_per_rank - used) * 4, s)) != cudaSuccess)
-        return check_cuda(ctx, e, "rc_check_gather memset");
-    if (n > 0) {
-        const int rcode = rc_check(ctx, d_confs, n, d_valid, slot, RC_MODE_CULLED, stream);
-        if (rcode != RC_OK) return rcode;
+    // The call numbering lives in the buffer (header word [0], written by every push): a context
+    // that sees this buffer for the first time picks it up from there, so a fresh context on a used
+    // buffer continues the sequence of its peers instead of restarting at 1 (which would make every
+    // wait pass at once on stale signals).
+    if (ctx->gather_buf != mine) {
+        uint32_t calls = 0;
+        if ((e = cudaStreamSynchronize(s)) ||
+            (e = cudaMemcpy(&calls, row + world, sizeof calls, cudaMemcpyDeviceToHost)))
+            return check_cuda(ctx, e, "rc_check_gather: reading the call number of the buffer");
+        ctx->gather_buf = mine;
+        ctx->gather_calls = calls;
     }
+    const uint32_t call = ctx->gather_calls + 1;  // committed only when every launch below went through
+    const long area = (long)(call & 1u) * world * words_per_rank;  // the two gather areas alternate
+    uint32_t *slot = mine + area + (long)rank * words_per_rank;
     rc::GatherArgs a{};
     a.src = slot;
     for (int r = 0; r < world; r++) {
@@ -543,21 +604,85 @@ int rc_check_gather(rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_va
         a.peer_slot[r] = base + area + (long)rank * words_per_rank;
         a.peer_signal[r] = base + 2L * world * words_per_rank + rank;
     }
-    a.my_signal = mine + 2L * world * words_per_rank;
-    a.rank = rank; a.world = world; a.words = (int)words_per_rank; a.call = call;
+    a.my_row = row;
+    a.rank = rank; a.world = world; a.words = (int)words_per_rank; a.call = call; a.wait = wait;
     a.counters = ctx->d_counters;
     a.timeout_ns = 4000000000ULL;
-    e = rc::launch_gather_push(ctx, a, s);
+    const long used = (n + 31) / 32;
+    // words of the slot past the last configuration (short or empty last shards) are defined as 0
+    if (used < words_per_rank &&
+        (e = cudaMemsetAsync(slot + used, 0, (size_t)(words_per_rank - used) * 4, s)) != cudaSuccess)
+        return check_cuda(ctx, e, "rc_check_gather memset");
+    if (n > 0) {
+        // the bitmask goes straight into the rank's slot; the last CTA of the descent kernel pushes it
+        rc::CheckExtras x;
+        x.gather = &a;
+        const int rcode = check_on_stream(ctx, d_confs, n, d_valid, slot, RC_MODE_CULLED, s, &x,
+                                          "rc_check_gather launch");
+        if (rcode != RC_OK) return rcode;
+    } else if (world > 1) {
+        if ((e = rc::launch_gather_push(ctx, a, s)) != cudaSuccess) return check_cuda(ctx, e, "rc_check_gather push");
+        ctx->launches += 1;
+    }
+    ctx->gather_calls = call;
+    if (d_result) *d_result = mine + area;
+    return RC_OK;
+}
+
+int rc_check_gather(rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_valid,
+                    void *const *peer_buffers, int rank, int world, long words_per_rank,
+                    uint32_t **d_result, void *stream)
+{
+    return check_gather(ctx, d_confs, n, d_valid, peer_buffers, rank, world, words_per_rank, d_result, stream, 1);
+}
+
+int rc_check_gather_begin(rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_valid,
+                          void *const *peer_buffers, int rank, int world, long words_per_rank,
+                          uint32_t **d_result, void *stream)
+{
+    return check_gather(ctx, d_confs, n, d_valid, peer_buffers, rank, world, words_per_rank, d_result, stream, 0);
+}
+
+int rc_gather_end(rc_ctx *ctx, void *const *peer_buffers, int rank, int world, long words_per_rank, void *stream)
+{
+    if (!ctx || !peer_buffers || world <= 0 || world > rc::kMaxGatherRanks || rank < 0 || rank >= world ||
+        words_per_rank <= 0 || !peer_buffers[rank])
+        return RC_ERR_INVALID;
+    uint32_t *mine = static_cast<uint32_t *>(peer_buffers[rank]);
+    if (ctx->gather_buf != mine || ctx->gather_calls == 0)
+        return set_error(ctx, RC_ERR_INVALID, "rc_gather_end without rc_check_gather_begin on this buffer");
+    cudaSetDevice(ctx->device);
+    rc::GatherArgs a{};
+    a.my_row = mine + 2L * world * words_per_rank;
+    a.rank = rank; a.world = world; a.words = (int)words_per_rank; a.call = ctx->gather_calls; a.wait = 1;
+    a.counters = ctx->d_counters;
+    a.timeout_ns = 4000000000ULL;
     if (world > 1) ctx->launches += 1;
-    return check_cuda(ctx, e, "rc_check_gather push");
+    return check_cuda(ctx, rc::launch_gather_wait(ctx, a, stream_of(ctx, stream)), "rc_gather_end");
+}
+
+int rc_gather_status(rc_ctx *ctx, const void *own_buffer, int world, long words_per_rank, uint32_t *calls,
+                     uint32_t *timeouts)
+{
+    if (!ctx || !own_buffer || world <= 0 || world > rc::kMaxGatherRanks || words_per_rank <= 0) return RC_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    uint32_t h[2] = {0, 0};
+    const uint32_t *row = static_cast<const uint32_t *>(own_buffer) + 2L * world * words_per_rank + world;
+    const cudaError_t e = cudaMemcpy(h, row, sizeof h, cudaMemcpyDeviceToHost);  // synchronises with the device
+    if (e != cudaSuccess) return check_cuda(ctx, e, "rc_gather_status");
+    if (calls) *calls = h[0];
+    if (timeouts) *timeouts = h[1];
+    return RC_OK;
 }
 
 int rc_check_host(rc_ctx *ctx, const rc_config *h_confs, long n, uint8_t *h_valid, int mode)
 {
-    if (!ctx || n < 0 || (n > 0 && (!h_confs || !h_valid))) return RC_ERR_INVALID;
+    int rcode = check_args(ctx, n, h_confs, mode);
+    if (rcode != RC_OK) return rcode;
+    if (n > 0 && !h_valid) return RC_ERR_INVALID;
     if (n == 0) return RC_OK;
     cudaSetDevice(ctx->device);
-    int rcode = ensure_staging(ctx, n);
+    rcode = ensure_staging(ctx, n);
     if (rcode != RC_OK) return rcode;
     cudaStream_t s = ctx->own_stream;
     cudaError_t e;
@@ -593,13 +718,9 @@ int rc_check_host(rc_ctx *ctx, const rc_config *h_confs, long n, uint8_t *h_vali
                              cudaMemcpyHostToDevice, s)))
         return check_cuda(ctx, e, "H2D configurations");
     cudaEventRecord(ctx->ev0, s);
-    if (mode == RC_MODE_CULLED && (rcode = ensure_work_list(ctx, n)) != RC_OK) return rcode;
-    e = launch_check(ctx, ctx->d_stage_confs, n, d_out, nullptr, mode, ctx->stats_on, s,
-                     ctx->d_queues);
-    if (e == cudaErrorInvalidConfiguration)
-        return set_error(ctx, RC_ERR_UNSUPPORTED, "mesh tables do not fit in shared memory");
-    if (e) return check_cuda(ctx, e, "rc_check_host launch");
-    ctx->launches += mode == RC_MODE_CULLED ? 2 : 1;
+    if ((rcode = check_on_stream(ctx, ctx->d_stage_confs, n, d_out, nullptr, mode, s, nullptr,
+                                 "rc_check_host launch")) != RC_OK)
+        return rcode;
     cudaEventRecord(ctx->ev1, s);
     if ((!direct && (e = cudaMemcpyAsync(dst, ctx->d_stage_valid, (size_t)n, cudaMemcpyDeviceToHost, s))) ||
         (e = cudaStreamSynchronize(s)))
@@ -611,14 +732,13 @@ int rc_check_host(rc_ctx *ctx, const rc_config *h_confs, long n, uint8_t *h_vali
 
 int rc_check_host_submit(rc_ctx *ctx, const rc_config *h_confs, long n, uint8_t *h_valid, int mode, int *ticket)
 {
-    if (!ctx || !ticket || n <= 0 || !h_confs || !h_valid) return RC_ERR_INVALID;
-    if (mode != RC_MODE_CULLED && mode != RC_MODE_BRUTE) return RC_ERR_INVALID;
-    if (n > 0xffffffffL) return RC_ERR_INVALID;
+    int rcode = check_args(ctx, n, h_confs, mode);
+    if (rcode != RC_OK) return rcode;
+    if (!ticket || n <= 0 || !h_valid) return RC_ERR_INVALID;
     cudaSetDevice(ctx->device);
     PipeLane &l = ctx->pipe[ctx->pipe_next & 1];
-    int rcode = finish_lane(ctx, l);  // the batch submitted two calls ago, if nobody has waited for it yet
+    rcode = finish_lane(ctx, l);  // the batch submitted two calls ago, if nobody has waited for it yet
     if (rcode != RC_OK || (rcode = ensure_lane(ctx, l, n)) != RC_OK) return rcode;
-    if (mode == RC_MODE_CULLED && (rcode = ensure_work_list(ctx, n)) != RC_OK) return rcode;
     cudaStream_t copy = ctx->own_stream2, compute = ctx->own_stream;
     cudaPointerAttributes pa_in{}, pa_out{};
     const bool in_pinned = cudaPointerGetAttributes(&pa_in, h_confs) == cudaSuccess && pa_in.type == cudaMemoryTypeHost;
@@ -639,12 +759,9 @@ int rc_check_host_submit(rc_ctx *ctx, const rc_config *h_confs, long n, uint8_t 
     if ((e = cudaMemcpyAsync(l.d_confs, src, (size_t)n * sizeof(rc_config), cudaMemcpyHostToDevice, copy)) ||
         (e = cudaEventRecord(l.copied, copy)) || (e = cudaStreamWaitEvent(compute, l.copied, 0)))
         return check_cuda(ctx, e, "rc_check_host_submit copy");
-    e = launch_check(ctx, l.d_confs, n, direct ? static_cast<uint8_t *>(mapped) : l.d_valid, nullptr, mode,
-                     ctx->stats_on, compute, ctx->d_queues);
-    if (e == cudaErrorInvalidConfiguration)
-        return set_error(ctx, RC_ERR_UNSUPPORTED, "mesh tables do not fit in shared memory");
-    if (e) return check_cuda(ctx, e, "rc_check_host_submit launch");
-    ctx->launches += mode == RC_MODE_CULLED ? 2 : 1;
+    if ((rcode = check_on_stream(ctx, l.d_confs, n, direct ? static_cast<uint8_t *>(mapped) : l.d_valid, nullptr,
+                                 mode, compute, nullptr, "rc_check_host_submit launch")) != RC_OK)
+        return rcode;
     if ((!direct && (e = cudaMemcpyAsync(dst, l.d_valid, (size_t)n, cudaMemcpyDeviceToHost, compute))) ||
         (e = cudaEventRecord(l.done, compute)))
         return check_cuda(ctx, e, "rc_check_host_submit");
@@ -693,6 +810,7 @@ int rc_check_multi(rc_ctx **ctxs, int n_gpus, const rc_config *h_confs, long n, 
         if (d_bitmask_all && !d_bitmask_all[g]) return RC_ERR_INVALID;
     }
     if (n == 0) return RC_OK;
+    if (n > 0xffffffffL) return RC_ERR_INVALID;
     const long per = rc_shard_size(n, n_gpus);
     if (per <= 0) return RC_ERR_INVALID;
     cudaPointerAttributes pa{};
@@ -716,7 +834,6 @@ int rc_check_multi(rc_ctx **ctxs, int n_gpus, const rc_config *h_confs, long n, 
         if (cnt <= 0) continue;
         cudaSetDevice(ctx->device);
         int rcode = ensure_staging(ctx, cnt);
-        if (rcode == RC_OK) rcode = ensure_work_list(ctx, cnt);
         if (rcode != RC_OK) return rcode;
         cudaStream_t s = ctx->own_stream;
         const rc_config *src = h_confs + lo;
@@ -729,12 +846,9 @@ int rc_check_multi(rc_ctx **ctxs, int n_gpus, const rc_config *h_confs, long n, 
         if (e) return check_cuda(ctx, e, "rc_check_multi H2D");
         // with a gather buffer on this device the kernel writes its words straight into its slot
         uint32_t *mask = d_bitmask_all ? d_bitmask_all[g] + lo / 32 : ctx->d_stage_mask;
-        e = launch_check(ctx, ctx->d_stage_confs, cnt, h_valid ? ctx->d_stage_valid : nullptr, mask,
-                         RC_MODE_CULLED, ctx->stats_on, s, ctx->d_queues);
-        if (e == cudaErrorInvalidConfiguration)
-            return set_error(ctx, RC_ERR_UNSUPPORTED, "mesh tables do not fit in shared memory");
-        if (e) return check_cuda(ctx, e, "rc_check_multi launch");
-        ctx->launches += 2;
+        if ((rcode = check_on_stream(ctx, ctx->d_stage_confs, cnt, h_valid ? ctx->d_stage_valid : nullptr, mask,
+                                     RC_MODE_CULLED, s, nullptr, "rc_check_multi launch")) != RC_OK)
+            return rcode;
         const size_t words = (size_t)(cnt + 31) / 32;
         if (h_bitmask && (e = cudaMemcpyAsync(ctx->h_pinned_mask, mask, words * 4, cudaMemcpyDeviceToHost, s)))
             return check_cuda(ctx, e, "rc_check_multi D2H bitmask");
@@ -1015,6 +1129,13 @@ int rc_set_robot_spheres(rc_ctx *ctx, const float *xyzr, int n)
     }
     cudaError_t e;
     cudaDeviceSynchronize();  // an earlier asynchronous check may still read the old tables
+    for (void *old : {static_cast<void *>(t.sph), static_cast<void *>(t.sph_bvh)}) {  // replaced, not leaked
+        if (!old) continue;
+        auto it = std::find(ctx->allocations.begin(), ctx->allocations.end(), old);
+        if (it != ctx->allocations.end()) ctx->allocations.erase(it);
+        cudaFree(old);
+    }
+    t.sph = nullptr; t.sph_bvh = nullptr; t.n_sph = 0; t.n_sph_nodes = 0;
     if ((e = upload(ctx, &t.sph, sorted)) || (e = upload(ctx, &t.sph_bvh, nodes)))
         return check_cuda(ctx, e, "sphere tables");
     t.n_sph = n;
@@ -1046,12 +1167,124 @@ int rc_check_spheres(rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_v
         const int rcode = ensure_work_list(ctx, n);
         if (rcode != RC_OK) return rcode;
     }
+    {
+        const int rcode = scratch_acquire(ctx, stream_of(ctx, stream));
+        if (rcode != RC_OK) return rcode;
+    }
     cudaError_t e = launch_check_spheres(ctx, d_confs, n, d_valid, d_bitmask, ctx->stats_on,
                                          stream_of(ctx, stream), nullptr);
+    scratch_release(ctx, stream_of(ctx, stream));
     if (e == cudaErrorInvalidConfiguration)
         return set_error(ctx, RC_ERR_UNSUPPORTED, "sphere / obstacle tables do not fit");
     ctx->launches += 2;  // classify + sphere descent
     return check_cuda(ctx, e, "rc_check_spheres launch");
+}
+
+// ---- audits ------------------------------------------------------------------------------------
+
+int rc_hit_counts(rc_ctx *ctx, const rc_config *d_confs, long n, int mode, uint8_t *d_valid,
+                  uint32_t *d_counts, void *stream)
+{
+    const int rcode = check_args(ctx, n, d_confs, mode);
+    if (rcode != RC_OK) return rcode;
+    if (n > 0 && !d_counts) return RC_ERR_INVALID;
+    if (n == 0) return RC_OK;
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = stream_of(ctx, stream);
+    uint8_t *flags = d_valid;
+    if (!flags) {  // the kernels need one of the two outputs: a scratch flag array of the context
+        const int r2 = ensure_staging(ctx, n);
+        if (r2 != RC_OK) return r2;
+        flags = ctx->d_stage_valid;
+    }
+    rc::CheckExtras x;
+    x.hit_counts = d_counts;
+    return check_on_stream(ctx, d_confs, n, flags, nullptr, mode, s, &x, "rc_hit_counts launch");
+}
+
+int rc_audit(rc_ctx *ctx, const rc_config *d_confs, long n, long *n_flags_differ, long *n_counts_differ,
+             uint32_t *h_indices, long cap)
+{
+    if (!ctx || n < 0 || (n > 0 && !d_confs) || cap < 0 || (cap > 0 && !h_indices)) return RC_ERR_INVALID;
+    if (n_flags_differ) *n_flags_differ = 0;
+    if (n_counts_differ) *n_counts_differ = 0;
+    if (n == 0) return RC_OK;
+    if (n > 0xffffffffL) return RC_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    uint8_t *d_flags = nullptr;
+    uint32_t *d_cnt = nullptr;
+    std::vector<uint8_t> f[2];
+    std::vector<uint32_t> k[2];
+    cudaError_t e = cudaSuccess;
+    int rcode = RC_OK;
+    if ((e = cudaMalloc(&d_flags, (size_t)n)) || (e = cudaMalloc(&d_cnt, (size_t)n * 4)))
+        rcode = check_cuda(ctx, e, "rc_audit buffers");
+    for (int mode = 0; mode < 2 && rcode == RC_OK; mode++) {
+        f[mode].resize((size_t)n);
+        k[mode].resize((size_t)n);
+        rcode = rc_hit_counts(ctx, d_confs, n, mode == 0 ? RC_MODE_CULLED : RC_MODE_BRUTE, d_flags, d_cnt,
+                              ctx->own_stream);
+        if (rcode == RC_OK &&
+            ((e = cudaMemcpyAsync(f[mode].data(), d_flags, (size_t)n, cudaMemcpyDeviceToHost, ctx->own_stream)) ||
+             (e = cudaMemcpyAsync(k[mode].data(), d_cnt, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->own_stream)) ||
+             (e = cudaStreamSynchronize(ctx->own_stream))))
+            rcode = check_cuda(ctx, e, "rc_audit copies");
+    }
+    cudaFree(d_flags);
+    cudaFree(d_cnt);
+    if (rcode != RC_OK) return rcode;
+    long nf = 0, nc = 0, listed = 0;
+    for (long i = 0; i < n; i++) {
+        const bool df = f[0][i] != f[1][i], dc = k[0][i] != k[1][i];
+        nf += df;
+        nc += dc;
+        if ((df || dc) && listed < cap) h_indices[listed++] = (uint32_t)i;
+    }
+    if (n_flags_differ) *n_flags_differ = nf;
+    if (n_counts_differ) *n_counts_differ = nc;
+    return RC_OK;
+}
+
+int rc_kat_pairs(rc_ctx *ctx, const float *h_rob9, const float *h_obs9, int n, float *h_out32, int *h_verdict)
+{
+    if (!ctx || n < 0 || (n > 0 && (!h_rob9 || !h_obs9 || !h_out32 || !h_verdict))) return RC_ERR_INVALID;
+    if (n == 0) return RC_OK;
+    cudaSetDevice(ctx->device);
+    float *d_r = nullptr, *d_o = nullptr, *d_out = nullptr;
+    int *d_v = nullptr;
+    cudaError_t e;
+    int rcode = RC_OK;
+    if ((e = cudaMalloc(&d_r, (size_t)n * 36)) || (e = cudaMalloc(&d_o, (size_t)n * 36)) ||
+        (e = cudaMalloc(&d_out, (size_t)n * 128)) || (e = cudaMalloc(&d_v, (size_t)n * 4)) ||
+        (e = cudaMemcpy(d_r, h_rob9, (size_t)n * 36, cudaMemcpyHostToDevice)) ||
+        (e = cudaMemcpy(d_o, h_obs9, (size_t)n * 36, cudaMemcpyHostToDevice)) ||
+        (e = rc::launch_kat_pairs(d_r, d_o, n, d_out, d_v, ctx->own_stream)) ||
+        (e = cudaStreamSynchronize(ctx->own_stream)) ||
+        (e = cudaMemcpy(h_out32, d_out, (size_t)n * 128, cudaMemcpyDeviceToHost)) ||
+        (e = cudaMemcpy(h_verdict, d_v, (size_t)n * 4, cudaMemcpyDeviceToHost)))
+        rcode = check_cuda(ctx, e, "rc_kat_pairs");
+    ctx->launches++;
+    cudaFree(d_r); cudaFree(d_o); cudaFree(d_out); cudaFree(d_v);
+    return rcode;
+}
+
+int rc_kat_la_solve(rc_ctx *ctx, const float *h_in6, int n, float *h_out2)
+{
+    if (!ctx || n < 0 || (n > 0 && (!h_in6 || !h_out2))) return RC_ERR_INVALID;
+    if (n == 0) return RC_OK;
+    cudaSetDevice(ctx->device);
+    float *d_in = nullptr, *d_out = nullptr;
+    cudaError_t e;
+    int rcode = RC_OK;
+    if ((e = cudaMalloc(&d_in, (size_t)n * 24)) || (e = cudaMalloc(&d_out, (size_t)n * 8)) ||
+        (e = cudaMemcpy(d_in, h_in6, (size_t)n * 24, cudaMemcpyHostToDevice)) ||
+        (e = rc::launch_kat_la_solve(d_in, n, d_out, ctx->own_stream)) ||
+        (e = cudaStreamSynchronize(ctx->own_stream)) ||
+        (e = cudaMemcpy(h_out2, d_out, (size_t)n * 8, cudaMemcpyDeviceToHost)))
+        rcode = check_cuda(ctx, e, "rc_kat_la_solve");
+    ctx->launches++;
+    cudaFree(d_in); cudaFree(d_out);
+    return rcode;
 }
 
 // ---- coplanar pairs ------------------------------------------------------------

@@ -35,14 +35,14 @@ __host__ __device__ constexpr int stack_cap_of(int warps, bool gobs)
 {
     return gobs ? (warps > 24 ? 1024 : kStackCapGlobal) : (warps > 28 ? 512 : warps > 24 ? 768 : kStackCap);
 }
-constexpr float kTriMargin = 2e-3f;  // triangle-box clearance, same as the two inflated tree boxes
 constexpr int kLeafTrisDev = 4;  // must match rc::kLeafTris of the host builder (rc_bvh.h)
 constexpr int kClassifyBoxes = 32;  // vertex groups of the robot bounded in classify_kernel
 constexpr int kMailSlots = 16;   // per CTA (capacity; a.mail_slots are used): pieces of a deep descent handed to warps without work
 constexpr int kDonateMin = 64;   // node pairs on a warp's stack before it hands 32 of them out
 constexpr uint32_t kPendHit = 0x80000000u;
-constexpr uint32_t kWatchdogSpins = 1u << 22;  // x 256 ns: about a second
-constexpr uint32_t kAbortTicks = 8192;          // x 2^20 SM cycles: about four seconds after the CTA started
+constexpr uint32_t kWatchdogSpins = 1u << 24;  // polls of 256 ns each that a warp without work EXECUTES (time the
+                                                // context spends switched out does not count): several seconds
+constexpr int kSplitMax = 16;    // parts one configuration may be cut into when the list is short (rc_culled.cuh: split)
 
 struct __align__(16) Mail {
     float4 m[3];         // [R | t] of the configuration
@@ -76,6 +76,17 @@ struct CulledArgs {
     long work_cap;
     uint32_t *trace;                 // rc_stats_trace, STATS kernels only
     unsigned long long *work_count;  // [0..7] entries per cost class  [8] next entry  [9] CTAs finished (self-resetting)
+    // Short lists (planner-sized batches): a configuration is cut into up to split_max PARTS, each a
+    // subset of the seed pairs of the deeper cut below, each an entry of its own for the warps of the
+    // whole grid.  Parts never meet again, which is why the flags are written optimistically:
+    // classify_kernel has marked every listed configuration valid, a part that finds a hit writes
+    // "invalid" (optimistic != 0; the statistics kernels keep the one-warp-one-flag protocol).
+    int optimistic, split_max, split_load;
+    float tri_margin;                // triangle-box clearance of step C = the two inflated tree boxes
+    uint32_t seed_r3[8], seed_o3[8];
+    int n_seed_r3, n_seed_o3;
+    uint32_t *hit_counts;            // STATS kernels: hitting pairs per configuration, no early exit (rc_hit_counts)
+    GatherArgs g;                    // g.world > 1: the last CTA pushes the bitmask slot to the peers (rc_gather.cuh)
 };
 
 __device__ __forceinline__ bool boxes_overlap(const Mat34 &m, const float4 r0, const float4 r1,
@@ -183,6 +194,7 @@ struct ClassifyArgs {
     long work_cap;
     unsigned long long *work_count;
     unsigned long long *counters;
+    int optimistic;        // listed configurations are marked valid here; the descent only ever writes "invalid"
 };
 
 template <bool STATS>
@@ -258,9 +270,11 @@ __global__ void __launch_bounds__(64) classify_kernel(const __grid_constant__ Cl
         clear = clear && in;
         const bool work = in && !clear;
         const unsigned mc = __ballot_sync(kFull, clear), mw = __ballot_sync(kFull, work);
-        if (clear && a.valid) a.valid[i] = 1;
-        // the warp covers exactly one bitmask word: write it (the second kernel ORs its bits in)
-        if (lane == 0 && a.bitmask) a.bitmask[i >> 5] = mc;
+        const bool one = clear || (work && a.optimistic);
+        if (one && a.valid) a.valid[i] = 1;
+        // the warp covers exactly one bitmask word: write it (the second kernel ORs its bits in, or,
+        // in optimistic mode, clears the bits of the colliding configurations)
+        if (lane == 0 && a.bitmask) a.bitmask[i >> 5] = a.optimistic ? (mc | mw) : mc;
         if (mw) {
             // cost class from the share of the robot inside the obstacle AABB (edges ~ 1/64, 3/64, 7/64,
             // 13/64, 21/64, 31/64, 43/64 of the groups), one list per class, warp-aggregated append
@@ -286,8 +300,16 @@ __global__ void __launch_bounds__(64) classify_kernel(const __grid_constant__ Cl
 // GOBS = obstacle tables (BVH + triangles) stay in global memory (L2-resident) instead of being
 // staged into shared memory: meshes of any size (BASELINE config 5, the subdivided obstacle).
 // Pair encodings then use 11 bits for the robot side and 21 bits for the obstacle side.
+__device__ __forceinline__ void publish_invalid(const CheckArgs &a, long i, int lane)
+{
+    if (lane == 0) {
+        if (a.valid) a.valid[i] = 0;
+        if (a.bitmask) atomicAnd(a.bitmask + (i >> 5), ~(1u << (i & 31)));
+    }
+}
+
 template <bool STATS, int WARPS, bool GOBS, bool COP>
-__global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const CulledArgs a)
+__global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __grid_constant__ CulledArgs a)
 {
     constexpr int SH = GOBS ? 21 : 16;
     constexpr uint32_t LOW = (1u << SH) - 1u;
@@ -308,8 +330,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
     Mail *s_mail = reinterpret_cast<Mail *>(s_work + WARPS * kWarpWork);
     uint32_t *s_pend = reinterpret_cast<uint32_t *>(s_mail + kMailSlots);
     uint32_t *s_idle = s_pend + WARPS;
-    uint32_t *s_t0 = s_idle + 1;  // kernel start, SM clock >> 20 (the hand-over code never waits longer than kAbortTicks)
-    uint32_t *s_bin = s_t0 + 1;   // [kWorkBins + 1] first list position of each cost class, dearest class first
+    uint32_t *s_misc = s_idle + 1;   // [0] split shift  [1] this CTA finished last  [2] spare
+    uint32_t *s_bin = s_misc + 3;    // [kWorkBins + 1] first list position of each cost class, dearest class first
+    uint32_t *s_wait = s_bin + kWorkBins + 1;  // [2 * WARPS] configuration a warp has finished but for its pieces: index, hit
     // obstacle accessors: shared memory, or the read-only global path
     auto obs_node = [&](int nb, int half) -> float4 {
         if constexpr (GOBS) return __ldg(a.obs_bvh + 2 * nb + half);
@@ -326,7 +349,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
     }
     if (threadIdx.x < kMailSlots) s_mail[threadIdx.x].state = 0u;
     if (threadIdx.x <= WARPS) s_pend[threadIdx.x] = 0u;  // the last one is s_idle
-    if (threadIdx.x == 0) *s_t0 = (uint32_t)(clock64() >> 20);
     __syncthreads();
     if (threadIdx.x == 0) {
         const uint32_t bv = c.n_rob_v_pad * 16u, bo = c.n_obs_t * 16u,
@@ -355,6 +377,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
             acc += (uint32_t)__ldcg(a.work_count + (kWorkBins - 1 - o));
         }
         s_bin[kWorkBins] = acc;
+        // split: as many parts per configuration (a power of two) as keep the entries at or below
+        // split_load per warp of the grid -- 1 for the large sets the kernel is tuned for
+        uint32_t gs = 0;
+        if (!STATS && a.optimistic)
+            while ((2u << gs) <= (uint32_t)a.split_max &&
+                   ((unsigned long long)acc << (gs + 1)) <= (unsigned long long)a.split_load * gridDim.x * WARPS)
+                gs++;
+        s_misc[0] = gs;
     }
     __syncthreads();
     mbar_wait(bar, 0);
@@ -366,21 +396,26 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
     uint32_t *tailq = leafq + kLeafQCap;
     unsigned long long st_broad = 0, st_valid = 0, st_invalid = 0, st_nodes = 0,
                        st_leaves = 0, st_tris = 0, st_over = 0, st_tails = 0, st_nr = 0, st_lr = 0, st_tr = 0, st_shared = 0;
+    const bool counting = STATS && a.hit_counts != nullptr;  // audit: every hitting pair, no early exit
 
     // Guided self-scheduling over the work list: chunks while plenty of work is left, single
-    // configurations near the end so that no warp is left holding a long chunk.  The cost of one
+    // entries near the end so that no warp is left holding a long chunk.  The cost of one
     // configuration is heavy-tailed (median 9 k cycles, 1 % above 120 k, maximum 280 k = 40 % of
     // the whole kernel), so once the list is dry the warps of a CTA SHARE what is left: a warp whose
     // pair stack is deep hands its 32 oldest entries (the largest subtrees) to a mail slot in shared
     // memory, warps without work of their own pick slots up and run the same descent on them.
-    // A configuration collides iff any of its pieces finds a hit; the owner waits for its pieces
-    // (s_pend: piece count + hit bit) and publishes the flag.
-    const uint32_t n_work = s_bin[kWorkBins];
+    // A configuration collides iff any of its pieces finds a hit; the owner collects the verdict of
+    // its pieces (s_pend: piece count + hit bit) and publishes the flag.  While it waits it serves
+    // the mail slots itself -- its own pieces included -- so every piece that was ever handed out is
+    // worked on even if no other warp picks it up: no wait of this protocol can give up on work, and
+    // no descent is ever abandoned.
+    const uint32_t gs = s_misc[0];
+    const uint32_t n_work = s_bin[kWorkBins] << gs;  // entries: (configuration, part)
     const uint32_t chunk = max(1u, min(16u, n_work / (gridDim.x * WARPS * 32u)));
     uint32_t w_next = 0, w_end = 0;
-    bool dry = false;
+    bool dry = false, waiting = false;
     for (;;) {
-        if (!dry && w_next >= w_end) {
+        if (!dry && !waiting && w_next >= w_end) {
             const uint32_t take = ((unsigned long long)w_end + a.tail_begin < n_work) ? chunk : 1u;
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(a.work_count + kWorkBins, (unsigned long long)take);
@@ -400,6 +435,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
         int sp = 0, lq = 0, tq = 0;
         long long t_begin = 0;
         uint32_t tr_nodes = 0, tr_leaves = 0, tr_tails = 0, tr_maxsp = 0;  // rounds of the owner itself
+        uint32_t n_hits = 0;   // counting mode
         if (STATS) t_begin = clock64();
         auto trace = [&]() {
             if (STATS && a.trace && lane == 0) {
@@ -411,31 +447,69 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
                 a.trace[4 * i + 3] = (tr_tails << 16) | min(tr_maxsp, 0xffffu);
             }
         };
-        if (dry) {
-            // no configuration of its own any more: serve the mail slots until every warp of the
-            // CTA is in this state (owners get here only after their pieces have reported back)
+        // verdict of a whole configuration (or, split, of one part of it) -> flags
+        auto finalize = [&](long ci, bool h) {
+            if constexpr (!STATS) {
+                // the reference's broad phase comes first: what it clears is valid whatever the
+                // narrow phase would say
+                if (h && exact_broad_clears(a.work_mat, ci, s_rob_v, c.n_rob_v_pad, a.probe_stride, c.obs_box, lane)) h = false;
+            }
+            if (a.optimistic) {
+                if (h) publish_invalid(c, ci, lane);
+            } else {
+                publish(c, ci, !h, lane);
+            }
+            if (STATS) { if (h) st_invalid++; else st_valid++; }
+        };
+        if (dry || waiting) {
+            // no configuration to start: serve the mail slots.  A warp that waits for the pieces of
+            // its configuration leaves when they are all back; a warp that found the list dry leaves
+            // when every warp of the CTA is in that state and no slot is full.
             int k;
             for (uint32_t spins = 0;; spins++) {
                 k = -1;
                 if (lane == 0) {
-                    for (int q = 0; q < a.mail_slots; q++)
-                        if (ld_volatile(&s_mail[q].state) == 2u && atomicCAS(&s_mail[q].state, 2u, 3u) == 2u) {
-                            k = q;
-                            break;
+                    if (waiting && (ld_volatile(&s_pend[warp]) & ~kPendHit) == 0u) {
+                        k = -3;
+                    } else {
+                        for (int q = 0; q < a.mail_slots; q++)
+                            if (ld_volatile(&s_mail[q].state) == 2u && atomicCAS(&s_mail[q].state, 2u, 3u) == 2u) {
+                                k = q;
+                                break;
+                            }
+                        if (k < 0 && !waiting) {
+                            if (ld_volatile(s_idle) == (uint32_t)WARPS) k = -2;
+                            else if (spins > kWatchdogSpins) {
+                                // cannot happen (every descent is finite).  Leaving costs parallelism only:
+                                // whoever still has pieces out works them off itself.
+                                atomicAdd(c.counters + CNT_WATCHDOG, 1ULL);
+                                atomicOr(c.counters + CNT_WATCHDOG_WHERE, 1ULL);
+                                k = -2;
+                            }
                         }
-                    if (k < 0 && ld_volatile(s_idle) == (uint32_t)WARPS) k = -2;
-                    if (k != -2 && (spins > kWatchdogSpins || ((k >= 0 || (spins & 1023u) == 1023u) &&
-                                    (uint32_t)(clock64() >> 20) - *s_t0 > kAbortTicks))) {  // cannot happen; never hang the device
-                        atomicAdd(c.counters + CNT_WATCHDOG, 1ULL);
-                        atomicOr(c.counters + CNT_WATCHDOG_WHERE, 1ULL);
-                        k = -2;
                     }
                 }
                 k = __shfl_sync(kFull, k, 0);
                 if (k != -1) break;
-                __nanosleep(256);
+                __nanosleep(waiting ? 64 : 256);
             }
             if (k == -2) break;
+            if (k == -3) {
+                // all pieces are back: take over their verdict, publish the configuration
+                uint32_t v = 0, wi = 0, wh = 0;
+                if (lane == 0) {
+                    v = ld_volatile(&s_pend[warp]);
+                    st_volatile(&s_pend[warp], 0u);
+                    wi = s_wait[2 * warp];
+                    wh = s_wait[2 * warp + 1];
+                }
+                v = __shfl_sync(kFull, v, 0);
+                wi = __shfl_sync(kFull, wi, 0);
+                wh = __shfl_sync(kFull, wh, 0);
+                waiting = false;
+                finalize((long)wi, wh != 0u || (v & kPendHit) != 0u);
+                continue;
+            }
             __threadfence_block();
             Mail &b = s_mail[k];
             owner = (int)b.owner;
@@ -455,10 +529,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
             __syncwarp();
         } else {
             const uint32_t w = w_next++;
+            const uint32_t wl = w >> gs, part = w & ((1u << gs) - 1u);
             {
                 // list position -> (cost class, position in its list): dearest class first
-                const uint32_t o = __popc(__ballot_sync(kFull, lane >= 1 && lane < kWorkBins && w >= s_bin[lane & (kWorkBins - 1)]));
-                i = (long)__ldcg(a.work_idx + (size_t)(kWorkBins - 1 - o) * a.work_cap + (w - s_bin[o]));
+                const uint32_t o = __popc(__ballot_sync(kFull, lane >= 1 && lane < kWorkBins && wl >= s_bin[lane & (kWorkBins - 1)]));
+                i = (long)__ldcg(a.work_idx + (size_t)(kWorkBins - 1 - o) * a.work_cap + (wl - s_bin[o]));
             }
             {
                 const float4 q0 = __ldcg(a.work_mat + 3 * i), q1 = __ldcg(a.work_mat + 3 * i + 1),
@@ -478,16 +553,27 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
             if constexpr (STATS) {
                 if (exact_broad_clears(a.work_mat, i, s_rob_v, c.n_rob_v_pad, a.probe_stride, c.obs_box, lane)) {
                     publish(c, i, true, lane);
+                    if (counting && lane == 0) a.hit_counts[i] = 0u;
                     st_broad++;
                     trace();
                     continue;
                 }
             }
             // the descent starts from a cut through both trees instead of (root, root): the top
-            // levels almost always overlap here and would cost steps with a handful of lanes
-            sp = a.n_seed_r * a.n_seed_o;
-            for (int q = lane; q < sp; q += 32)
-                stack[q] = (a.seed_r[q / a.n_seed_o] << SH) | a.seed_o[q % a.n_seed_o];
+            // levels almost always overlap here and would cost steps with a handful of lanes.
+            // Split: part p of 2^gs takes every 2^gs-th pair of the deeper cut.
+            if (gs == 0) {
+                sp = a.n_seed_r * a.n_seed_o;
+                for (int q = lane; q < sp; q += 32)
+                    stack[q] = (a.seed_r[q / a.n_seed_o] << SH) | a.seed_o[q % a.n_seed_o];
+            } else {
+                const int ns = a.n_seed_r3 * a.n_seed_o3;
+                sp = (int)part < ns ? (ns - (int)part + (1 << gs) - 1) >> gs : 0;
+                for (int j = lane; j < sp; j += 32) {
+                    const int q = (int)part + (j << gs);
+                    stack[j] = (a.seed_r3[q / a.n_seed_o3] << SH) | a.seed_o3[q % a.n_seed_o3];
+                }
+            }
             __syncwarp();
         }
         const int pend_slot = owner >= 0 ? owner : warp;
@@ -514,20 +600,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
                     if (lane == 0) {
                         seen = 1u;
                         if (sharing && (ld_volatile(&s_pend[pend_slot]) & kPendHit) != 0u) seen = 3u;
-                        if ((uint32_t)(clock64() >> 20) - *s_t0 > kAbortTicks) seen = 4u;
                     }
                     seen = __shfl_sync(kFull, seen, 0);
                 }
             }
             if (seen & 2u) {
                 hit = true;  // another piece of this configuration has found a hit
-                break;
-            }
-            if (seen & 4u) {  // cannot happen; never hang the device
-                if (lane == 0) {
-                    atomicAdd(c.counters + CNT_WATCHDOG, 1ULL);
-                    atomicOr(c.counters + CNT_WATCHDOG_WHERE, 4ULL);
-                }
                 break;
             }
             if (seen && kind >= 0) {
@@ -603,7 +681,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
                     if (verdict == kPairCoplanar) h = coplanar_overlap(r, o, pr);
                 }
                 if (STATS) { st_tails += cnt; st_tr++; tr_tails++; }
-                if (__any_sync(kFull, h)) { hit = true; break; }
+                const unsigned mh = __ballot_sync(kFull, h);
+                if (mh) {
+                    hit = true;
+                    if (STATS && counting) n_hits += __popc(mh);
+                    else break;
+                }
                 __syncwarp();
                 continue;
             }
@@ -632,12 +715,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
                 // triangle boxes are disjoint with clearance is skipped like a culled node pair
                 // (it cuts the queued pairs four-fold: most pairs of two overlapping leaves are
                 // themselves apart)
-                const float rlx = fminf(fminf(r.ax, r.bx), r.cx) - kTriMargin,
-                            rly = fminf(fminf(r.ay, r.by), r.cy) - kTriMargin,
-                            rlz = fminf(fminf(r.az, r.bz), r.cz) - kTriMargin,
-                            rhx = fmaxf(fmaxf(r.ax, r.bx), r.cx) + kTriMargin,
-                            rhy = fmaxf(fmaxf(r.ay, r.by), r.cy) + kTriMargin,
-                            rhz = fmaxf(fmaxf(r.az, r.bz), r.cz) + kTriMargin;
+                const float rlx = fminf(fminf(r.ax, r.bx), r.cx) - a.tri_margin,
+                            rly = fminf(fminf(r.ay, r.by), r.cy) - a.tri_margin,
+                            rlz = fminf(fminf(r.az, r.bz), r.cz) - a.tri_margin,
+                            rhx = fmaxf(fmaxf(r.ax, r.bx), r.cx) + a.tri_margin,
+                            rhy = fmaxf(fmaxf(r.ay, r.by), r.cy) + a.tri_margin,
+                            rhz = fmaxf(fmaxf(r.az, r.bz), r.cz) + a.tri_margin;
 #pragma unroll
                 for (int q = 0; q < kLeafTrisDev; q++) {
                     const int k = ofirst + min(q, ocount - 1);
@@ -710,6 +793,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
             else
                 hit = narrow_exhaustive<COP>(m, s_rob_v, s_rob_t, c.n_rob_t, s_obs_a, s_obs_b, s_obs_c,
                                         s_obs_d, c.n_obs_t, lane);
+            if (STATS && counting) n_hits = 0xffffffffu;  // the fallback does not count: the audit reports it
         }
         __syncwarp();
         if (owner >= 0) {
@@ -721,32 +805,21 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
             }
             continue;
         }
-        if (sharing) {
-            // pieces of this configuration went out: wait for all of them, take over their verdict
-            uint32_t v = 0;
-            if (lane == 0) {
-                uint32_t spins = 0;
-                while (((v = ld_volatile(&s_pend[warp])) & ~kPendHit) != 0u) {
-                    if (++spins > 2u * kWatchdogSpins) {  // cannot happen; never hang the device
-                        atomicAdd(c.counters + CNT_WATCHDOG, 1ULL);
-                        atomicOr(c.counters + CNT_WATCHDOG_WHERE, 2ULL);
-                        break;
-                    }
-                    __nanosleep(128);
-                }
-                st_volatile(&s_pend[warp], 0u);
-            }
-            v = __shfl_sync(kFull, v, 0);
-            hit = hit || (v & kPendHit) != 0u;
-        }
-        if constexpr (!STATS) {
-            // the reference's broad phase comes first: what it clears is valid whatever the narrow
-            // phase would say
-            if (hit && exact_broad_clears(a.work_mat, i, s_rob_v, c.n_rob_v_pad, a.probe_stride, c.obs_box, lane)) hit = false;
-        }
-        publish(c, i, !hit, lane);
-        if (STATS) { if (hit) st_invalid++; else st_valid++; }
         trace();
+        if (STATS && counting && lane == 0) a.hit_counts[i] = n_hits;
+        if (sharing) {
+            // pieces of this configuration went out: it is published when they are all back; until
+            // then this warp serves mail slots (top of the loop)
+            if (lane == 0) {
+                s_wait[2 * warp] = (uint32_t)i;
+                s_wait[2 * warp + 1] = hit ? 1u : 0u;
+                if (hit) atomicOr(&s_pend[warp], kPendHit);  // the pieces still out may stop
+            }
+            __syncwarp();
+            waiting = true;
+            continue;
+        }
+        finalize(i, hit);
     }
     if (STATS) {
 #pragma unroll
@@ -767,12 +840,21 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const Culle
         }
     }
     // the last CTA to finish leaves the list counters at zero for the next call (no memset per
-    // call): every CTA has read the list length and drawn its last entry by the time it gets here
+    // call): every CTA has read the list length and drawn its last entry by the time it gets here.
+    // With a gather attached (rc_check_gather) the same CTA then delivers the bitmask slot, which
+    // is complete at this point, to the peers.
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        if (atomicAdd(a.work_count + kWorkBins + 1, 1ULL) == (unsigned long long)gridDim.x - 1ULL)
+        const bool last = atomicAdd(a.work_count + kWorkBins + 1, 1ULL) == (unsigned long long)gridDim.x - 1ULL;
+        if (last)
             for (int q = 0; q < kWorkBins + 2; q++) a.work_count[q] = 0;
+        __threadfence();
+        s_misc[1] = last ? 1u : 0u;
+    }
+    if (a.g.world > 1) {
+        __syncthreads();
+        if (s_misc[1]) gather_tail(a.g);
     }
 }
 
@@ -783,7 +865,7 @@ static size_t culled_smem_bytes(const DeviceTables &t, int warps, bool gobs)
     if (!gobs)
         b += (size_t)t.n_obs_nodes * 32 + (size_t)t.n_obs_t * 48 + (size_t)pad4(t.n_obs_t) * 4;
     b += (size_t)warps * (stack_cap_of(warps, gobs) + kLeafQCap + kTailQCap) * 4;
-    b = (b + 15) / 16 * 16 + kMailSlots * sizeof(Mail) + ((size_t)warps + 4 + kWorkBins + 1) * 4;  // + s_pend, s_idle, s_t0, s_bin
+    b = (b + 15) / 16 * 16 + kMailSlots * sizeof(Mail) + (3 * (size_t)warps + 4 + kWorkBins + 1) * 4;  // + s_pend, s_idle, s_misc, s_bin, s_wait
     return b;
 }
 
@@ -799,7 +881,7 @@ static void (*pick_culled(int warps, int want_stats))(const CulledArgs)
 
 cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, long n,
                                 uint8_t *d_valid, uint32_t *d_bitmask, int want_stats,
-                                cudaStream_t stream, unsigned long long *queue)
+                                cudaStream_t stream, unsigned long long *queue, const CheckExtras *extras)
 {
     const DeviceTables &t = ctx->t;
     int warps = ctx->knob_warps;
@@ -823,7 +905,7 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
     a.c.n_rob_v_pad = t.n_rob_v_pad; a.c.n_rob_t = t.n_rob_t; a.c.n_obs_t = t.n_obs_t;
     a.c.obs_box = t.obs_box;
     a.c.confs = d_confs; a.c.n = n; a.c.valid = d_valid; a.c.bitmask = d_bitmask;
-    a.c.counters = ctx->d_counters; a.c.queue = queue;
+    a.c.counters = ctx->d_counters; a.c.queue = queue; a.c.hit_counts = nullptr;
     a.rob_bvh = t.rob_bvh; a.obs_bvh = t.obs_bvh;
     a.n_rob_nodes = t.n_rob_nodes; a.n_obs_nodes = t.n_obs_nodes;
     a.sph_x = t.rob_center[0]; a.sph_y = t.rob_center[1]; a.sph_z = t.rob_center[2];
@@ -844,6 +926,18 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
     if (ctx->knob_tail > 0) a.tail_thresh = min(32, ctx->knob_tail);
     if (ctx->knob_leaf > 0) a.leaf_thresh = min(8, ctx->knob_leaf);
     a.share = ctx->knob_share;
+    a.hit_counts = (want_stats && extras) ? extras->hit_counts : nullptr;
+    if (a.hit_counts) a.share = 0;  // counting: a configuration stays with one warp
+    // flags: written once per configuration by its warp (statistics kernels), or optimistically --
+    // marked valid by step 1, overwritten by whichever part of the descent finds a hit
+    a.optimistic = want_stats ? 0 : 1;
+    a.split_max = max(1, min(kSplitMax, ctx->knob_split_max));
+    a.split_load = max(1, ctx->knob_split_load);
+    a.tri_margin = 2.f * t.box_margin;
+    a.n_seed_r3 = t.n_seed_r[3]; a.n_seed_o3 = t.n_seed_o[3];
+    for (int q = 0; q < 8; q++) { a.seed_r3[q] = t.seed_r[3][q]; a.seed_o3[q] = t.seed_o[3][q]; }
+    if (extras && extras->gather) a.g = *extras->gather;
+    else { memset(&a.g, 0, sizeof a.g); a.g.world = 1; }
     a.mail_slots = max(1, min(kMailSlots, ctx->knob_mail_slots));
     a.donate_min = max(40, ctx->knob_donate_min);
     a.trace = want_stats ? ctx->d_trace : nullptr;
@@ -862,6 +956,7 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
     k.work_idx = ctx->d_work_idx; k.work_mat = ctx->d_work_mat; k.work_count = ctx->d_work_count;
     k.work_cap = ctx->work_cap;
     k.counters = ctx->d_counters;
+    k.optimistic = a.optimistic;
     void (*kern)(const CulledArgs);
     if (ctx->coplanar_mode)
         kern = gobs ? pick_culled<true, true>(warps, want_stats) : pick_culled<false, true>(warps, want_stats);

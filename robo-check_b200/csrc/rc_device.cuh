@@ -296,8 +296,12 @@ __device__ __noinline__ bool coplanar_overlap(const Tri r, const Tri o, const Pl
 // instantiation costs spills, so the default build contains none of this.
 constexpr int kPairMiss = 0, kPairHit = 1, kPairCoplanar = 2;
 
-__device__ __noinline__ int pair_tail(const Tri r, const Plane pr, float dR0, float dR1, float dR2,
-                                      const Tri o, const Plane po, float dO0, float dO1, float dO2)
+// DBG: the intermediate values go to dbg[0..9] = D, O, t_r01, t_r12, t_o01, t_o12 (device known-answer
+// tests, rc_kat.cuh); the production instantiation is pair_tail below.
+template <bool DBG>
+__device__ __forceinline__ int pair_tail_core(const Tri &r, const Plane &pr, float dR0, float dR1, float dR2,
+                                              const Tri &o, const Plane &po, float dO0, float dO1, float dO2,
+                                              float *dbg)
 {
     if (is_coplanar(pr, po)) return kPairCoplanar;
 
@@ -323,10 +327,20 @@ __device__ __noinline__ int pair_tail(const Tri r, const Plane pr, float dR0, fl
     float tr01, tr12, to01, to12;
     tri_interval(r, dR0, dR1, dR2, Dx, Dy, Dz, Ox, Oy, Oz, tr01, tr12);
     tri_interval(o, dO0, dO1, dO2, Dx, Dy, Dz, Ox, Oy, Oz, to01, to12);
+    if (DBG) {
+        dbg[0] = Dx; dbg[1] = Dy; dbg[2] = Dz; dbg[3] = Ox; dbg[4] = Oy; dbg[5] = Oz;
+        dbg[6] = tr01; dbg[7] = tr12; dbg[8] = to01; dbg[9] = to12;
+    }
     // :659-670 -- `>=`; a NaN makes both comparisons false, i.e. a collision, as in the reference
     if (fminf(tr01, tr12) >= fmaxf(to01, to12)) return kPairMiss;
     if (fminf(to01, to12) >= fmaxf(tr01, tr12)) return kPairMiss;
     return kPairHit;
+}
+
+__device__ __noinline__ int pair_tail(const Tri r, const Plane pr, float dR0, float dR1, float dR2,
+                                      const Tri o, const Plane po, float dO0, float dO1, float dO2)
+{
+    return pair_tail_core<false>(r, pr, dR0, dR1, dR2, o, po, dO0, dO1, dO2, nullptr);
 }
 
 // One (robot triangle, obstacle triangle) decision given both planes (the obstacle plane is

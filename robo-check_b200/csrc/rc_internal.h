@@ -36,6 +36,7 @@ struct DeviceTables {
     int n_rob_v = 0, n_rob_t = 0, n_obs_v = 0, n_obs_t = 0;
     int n_rob_nodes = 0, n_obs_nodes = 0;
     int n_rob_v_pad = 0;        // n_rob_v rounded up to 32 (padding repeats vertex 0)
+    float box_margin = 1e-3f;   // inflation of every tree box; scales with the scene (rc_create)
     rc_aabb obs_box;
     float rob_center[3];        // bounding sphere of the robot in its local frame
     float rob_radius;
@@ -86,7 +87,12 @@ struct rc_ctx {
     unsigned long long *d_counters = nullptr;  // [RC_NUM_COUNTERS] work queue + statistics
     rc_aabb *d_obs_box = nullptr;              // obstacle AABB on the device (broad-phase stage)
     int stats_on = 0;
-    uint32_t gather_calls = 0;                 // rc_check_gather calls so far (all ranks call in lock-step)
+    uint32_t gather_calls = 0;                 // number of the last rc_check_gather call on gather_buf (all ranks in lock-step)
+    uint32_t *gather_buf = nullptr;            // the own gather buffer that numbering belongs to
+    cudaEvent_t ev_scratch = nullptr;          // behind the last launch that used the scratch below
+    cudaStream_t scratch_stream = nullptr;
+    bool scratch_used = false;
+    int knob_host_chunks = 0;                  // RC_HOST_CHUNKS: waves rc_check_host cuts a batch into (0 = automatic)
     int coplanar_mode = 0;                     // rc_set_coplanar_mode: 0 = skip like the reference, 1 = decide in the plane
     uint32_t *d_trace = nullptr;               // rc_stats_trace (caller's memory)
     unsigned long long launches = 0;           // kernels launched through this context
@@ -120,6 +126,8 @@ struct rc_ctx {
     int knob_mail_slots = 4, knob_donate_min = 40;  // RC_MAIL_SLOTS, RC_DONATE_MIN
     int knob_host_direct = 0; // RC_HOST_DIRECT=1: rc_check_host stores the flags into the pinned buffer from the kernels instead of copying them back
     int knob_share = 1;      // RC_SHARE=0: warps of a CTA do not hand pieces of a deep descent to each other
+    int knob_split_max = 16;  // RC_SPLIT_MAX: parts a configuration may be cut into when the work list is short (1 = never)
+    int knob_split_load = 8;  // RC_SPLIT_LOAD: split while entries <= this many per warp of the grid
     std::string last_error;
     std::vector<void *> allocations;
 };
@@ -151,30 +159,44 @@ constexpr int kHostChunks = 8;
 int set_error(rc_ctx *ctx, int code, const std::string &msg);
 int check_cuda(rc_ctx *ctx, cudaError_t e, const char *what);
 
-// kernels.cu launchers (all asynchronous on `stream`)
-// `queue` = the work-queue counter of this launch (concurrent launches need distinct ones)
-cudaError_t launch_check(const rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_valid,
-                         uint32_t *d_bitmask, int mode, int want_stats, cudaStream_t stream,
-                         unsigned long long *queue);
-cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, long n,
-                                uint8_t *d_valid, uint32_t *d_bitmask, int want_stats,
-                                cudaStream_t stream, unsigned long long *queue);
-cudaError_t launch_check_spheres(const rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_valid,
-                                 uint32_t *d_bitmask, int want_stats, cudaStream_t stream,
-                                 unsigned long long *queue);
 // all-gather of the bitmask through peer-mapped buffers (rc_gather.cuh)
 constexpr int kMaxGatherRanks = 16;
+constexpr int kGatherHeaderWords = 4;        // behind the signal row: calls, timeouts, 2 reserved
 struct GatherArgs {
     const uint32_t *src;                     // this rank's slot in its own buffer
     uint32_t *peer_slot[kMaxGatherRanks];    // the same slot inside every rank's buffer
     uint32_t *peer_signal[kMaxGatherRanks];  // word [rank] of every rank's signal row
-    const uint32_t *my_signal;               // this rank's signal row
+    uint32_t *my_row;                        // this rank's signal row; [world] calls, [world + 1] timeouts
     int rank, world, words;
+    int wait;                                // 1: also wait for the peers' slots (one-call form)
     uint32_t call;                           // 1, 2, 3, ...
     unsigned long long *counters;
     unsigned long long timeout_ns;
 };
+// what a check launch may carry besides the flags
+struct CheckExtras {
+    const GatherArgs *gather = nullptr;      // culled mode: the last CTA pushes the bitmask slot to the peers
+    uint32_t *hit_counts = nullptr;          // statistics kernels: hitting pairs per configuration, no early exit
+};
+
+// kernels.cu launchers (all asynchronous on `stream`)
+// `queue` = the work-queue counter of this launch (concurrent launches need distinct ones)
+cudaError_t launch_check(const rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_valid,
+                         uint32_t *d_bitmask, int mode, int want_stats, cudaStream_t stream,
+                         unsigned long long *queue, const CheckExtras *extras = nullptr);
+cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, long n,
+                                uint8_t *d_valid, uint32_t *d_bitmask, int want_stats,
+                                cudaStream_t stream, unsigned long long *queue,
+                                const CheckExtras *extras = nullptr);
+cudaError_t launch_check_spheres(const rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_valid,
+                                 uint32_t *d_bitmask, int want_stats, cudaStream_t stream,
+                                 unsigned long long *queue);
 cudaError_t launch_gather_push(const rc_ctx *ctx, const GatherArgs &a, cudaStream_t stream);
+cudaError_t launch_gather_wait(const rc_ctx *ctx, const GatherArgs &a, cudaStream_t stream);
+// device known-answer tests of the per-pair helpers (rc_kat.cuh)
+cudaError_t launch_kat_pairs(const float *d_r9, const float *d_o9, int n, float *d_out, int *d_verdict,
+                             cudaStream_t stream);
+cudaError_t launch_kat_la_solve(const float *d_in, int n, float *d_out, cudaStream_t stream);
 cudaError_t launch_fma_peak(float *d_out, int grid, int iters, cudaStream_t stream);
 cudaError_t launch_conf_generate(rc_config *d_out, long n, const float box[6], uint64_t seed,
                                  cudaStream_t stream);

@@ -10,6 +10,7 @@
 //   stage kernels        the un-fused stage API (transform / AABB / broad / narrow).
 #include <float.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "rc_device.cuh"
 #include "rc_internal.h"
@@ -112,6 +113,7 @@ struct CheckArgs {
     unsigned long long *counters;  // statistics
     unsigned long long *queue;     // work-queue counter of this launch
     int chunk;
+    uint32_t *hit_counts;          // statistics kernels: hitting pairs per configuration, no early exit
 };
 
 __device__ __forceinline__ void publish(const CheckArgs &a, long i, bool valid, int lane)
@@ -130,16 +132,17 @@ __device__ __forceinline__ void publish(const CheckArgs &a, long i, bool valid, 
 // the end re-test the last triangle (a duplicate cannot change "some pair hits").  The later
 // stages run at most once per lane and triangle between two warp-wide flushes, so the rare path
 // executes with several lanes instead of one.  `load_tri(j)` yields the world-space triangle.
-template <bool COP, class LoadTri>
+// COUNT: no early exit, every hitting pair is counted into `tails`' sibling `n_hits` (audit mode).
+template <bool COP, bool COUNT, class LoadTri>
 __device__ __forceinline__ bool exhaustive_sweep(LoadTri load_tri, int n_rob_t,
                                                  const float4 *__restrict__ s_obs_a,
                                                  const float4 *__restrict__ s_obs_b,
                                                  const float4 *__restrict__ s_obs_c,
                                                  const float *__restrict__ s_obs_d, int n_obs_t,
-                                                 int lane, unsigned long long &tails)
+                                                 int lane, unsigned long long &tails, uint32_t &n_hits)
 {
     bool hit = false;
-    for (int jb = 0; jb < n_rob_t && !hit; jb += 64) {
+    for (int jb = 0; jb < n_rob_t && (COUNT || !hit); jb += 64) {
         const Tri r0 = load_tri(min(jb + lane, n_rob_t - 1));
         const Tri r1 = load_tri(min(jb + 32 + lane, n_rob_t - 1));
         const Plane p0 = plane_of(r0), p1 = plane_of(r1);
@@ -156,9 +159,13 @@ __device__ __forceinline__ bool exhaustive_sweep(LoadTri load_tri, int n_rob_t,
                 const float dO0 = sdist(pr, o.ax, o.ay, o.az), dO1 = sdist(pr, o.bx, o.by, o.bz),
                             dO2 = sdist(pr, o.cx, o.cy, o.cz);
                 const int verdict = pair_tail(r, pr, dR0, dR1, dR2, o, po, dO0, dO1, dO2);
-                if (verdict == kPairHit) hit = true;
+                bool h = verdict == kPairHit;
                 if constexpr (COP) {  // RC_COPLANAR_DECIDE
-                    if (verdict == kPairCoplanar && coplanar_overlap(r, o, pr)) hit = true;
+                    if (verdict == kPairCoplanar && coplanar_overlap(r, o, pr)) h = true;
+                }
+                if (h) {
+                    hit = true;
+                    if (COUNT) n_hits++;
                 }
             }
         };
@@ -180,6 +187,10 @@ __device__ __forceinline__ bool exhaustive_sweep(LoadTri load_tri, int n_rob_t,
                 m0 |= (uint32_t)pass0 << q;
                 m1 |= (uint32_t)pass1 << q;
             }
+            if (COUNT) {  // lanes past the end re-test the last triangle: not counted twice
+                if (jb + lane >= n_rob_t) m0 = 0u;
+                if (jb + 32 + lane >= n_rob_t) m1 = 0u;
+            }
             while (__any_sync(kFull, (m0 | m1) != 0u)) {
                 if (m0 | m1) {
                     // one code path for both triangles of the lane (selects instead of branches)
@@ -195,7 +206,7 @@ __device__ __forceinline__ bool exhaustive_sweep(LoadTri load_tri, int n_rob_t,
                     finish(r, pr, kb + q);
                 }
             }
-            if (__any_sync(kFull, hit)) break;
+            if (!COUNT && __any_sync(kFull, hit)) break;
         }
         hit = __any_sync(kFull, hit);
     }
@@ -255,7 +266,10 @@ __global__ void __launch_bounds__(kThreads, 2) check_brute_kernel(const CheckArg
                             a.obs_box.y_min, a.obs_box.z_min, a.obs_box.x_max, a.obs_box.y_max,
                             a.obs_box.z_max)) {
                 publish(a, i, true, lane);
-                if (STATS) st_broad++;
+                if (STATS) {
+                    st_broad++;
+                    if (a.hit_counts && lane == 0) a.hit_counts[i] = 0u;
+                }
                 continue;
             }
             auto load_tri = [&](int j) {
@@ -267,8 +281,18 @@ __global__ void __launch_bounds__(kThreads, 2) check_brute_kernel(const CheckArg
                 xform(m, C.x, C.y, C.z, r.cx, r.cy, r.cz);
                 return r;
             };
-            const bool hit = exhaustive_sweep<COP>(load_tri, a.n_rob_t, s_obs_a, s_obs_b, s_obs_c, s_obs_d,
-                                                   a.n_obs_t, lane, st_tail);
+            bool hit;
+            uint32_t n_hits = 0;
+            if (STATS && a.hit_counts) {
+                hit = exhaustive_sweep<COP, true>(load_tri, a.n_rob_t, s_obs_a, s_obs_b, s_obs_c, s_obs_d,
+                                                  a.n_obs_t, lane, st_tail, n_hits);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) n_hits += __shfl_xor_sync(kFull, n_hits, o);
+                if (lane == 0) a.hit_counts[i] = n_hits;
+            } else {
+                hit = exhaustive_sweep<COP, false>(load_tri, a.n_rob_t, s_obs_a, s_obs_b, s_obs_c, s_obs_d,
+                                                   a.n_obs_t, lane, st_tail, n_hits);
+            }
             publish(a, i, !hit, lane);
             if (STATS) { if (hit) st_invalid++; else st_valid++; }
         }
@@ -293,10 +317,11 @@ __global__ void __launch_bounds__(kThreads, 2) check_brute_kernel(const CheckArg
 
 }  // namespace rc
 
+#include "rc_gather.cuh"
 #include "rc_culled.cuh"
 #include "rc_spheres.cuh"
 #include "rc_stages.cuh"
-#include "rc_gather.cuh"
+#include "rc_kat.cuh"
 
 namespace rc {
 
@@ -308,7 +333,7 @@ static size_t brute_smem_bytes(const DeviceTables &t)
 
 cudaError_t launch_check(const rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_valid,
                          uint32_t *d_bitmask, int mode, int want_stats, cudaStream_t stream,
-                         unsigned long long *queue)
+                         unsigned long long *queue, const CheckExtras *extras)
 {
     if (!queue) queue = ctx->d_counters + CNT_QUEUE;
     const DeviceTables &t = ctx->t;
@@ -330,6 +355,7 @@ cudaError_t launch_check(const rc_ctx *ctx, const rc_config *d_confs, long n, ui
         a.obs_box = t.obs_box;
         a.confs = d_confs; a.n = n; a.valid = d_valid; a.bitmask = d_bitmask;
         a.counters = ctx->d_counters; a.queue = queue;
+        a.hit_counts = (want_stats && extras) ? extras->hit_counts : nullptr;
         const size_t smem = brute_smem_bytes(t);
         if (smem > (size_t)ctx->max_smem_optin) return cudaErrorInvalidConfiguration;
         const int ctas_per_sm = (2 * smem + 2048 <= (size_t)ctx->max_smem_optin) ? 2 : 1;
@@ -345,7 +371,7 @@ cudaError_t launch_check(const rc_ctx *ctx, const rc_config *d_confs, long n, ui
         kern<<<grid, kThreads, smem, stream>>>(a);
         return cudaGetLastError();
     }
-    return launch_check_culled(ctx, d_confs, n, d_valid, d_bitmask, want_stats, stream, queue);
+    return launch_check_culled(ctx, d_confs, n, d_valid, d_bitmask, want_stats, stream, queue, extras);
 }
 
 }  // namespace rc

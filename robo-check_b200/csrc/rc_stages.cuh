@@ -380,8 +380,9 @@ __global__ void __launch_bounds__(kThreads, 2) narrow_soa_kernel(const CheckArgs
                        __ldg(z + vb), __ldg(x + vc), __ldg(y + vc), __ldg(z + vc)};
         };
         unsigned long long tails = 0;
-        const bool hit = exhaustive_sweep<COP>(load_tri, a.n_rob_t, s_obs_a, s_obs_b, s_obs_c, s_obs_d,
-                                               a.n_obs_t, lane, tails);
+        uint32_t n_hits = 0;
+        const bool hit = exhaustive_sweep<COP, false>(load_tri, a.n_rob_t, s_obs_a, s_obs_b, s_obs_c, s_obs_d,
+                                                      a.n_obs_t, lane, tails, n_hits);
         if (lane == 0) a.valid[i] = hit ? 0 : 1;
     }
 }

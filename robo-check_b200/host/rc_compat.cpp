@@ -147,6 +147,27 @@ void narrowPhase_unopt(int num_confs, int num_rob_trs, int num_rob_pts, int num_
                 obs_pts, valid_conf);
 }
 
+void narrowPhaseBaseline(int num_confs, int num_rob_trs, int num_rob_pts, int num_obs_trs, int num_obs_pts,
+                         const Triangle *rob_trs, const Vector3f *rob_pts, const Triangle *obs_trs,
+                         const Vector3f *obs_pts, bool *valid_conf)
+{
+    // narrow-phase.cu:346-423 decides every configuration, whatever valid_conf held
+    if (num_confs > 0 && valid_conf) memset(valid_conf, 0, (size_t)num_confs);
+    narrowPhase(num_confs, num_rob_trs, num_rob_pts, num_obs_trs, num_obs_pts, rob_trs, rob_pts, obs_trs,
+                obs_pts, valid_conf);
+}
+
+void broadPhaseBaseline(int num_confs, const AABB *robots, const AABB *obstacle, bool *valid_conf)
+{
+    if (!robots || !obstacle || !valid_conf) return;
+    for (int i = 0; i < num_confs; i++) {
+        const AABB &r = robots[i], &o = *obstacle;
+        const bool hit = (o.x_min <= r.x_max && r.x_min <= o.x_max) && (o.y_min <= r.y_max && r.y_min <= o.y_max) &&
+                         (o.z_min <= r.z_max && r.z_min <= o.z_max);
+        valid_conf[i] = !hit;
+    }
+}
+
 // ---- host utilities ---------------------------------------------------------------------------
 
 void loadOBJFile(const char *filename, std::vector<float> &x, std::vector<float> &y, std::vector<float> &z,

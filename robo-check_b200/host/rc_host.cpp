@@ -247,6 +247,153 @@ int rc_mesh_subdivide(const rc_mesh *src, int levels, rc_mesh **out)
     return RC_OK;
 }
 
+// ---- .env / .query (placement of the bodies, start and goal) -----------------------------------
+// The benchmark's environment file (models/alpha1.0/alpha.env) names the bodies and places the
+// passive ones in the world: `obstacle.obj -c(1 1 0 1) 11.0899 9.00906 3.24427  0 0 0` (:13).  The
+// reference never reads it -- its pipeline checks the two OBJ files as they are -- so nothing in
+// this library applies a placement unless the caller asks for it with rc_mesh_place.
+//
+//   Boundary Box [lo:hi ; lo:hi ; lo:hi]
+//   Multibodies / <count>
+//   Active  / <count> / <file> [-c(r g b a)] <base type words> / Connections / <count>
+//   Passive / <file> [-c(r g b a)] x y z  rx ry rz
+// Tokens are read in order; a body line is any token ending in .obj or .g.
+
+namespace {
+
+bool ends_with(const std::string &s, const char *suffix)
+{
+    const size_t n = strlen(suffix);
+    return s.size() >= n && s.compare(s.size() - n, n, suffix) == 0;
+}
+
+bool parse_float(const std::string &tok, float *out)
+{
+    if (tok.empty()) return false;
+    char *end = nullptr;
+    const float v = strtof(tok.c_str(), &end);
+    if (end == tok.c_str() || *end != '\0') return false;
+    *out = v;
+    return true;
+}
+
+}  // namespace
+
+int rc_env_read(const char *path, rc_env *out)
+{
+    if (!path || !out) return RC_ERR_INVALID;
+    std::ifstream in(path);
+    if (!in.is_open()) return RC_ERR_IO;
+    memset(out, 0, sizeof *out);
+    for (int k = 0; k < 3; k++) { out->box_lo[k] = -FLT_MAX; out->box_hi[k] = FLT_MAX; }
+    std::string line;
+    int active = -1;  // section: 1 active, 0 passive, -1 none yet
+    while (std::getline(in, line)) {
+        // punctuation of the header and of the colour option becomes white space
+        std::string flat = line;
+        for (char &c : flat)
+            if (c == '[' || c == ']' || c == ':' || c == ';' || c == '(' || c == ')' || c == ',') c = ' ';
+        const std::vector<std::string> tok = tokens_of(flat);
+        if (tok.empty() || tok[0][0] == '#') continue;
+        if (tok[0] == "Boundary") {
+            std::vector<float> v;
+            for (const std::string &t : tok) { float f; if (parse_float(t, &f)) v.push_back(f); }
+            if (v.size() != 6) return RC_ERR_FORMAT;
+            for (int k = 0; k < 3; k++) { out->box_lo[k] = v[2 * k]; out->box_hi[k] = v[2 * k + 1]; }
+            out->has_box = 1;
+            continue;
+        }
+        if (tok[0] == "Active") { active = 1; continue; }
+        if (tok[0] == "Passive") { active = 0; continue; }
+        if (!(ends_with(tok[0], ".obj") || ends_with(tok[0], ".g"))) continue;  // counts, "Multibodies", "Connections"
+        if (active < 0) return RC_ERR_FORMAT;
+        if (out->n_bodies >= RC_ENV_MAX_BODIES) return RC_ERR_UNSUPPORTED;
+        rc_env_body &b = out->bodies[out->n_bodies];
+        if (tok[0].size() >= sizeof b.file) return RC_ERR_FORMAT;
+        strcpy(b.file, tok[0].c_str());
+        b.active = active;
+        b.color[0] = b.color[1] = b.color[2] = 0.f; b.color[3] = 1.f;
+        size_t k = 1;
+        if (k < tok.size() && tok[k] == "-c") {
+            for (int q = 0; q < 4; q++)
+                if (k + 1 + q >= tok.size() || !parse_float(tok[k + 1 + q], &b.color[q])) return RC_ERR_FORMAT;
+            k += 5;
+        }
+        // six numbers = placement (passive bodies; an active body carries its base type instead)
+        std::vector<float> v;
+        for (; k < tok.size(); k++) { float f; if (parse_float(tok[k], &f)) v.push_back(f); else break; }
+        if (v.size() >= 6) {
+            b.has_placement = 1;
+            b.x = v[0]; b.y = v[1]; b.z = v[2]; b.rx = v[3]; b.ry = v[4]; b.rz = v[5];
+        } else if (!active && !v.empty()) {
+            return RC_ERR_FORMAT;  // a passive body with a truncated placement
+        }
+        out->n_bodies++;
+    }
+    return out->n_bodies > 0 ? RC_OK : RC_ERR_FORMAT;
+}
+
+// Lines of `<robot index> x y z r1 r2 r3` (models/alpha1.0/alpha.query: start, then goal).  The
+// rotations are fractions of a full turn about x, y, z, i.e. roll, pitch, yaw of Configuration
+// (Utils_rai.h:51-58) after scaling by 2 pi and wrapping into [-pi, pi).
+int rc_query_read(const char *path, rc_config **confs, long *n)
+{
+    if (!path || !confs || !n) return RC_ERR_INVALID;
+    std::ifstream in(path);
+    if (!in.is_open()) return RC_ERR_IO;
+    std::vector<rc_config> v;
+    std::string line;
+    const double two_pi = 6.283185307179586;
+    while (std::getline(in, line)) {
+        const std::vector<std::string> tok = tokens_of(line);
+        if (tok.empty() || tok[0][0] == '#') continue;
+        float f[7];
+        if (tok.size() < 7) return RC_ERR_FORMAT;
+        for (int k = 0; k < 7; k++)
+            if (!parse_float(tok[k], &f[k])) return RC_ERR_FORMAT;
+        auto angle = [&](float turns) {
+            double a = std::fmod((double)turns, 1.0) * two_pi;
+            if (a >= 3.141592653589793) a -= two_pi;
+            if (a < -3.141592653589793) a += two_pi;
+            return (float)a;
+        };
+        rc_config c;
+        c.x = f[1]; c.y = f[2]; c.z = f[3];
+        c.roll = angle(f[4]); c.pitch = angle(f[5]); c.yaw = angle(f[6]);
+        v.push_back(c);
+    }
+    *n = (long)v.size();
+    *confs = (rc_config *)malloc(sizeof(rc_config) * std::max<size_t>(v.size(), 1));
+    if (!*confs) return RC_ERR_NOMEM;
+    if (!v.empty()) memcpy(*confs, v.data(), sizeof(rc_config) * v.size());
+    return RC_OK;
+}
+
+// The body moved to its place in the world: p' = Rz(rz) Ry(ry) Rx(rx) p + (x, y, z), angles in
+// degrees, the matrix the reference builds for a configuration (broad-phase-fused.cu:26-55, A = yaw
+// about z, B = pitch about y, C = roll about x), evaluated in double and rounded once per coordinate.
+int rc_mesh_place(const rc_mesh *m, float x, float y, float z, float rx_deg, float ry_deg, float rz_deg,
+                  rc_mesh **out)
+{
+    if (!m || !out) return RC_ERR_INVALID;
+    const double d2r = 3.141592653589793 / 180.0;
+    const double cA = std::cos(rz_deg * d2r), sA = std::sin(rz_deg * d2r);
+    const double cB = std::cos(ry_deg * d2r), sB = std::sin(ry_deg * d2r);
+    const double cC = std::cos(rx_deg * d2r), sC = std::sin(rx_deg * d2r);
+    const double R[3][3] = {{cA * cB, cA * sB * sC - sA * cC, cA * sB * cC + sA * sC},
+                            {sA * cB, sA * sB * sC + cA * cC, sA * sB * cC - cA * sC},
+                            {-sB, cB * sC, cB * cC}};
+    rc_mesh *r = new rc_mesh(*m);
+    for (size_t v = 0; v < m->x.size(); v++) {
+        const double px = m->x[v], py = m->y[v], pz = m->z[v];
+        r->x[v] = (float)(R[0][0] * px + R[0][1] * py + R[0][2] * pz + x);
+        r->y[v] = (float)(R[1][0] * px + R[1][1] * py + R[1][2] * pz + y);
+        r->z[v] = (float)(R[2][0] * px + R[2][1] * py + R[2][2] * pz + z);
+    }
+    *out = r;
+    return RC_OK;
+}
+
 // ---- .conf ---------------------------------------------------------------------------------
 
 int rc_conf_read(const char *path, rc_config **confs, uint8_t **tags, long *n)

@@ -197,17 +197,28 @@ def test_shard_size_and_multi_argument_checks(rc):
 
 
 def test_gather_and_coplanar_argument_checks(rc):
-    """rc_gather_buffer_words sizes the peer buffer (two gather areas + a signal row); rc_check_gather
-    and rc_set_coplanar_mode reject bad arguments with a status, without touching a device."""
+    """rc_gather_buffer_words sizes the peer buffer (two gather areas + a signal row + a four-word
+    header: call number, timeouts); rc_check_gather and rc_set_coplanar_mode reject bad arguments with
+    a status, without touching a device."""
     import ctypes
     lib = rc.lib()
-    assert lib.rc_gather_buffer_words(8, 3125) == 2 * 8 * 3125 + 8
-    assert lib.rc_gather_buffer_words(1, 1) == 3
+    assert lib.rc_gather_buffer_words(8, 3125) == 2 * 8 * 3125 + 8 + 4
+    assert lib.rc_gather_buffer_words(1, 1) == 3 + 4
     for world, words in ((0, 10), (17, 10), (2, 0), (-1, 5)):
         assert lib.rc_gather_buffer_words(world, words) == rc.RC_ERR_INVALID
     peers = (ctypes.c_void_p * 2)(None, None)
     res = ctypes.c_void_p()
     assert lib.rc_check_gather(None, None, 0, None, peers, 0, 2, 10, ctypes.byref(res), None) == rc.RC_ERR_INVALID
+    assert lib.rc_check_gather_begin(None, None, 0, None, peers, 0, 2, 10, ctypes.byref(res), None) == rc.RC_ERR_INVALID
+    assert lib.rc_gather_end(None, peers, 0, 2, 10, None) == rc.RC_ERR_INVALID
+    assert lib.rc_gather_status(None, None, 2, 10, None, None) == rc.RC_ERR_INVALID
+    # audits and device known-answer tests: argument checks come before any device work
+    assert lib.rc_hit_counts(None, None, 4, rc.RC_MODE_BRUTE, None, None, None) == rc.RC_ERR_INVALID
+    assert lib.rc_audit(None, None, 4, None, None, None, 0) == rc.RC_ERR_INVALID
+    assert lib.rc_kat_pairs(None, None, None, 1, None, None) == rc.RC_ERR_INVALID
+    assert lib.rc_kat_la_solve(None, None, 1, None) == rc.RC_ERR_INVALID
+    assert lib.rc_check(None, None, 4, None, None, 7, None) == rc.RC_ERR_INVALID
+    assert lib.rc_check_host(None, None, 4, None, 7) == rc.RC_ERR_INVALID
     assert lib.rc_set_coplanar_mode(None, rc.RC_COPLANAR_DECIDE) == rc.RC_ERR_INVALID
     assert lib.rc_coplanar_mode(None) == rc.RC_ERR_INVALID
     assert (rc.RC_COPLANAR_SKIP, rc.RC_COPLANAR_DECIDE) == (0, 1)
@@ -256,3 +267,84 @@ def test_host_io_properties(rc, tmp_path):
 
     obj_case()
     conf_case()
+
+
+ALPHA_ENV = """Boundary Box [-200:200 ; -200:200 ; -200:200]
+
+Multibodies
+2
+
+Active
+1
+robot.obj -c(0 1 0 1) Volumetric Rotational
+Connections
+0
+
+Passive
+obstacle.obj -c(1 1 0 1) 11.0899 9.00906 3.24427  0 0 0
+"""
+ALPHA_QUERY = """ 0 78.240253 24.147785 -8.133371 0.286451 0.769112 0.706202
+ 0 -1.393717 14.630385 0.415858 0.713232 0.156663 0.826461
+"""
+
+
+def test_env_and_query_readers(rc, meshes, tmp_path):
+    """the benchmark's .env / .query (text of models/alpha1.0/alpha.env, alpha.query):
+    the environment names robot (active) and obstacle (passive) and places the obstacle at
+    11.0899 9.00906 3.24427 (:13) -- a placement the reference ignores, so it is applied only on
+    request (Mesh.place) and the default context stays on the untransformed mesh."""
+    env_p, q_p = tmp_path / "alpha.env", tmp_path / "alpha.query"
+    env_p.write_text(ALPHA_ENV)
+    q_p.write_text(ALPHA_QUERY)
+    env = rc.readEnvironment(str(env_p))
+    assert env["box"] == ((-200.0, -200.0, -200.0), (200.0, 200.0, 200.0))
+    rob_b, obs_b = env["bodies"]
+    assert rob_b["file"] == "robot.obj" and rob_b["active"] and rob_b["placement"] is None
+    assert rob_b["color"] == (0.0, 1.0, 0.0, 1.0)
+    assert obs_b["file"] == "obstacle.obj" and not obs_b["active"]
+    assert np.allclose(obs_b["placement"], (11.0899, 9.00906, 3.24427, 0, 0, 0), rtol=1e-7)
+    q = rc.readQuery(str(q_p))
+    assert q.shape == (2, 6)
+    assert np.allclose(q[:, :3], [[78.240253, 24.147785, -8.133371], [-1.393717, 14.630385, 0.415858]], rtol=1e-7)
+    turns = np.array([[0.286451, 0.769112, 0.706202], [0.713232, 0.156663, 0.826461]])  # about x, y, z
+    want = (turns * 2 * np.pi + np.pi) % (2 * np.pi) - np.pi
+    assert np.allclose(q[:, 5], want[:, 0], atol=1e-5)   # roll  (x)
+    assert np.allclose(q[:, 3], want[:, 1], atol=1e-5)   # pitch (y)
+    assert np.allclose(q[:, 4], want[:, 2], atol=1e-5)   # yaw   (z)
+    assert np.all(np.abs(q[:, 3:]) <= np.pi)
+    # placement: pure translation moves every vertex and the AABB by exactly the offset ...
+    obs = meshes[1]
+    placed = obs.place(*obs_b["placement"])
+    off = np.float32(obs_b["placement"][:3])
+    assert np.allclose(placed.x, obs.x + off[0], atol=1e-5) and np.allclose(placed.z, obs.z + off[2], atol=1e-5)
+    assert np.array_equal(placed.v1, obs.v1) and placed.counts() == obs.counts()
+    # ... a quarter turn about z maps (x, y, z) to (-y, x, z); a zero placement is the identity
+    turned = obs.place(0, 0, 0, 0, 0, 90)
+    assert np.allclose(turned.x, -obs.y, atol=1e-4) and np.allclose(turned.y, obs.x, atol=1e-4)
+    same = obs.place()
+    assert np.array_equal(same.x, obs.x) and np.array_equal(same.y, obs.y) and np.array_equal(same.z, obs.z)
+    # malformed input is an error code, never a crash
+    bad = tmp_path / "bad.env"
+    bad.write_text("Passive\nobstacle.obj 1 2\n")
+    with pytest.raises(rc.RoboCheckError) as e:
+        rc.readEnvironment(str(bad))
+    assert e.value.code == rc.RC_ERR_FORMAT
+    with pytest.raises(rc.RoboCheckError) as e:
+        rc.readEnvironment(str(tmp_path / "missing.env"))
+    assert e.value.code == rc.RC_ERR_IO
+    bad_q = tmp_path / "bad.query"
+    bad_q.write_text("0 1 2 3\n")
+    with pytest.raises(rc.RoboCheckError):
+        rc.readQuery(str(bad_q))
+
+
+def test_compat_header_declares_the_baselines():
+    """narrow-phase.hu:37 / broad-phase.hu:17: the reference's test_baseline call site
+    (test-narrow-phase.cu:628-686) must find the names it calls."""
+    text = open(os.path.join(ROOT, "include", "robocheck_compat.hpp")).read()
+    for name in ("narrowPhaseBaseline(", "broadPhaseBaseline(", "narrowPhase(", "broadPhaseFused_sep(", "CallMegaKernel("):
+        assert name in text, name
+    import subprocess
+    out = subprocess.run(["nm", "-DC", os.path.join(ROOT, "robo-check_b200", "librobocheck.so")],
+                         capture_output=True, text=True).stdout
+    assert "narrowPhaseBaseline(" in out and "broadPhaseBaseline(" in out
