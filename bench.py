@@ -8,8 +8,14 @@ Workload (config.workload): BASELINE.json configs[1], "alpha1.0 hard_confs100,00
 near-contact configurations drawn like the reference's generator (Utils_rai.cu:111-136, 322-348;
 the shipped 100k file is a missing blob, so the set is regenerated with seed 508 + rank).  A
 "step" is one pass of the hot path over the batch.  With N GPUs every rank checks its own 100,000
-configurations (weak scaling) and the per-configuration validity bitmask is all-gathered over NCCL
-inside the timed region; value = all configurations of all ranks / max-over-ranks device time.
+configurations (weak scaling) and the per-configuration validity bitmask is gathered on every rank
+inside the timed region (by the check kernel itself over peer-mapped memory, or NCCL);
+value = all configurations of all ranks / max-over-ranks device time.
+
+Behind the headline the same run times the two north_star scaling workloads, ONE global set
+sharded over the N ranks (strong scaling): scale_c4 = BASELINE configs[3] (1 M configurations) and
+scale_c5 = configs[4] (10 M configurations against the 1,032,192-triangle obstacle, generated on
+the device per shard), each with the gather inside the timed region.
 
 Timing: CUDA events on the launching stream around every step, L2 flushed (256 MiB memset) before
 each timed step outside the event pair, barrier + synchronize on both sides of the K steps.
@@ -43,6 +49,14 @@ def parse():
                          "(rc_check_gather), or the NCCL all-gather; auto = peer when available")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip cpu_baseline / brute / stage rooflines (used by the ncu passes)")
+    ap.add_argument("--no-scale", action="store_true",
+                    help="skip the sharded C4 / C5 workloads (scale_c4, scale_c5)")
+    ap.add_argument("--preheat", type=float, default=1.2,
+                    help="seconds of untimed steps right before the timed ones (clock sampling)")
+    ap.add_argument("--c4", type=int, default=1_000_000, help=argparse.SUPPRESS)
+    ap.add_argument("--c5", type=int, default=10_000_000, help=argparse.SUPPRESS)
+    ap.add_argument("--c5-levels", type=int, default=5, help=argparse.SUPPRESS)
+    ap.add_argument("--scale-steps", type=int, default=3, help=argparse.SUPPRESS)
     return ap.parse_args()
 
 
@@ -180,6 +194,114 @@ def divert_stdout():
     os.dup2(2, 1)
 
 
+# executed floating-point work of the descent kernel, per counted event (FMA = 2; abs / negate are
+# operand modifiers; DESIGN 5.1 lists the operations behind each figure)
+FLOP_BOX_TEST = 78        # boxes_overlap: six axes
+FLOP_TRI_SETUP = 83       # robot triangle of a leaf round: three vertices transformed (63) + its plane (20)
+FLOP_TRI_BOX = 18         # triangle-box prefilter of one pair
+FLOP_PLANE_TEST = 24      # three signed distances + the straddle test
+FLOP_TAIL = 220           # a pair that passed both plane tests: transform, planes, distances, pair_tail
+
+
+def executed_flop(st):
+    return (FLOP_BOX_TEST * st["node_pairs"] + FLOP_TRI_SETUP * 4 * st["leaf_pairs"] +
+            FLOP_TRI_BOX * st["tri_pairs"] + FLOP_PLANE_TEST * (st["prefilter_pairs"] + st["plane1_pairs"]) +
+            FLOP_TAIL * st["tail_pairs"])
+
+
+class Sharded:
+    """One workload sharded over the ranks: every rank checks its contiguous shard, the validity
+    bitmask is gathered inside the check (rc_check_gather over peer-mapped memory) or, when symmetric
+    memory is not available, with one NCCL all-gather behind it."""
+
+    def __init__(self, rc, dist, ctx, dev, d_confs, n_local, words, world, rank, mode, stream, d_valid=None):
+        import torch
+        self.rc, self.dist, self.ctx, self.d_confs, self.n, self.words = rc, dist, ctx, d_confs, n_local, words
+        self.d_valid = d_valid   # optional flag bytes of the rank's own configurations, next to the bitmask
+        self.world, self.rank, self.stream = world, rank, stream
+        self.pg, self.note = None, "none"
+        self.d_gather = torch.zeros(world * words, dtype=torch.int32, device=dev)
+        self.d_mask = self.d_gather[rank * words:(rank + 1) * words]
+        if world > 1:
+            self.note = "all_gather of the validity bitmask (NCCL)"
+            if mode != "nccl":
+                try:
+                    from robocheck_b200 import sharding as sh
+                    self.pg = sh.PeerGather(rc, dist, dev, words)
+                except Exception as exc:
+                    self.pg = None
+                    print(f"[bench] rank {rank}: peer gather unavailable ({type(exc).__name__}: {exc})", file=sys.stderr)
+                okf = torch.tensor([1 if self.pg is not None else 0], device=dev)
+                dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+                if int(okf.item()) == 0:
+                    assert mode != "peer", "--gather peer: symmetric memory not available"
+                    self.pg = None
+                else:
+                    self.note = ("bitmask words stored into the peers' buffers over NVLink by the last CTA of the "
+                                 "check kernel (rc_check_gather, torch symmetric memory): no communicator call, "
+                                 "no extra launch")
+
+    def step(self):
+        if self.pg is not None:
+            return self.pg.check(self.ctx, self.d_confs, self.n, self.d_valid, self.stream)
+        if self.n > 0:
+            self.ctx.check(self.d_confs, self.n, self.d_valid, self.d_mask, self.rc.RC_MODE_CULLED, self.stream)
+        if self.world > 1:
+            self.dist.all_gather_into_tensor(self.d_gather, self.d_mask)
+        return self.d_gather
+
+    def verify_gather(self, mode):
+        """Untimed: the gathered bitmask of one step against an NCCL all-gather of the same words on every
+        rank; a peer gather that disagrees (or whose wait gave up) is not used for the timed steps."""
+        import torch
+        if self.world == 1:
+            return None
+        got = self.step().clone()
+        if self.n > 0:
+            self.ctx.check(self.d_confs, self.n, None, self.d_mask, self.rc.RC_MODE_CULLED, self.stream)
+        else:
+            self.d_mask.zero_()
+        self.dist.all_gather_into_tensor(self.d_gather, self.d_mask)
+        torch.cuda.synchronize()
+        good = torch.equal(got, self.d_gather) and self.ctx.stats()["watchdog"] == 0
+        same = torch.tensor([int(good)], device=got.device)
+        self.dist.all_reduce(same, op=self.dist.ReduceOp.MIN)
+        if int(same.item()) == 0 and self.pg is not None:
+            assert mode != "peer", "peer gather disagrees with the NCCL all-gather"
+            self.pg, self.note = None, "all_gather of the validity bitmask (NCCL; the peer gather failed its check)"
+            return "NCCL"
+        assert int(same.item()) == 1
+        return "gathered bitmask == NCCL all-gather on every rank"
+
+    def launches_per_step(self):
+        # kernels of ours: classify + descent (the gather rides in the descent's last CTA); an empty
+        # shard still pushes its slot with one small kernel
+        if self.n > 0:
+            return 2
+        return 1 if (self.pg is not None and self.world > 1) else 0
+
+
+def timed_steps(torch, dist, world, dev, stream, flush, fn, steps):
+    """K steps, CUDA events on the launching stream around each, L2 flushed before each outside the
+    event pair, barrier + synchronize on both sides; returns the max over ranks of the summed time (ms)."""
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    barrier()
+    for e0, e1 in evs:
+        flush.fill_(1)
+        e0.record(stream)
+        fn()
+        e1.record(stream)
+    barrier()
+    total = torch.tensor([sum(e0.elapsed_time(e1) for e0, e1 in evs)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total, op=dist.ReduceOp.MAX)
+    return float(total.item())
+
+
 def main():
     args = parse()
     divert_stdout()
@@ -191,6 +313,7 @@ def main():
     import torch.distributed as dist
 
     import robocheck_b200 as rc
+    from robocheck_b200 import sharding as sh
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -200,106 +323,68 @@ def main():
     if world > 1:
         import datetime
         dist.init_process_group("nccl", device_id=torch.device("cuda", local),
-                                timeout=datetime.timedelta(seconds=180))
+                                timeout=datetime.timedelta(seconds=300))
     dev = torch.device("cuda", local)
     n = args.confs
     words = (n + 31) // 32
-
-    ctx = rc.Context(device=local)
-    confs = rc.createAlphaBotConfigurations(n, True, 508 + rank)
-    d_confs = torch.from_numpy(confs).to(dev)
-    d_valid = torch.zeros(n, dtype=torch.uint8, device=dev)
-    # every rank's kernel writes its words straight into its slot of the gather buffer
-    d_gather = torch.zeros(world * words, dtype=torch.int32, device=dev)
-    d_mask = d_gather[rank * words:(rank + 1) * words]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream()
-
-    # N>1: the all-gather of the bitmask fused behind the check over peer-mapped memory (NVLink),
-    # falling back to the NCCL all-gather when symmetric memory is not available on the box
-    pg, gather_note = None, "none"
-    if world > 1:
-        gather_note = "all_gather of the validity bitmask (NCCL)"
-        if args.gather != "nccl":
-            try:
-                from robocheck_b200 import sharding as sh
-                pg = sh.PeerGather(rc, dist, dev, words)
-            except Exception as exc:
-                pg = None
-                print(f"[bench] rank {rank}: peer gather unavailable ({type(exc).__name__}: {exc})", file=sys.stderr)
-            okf = torch.tensor([1 if pg is not None else 0], device=dev)
-            dist.all_reduce(okf, op=dist.ReduceOp.MIN)
-            if int(okf.item()) == 0:
-                assert args.gather != "peer", "--gather peer: symmetric memory not available"
-                pg = None
-            else:
-                gather_note = ("bitmask words stored into the peers' buffers over NVLink by a kernel behind the "
-                               "check (rc_check_gather, torch symmetric memory), no communicator call")
-
-    def step():
-        if pg is not None:
-            return pg.check(ctx, d_confs, n, d_valid, stream)
-        ctx.check(d_confs, n, d_valid, d_mask, rc.RC_MODE_CULLED, stream)
-        if world > 1:
-            dist.all_gather_into_tensor(d_gather, d_mask)
-        return d_gather
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    ctx = rc.Context(device=local)
+    confs = rc.createAlphaBotConfigurations(n, True, 508 + rank)
+    d_confs = torch.from_numpy(confs).to(dev)
+    d_valid = torch.zeros(n, dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+
+    # ---- headline: BASELINE configs[1], every rank its own 100,000 (weak scaling) -------------------
+    head = Sharded(rc, dist, ctx, dev, d_confs, n, words, world, rank, args.gather, stream, d_valid)
     for _ in range(max(args.warmup, 3)):  # never fewer than three warm-up steps
-        step()
-    # untimed, before the timed steps: the gathered bitmask of one step against an NCCL all-gather of the
-    # same words; a peer gather that disagrees (or whose wait gave up) is not used for the timed steps
-    gather_check = None
-    if world > 1:
-        got = step().clone()
-        ctx.check(d_confs, n, d_valid, d_mask, rc.RC_MODE_CULLED, stream)
-        dist.all_gather_into_tensor(d_gather, d_mask)
-        torch.cuda.synchronize()
-        good = torch.equal(got, d_gather) and ctx.stats()["watchdog"] == 0
-        same = torch.tensor([int(good)], device=dev)
-        dist.all_reduce(same, op=dist.ReduceOp.MIN)
-        if int(same.item()) == 0 and pg is not None:
-            assert args.gather != "peer", "peer gather disagrees with the NCCL all-gather"
-            pg, gather_note = None, "all_gather of the validity bitmask (NCCL; the peer gather failed its check)"
-            gather_check = "NCCL"
-        else:
-            assert int(same.item()) == 1
-            gather_check = "gathered bitmask == NCCL all-gather on every rank"
+        head.step()
+    gather_check = head.verify_gather(args.gather)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-           for _ in range(args.steps)]
-    barrier()
-    for e0, e1 in evs:
-        flush.fill_(1)          # L2 flush, outside the event pair
-        e0.record(stream)
-        step()
-        e1.record(stream)
-    barrier()
-    ms = [e0.elapsed_time(e1) for e0, e1 in evs]
-    total_ms = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms.item())
+    # >= 1 s of the same steps, untimed, right before the timed ones: the device is at its working
+    # clocks and the clock sampler (100 ms period) sees more than a handful of samples under load
+    t_warm = time.perf_counter()
+    while time.perf_counter() - t_warm < args.preheat:
+        for _ in range(50):
+            head.step()
+        torch.cuda.synchronize()
+    total_ms = timed_steps(torch, dist, world, dev, stream, flush, head.step, args.steps)
     value = world * n * args.steps / (total_ms * 1e-3)
-    # kernels of ours per step: classify + descent (+ the gather push at N>1); memsets and NCCL are not ours
-    launches = (3 if pg is not None else 2) * args.steps
+    launches = head.launches_per_step() * args.steps
+
     # ---- end to end: host buffers in, host flags out, through the public host call ---------------
     h_confs = torch.from_numpy(confs).pin_memory()
     h_valid = torch.zeros(n, dtype=torch.uint8).pin_memory()
     np_confs, np_valid = h_confs.numpy(), h_valid.numpy()
     lib = rc.lib()
+    e2e_api = "rc_check_host (pinned host buffers)"
+    h_mask_all = torch.zeros(world * words, dtype=torch.int32).pin_memory()
+    d_stage = torch.empty(n * 6, dtype=torch.float32, device=dev)
+    h_flat = h_confs.view(-1)
 
-    def e2e_step():
-        code = lib.rc_check_host(ctx._h, np_confs.ctypes.data, n, np_valid.ctypes.data, rc.RC_MODE_CULLED)
-        assert code == 0
+    if world > 1 and head.pg is not None:
+        # N > 1: the call a rank of a sharded job makes -- host configurations in, the gathered bitmask
+        # of ALL ranks back in host memory; the collective is inside the timed region
+        e2e_api = ("sharding.PeerGather.check_host: H2D of the rank's configurations, rc_check_gather, D2H of "
+                   "the gathered bitmask of all ranks")
+        d2h_bytes = world * words * 4
+
+        def e2e_step():
+            head.pg.check_host(ctx, h_flat, d_stage, n, h_mask_all, stream)
+    else:
+        d2h_bytes = n
+
+        def e2e_step():
+            code = lib.rc_check_host(ctx._h, np_confs.ctypes.data, n, np_valid.ctypes.data, rc.RC_MODE_CULLED)
+            assert code == 0
 
     for _ in range(3):
         e2e_step()
@@ -311,14 +396,21 @@ def main():
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            e2e_step()   # synchronous: returns when the flags are in host memory
+            e2e_step()   # synchronous: returns when the result is in host memory
         barrier()
         e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
         e2e_runs.append(float(e2e_s.item()))
     e2e_value = world * n * args.steps / sorted(e2e_runs)[1]
-    assert np.array_equal(np_valid, d_valid.cpu().numpy())
+    ctx.check(d_confs, n, d_valid, None, rc.RC_MODE_CULLED, stream)
+    torch.cuda.synchronize()
+    gpu_flags_now = d_valid.cpu().numpy()
+    if world > 1 and head.pg is not None:
+        mine = sh.unpack_bitmask(h_mask_all.numpy()[rank * words:(rank + 1) * words], words * 32)[:n]
+        assert np.array_equal(mine, gpu_flags_now), "end-to-end gathered bitmask != device-resident flags"
+    else:
+        assert np.array_equal(np_valid, gpu_flags_now)
     # the same K host batches through the pipelined calls (planner loop: batch k+1 is submitted before the
     # flags of batch k are read, its copy overlaps the kernels of batch k); every step still moves its
     # inputs host->device and its flags device->host inside the timed region.  Reported next to e2e,
@@ -342,10 +434,64 @@ def main():
         if world > 1:
             dist.all_reduce(pipe_s, op=dist.ReduceOp.MAX)
         pipe_runs.append(float(pipe_s.item()))
-    gpu_flags_now = d_valid.cpu().numpy()
     assert all(np.array_equal(o, gpu_flags_now) for o in outs[:min(2, args.steps)])
     e2e_pipelined = world * n * args.steps / sorted(pipe_runs)[1]
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---- north_star scaling workloads: ONE global set sharded over the ranks (strong scaling) -----
+    scale = {}
+    if not args.no_scale:
+        # C4: BASELINE configs[3], 1 M configurations of the reference's sampler, seed 510
+        n4 = args.c4
+        lo, hi, per = sh.shard_bounds(n4, world, rank)
+        all4 = rc.createAlphaBotConfigurations(n4, False, 510)
+        d4 = torch.from_numpy(np.ascontiguousarray(all4[lo:hi])).to(dev) if hi > lo else torch.zeros(6, device=dev)
+        run4 = Sharded(rc, dist, ctx, dev, d4, hi - lo, per // 32, world, rank, args.gather, stream)
+        for _ in range(3):
+            run4.step()
+        chk4 = run4.verify_gather(args.gather)
+        ms4 = timed_steps(torch, dist, world, dev, stream, flush, run4.step, args.scale_steps)
+        bits4 = sh.unpack_bitmask(run4.step().cpu().numpy(), world * per)[:n4]
+        scale["scale_c4"] = {
+            "workload": f"BASELINE configs[3]: alpha1.0, {n4} configurations of the reference's sampler (seed 510), "
+                        f"contiguous shards of {per}, bitmask gathered on every rank",
+            "value": n4 * args.scale_steps / (ms4 * 1e-3), "unit": "configs/s", "ms": ms4 / args.scale_steps,
+            "n_total": n4, "steps": args.scale_steps, "scaling": "strong", "collective": run4.note,
+            "collective_check": chk4, "valid_fraction": float(bits4.mean()),
+            "gpu_launches": run4.launches_per_step() * args.scale_steps}
+        launches += run4.launches_per_step() * args.scale_steps
+        del all4, d4, run4
+        # C5: BASELINE configs[4], robot vs the obstacle subdivided five times (1,032,192 triangles),
+        # 10 M configurations, nine blocks of 1,024 "easy" then one "hard" (SURVEY 8d), generated on
+        # the device per shard: no 240 MB host-to-device copy anywhere
+        n5 = args.c5
+        rob_m, obs_m = rc.alpha_meshes()
+        t0 = time.perf_counter()
+        obs5 = obs_m.subdivide(args.c5_levels)
+        ctx5 = rc.Context(rob_m, obs5, device=local)
+        build5 = time.perf_counter() - t0
+        lo, hi, per = sh.shard_bounds(n5, world, rank)
+        cnt5 = hi - lo
+        d5 = torch.empty(max(cnt5, 1) * 6, dtype=torch.float32, device=dev)
+        ctx5.generate_device_mix(d5, lo, cnt5, rc.alpha_box(False), rc.alpha_box(True), 1024, 10, 511, stream)
+        run5 = Sharded(rc, dist, ctx5, dev, d5, cnt5, per // 32, world, rank, args.gather, stream)
+        run5.step()
+        chk5 = run5.verify_gather(args.gather)
+        ms5 = timed_steps(torch, dist, world, dev, stream, flush, run5.step, args.scale_steps)
+        bits5 = sh.unpack_bitmask(run5.step().cpu().numpy(), world * per)[:n5]
+        scale["scale_c5"] = {
+            "workload": f"BASELINE configs[4]: alpha1.0 robot vs obstacle subdivided x{args.c5_levels} "
+                        f"({obs5.n_t} triangles, tables in global memory), {n5} configurations generated on the "
+                        "device per shard (blocks of 1,024: nine easy, one hard; seed 511), bitmask gathered",
+            "value": n5 * args.scale_steps / (ms5 * 1e-3), "unit": "configs/s", "ms": ms5 / args.scale_steps,
+            "n_total": n5, "steps": args.scale_steps, "scaling": "strong", "collective": run5.note,
+            "collective_check": chk5, "valid_fraction": float(bits5.mean()),
+            "context_build_s": build5, "gpu_launches": run5.launches_per_step() * args.scale_steps}
+        launches += run5.launches_per_step() * args.scale_steps
+        watchdog5 = ctx5.stats()["watchdog"]
+        del run5, d5
+        ctx5.close()
+        assert watchdog5 == 0
 
     if world > 1:
         # every rank leaves the group here, after the last collective of the timed regions
@@ -363,6 +509,7 @@ def main():
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     fp32_peak = ctx.fp32_peak_tflops()
+    d_mask = torch.zeros(words, dtype=torch.int32, device=dev)
     ctx.stats_enable(True)
     ctx.stats(reset=True)
     # rank 0 only from here on: the kernel alone, never the collective
@@ -370,43 +517,64 @@ def main():
     st = ctx.stats(reset=True)
     ctx.stats_enable(False)
     step_s = total_ms * 1e-3 / args.steps
-    # algorithmic work of one launch: 19,008 flop per configuration for transform +
-    # AABB, 18 flop per decided triangle pair; a narrow-phase configuration found valid decides
-    # all 1008 x 1008 pairs, a colliding one is counted with a single pair.
+    # EXECUTED work of one launch, from the kernel's own counters (statistics build, same workload):
+    # box tests, robot triangles set up in leaf rounds, triangle-box tests, plane tests, finished pairs
+    exe_flop = executed_flop(st)
+    # algorithmic work of the reference formulation: 19,008 flop per configuration for
+    # transform + AABB, 18 flop per decided triangle pair; a narrow-phase configuration found valid
+    # decides all 1008 x 1008 pairs, a colliding one is counted with a single pair
     decided = st["narrow_valid"] * PAIRS_PER_CONFIG + st["narrow_invalid"]
     alg_flop = 19008.0 * n + 18.0 * decided
-    roofline = {
-        "kernel": "check_culled_kernel", "bound": "fp32",
-        "achieved": alg_flop / step_s / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
-        "frac": alg_flop / step_s / 1e12 / fp32_peak, "traffic": None,
-        "peak_source": "FP32 FMA rate measured live by rc_measure_fp32_peak (MEASURED_PEAKS.json "
-                       "has no FP32 entry)",
-        "note": "algorithmic flops of the reference formulation (18 flop x every decided pair); "
-                "BVH culling decides most pairs without touching them, so frac > 1 is expected - "
-                "see roofline_brute for the un-culled kernel and profiles/ for the ncu pipe view",
-        "executed": {k: st[k] for k in ("node_pairs", "leaf_pairs", "tri_pairs", "overflow")},
-        "mix": {k: st[k] for k in ("broad_cleared", "sphere_cleared", "narrow_valid", "narrow_invalid")},
-    }
     # hardware view of the same kernels from the committed ncu capture (not live; profiles/)
-    prof = {}
-    try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_r01_metrics.json")))
-    except (OSError, ValueError):
-        pass
+    prof, prof_name = {}, None
+    for name in ("ncu_r02_metrics.json", "ncu_r01_metrics.json"):
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", name)))
+            prof_name = name
+            break
+        except (OSError, ValueError):
+            continue
 
     def hw_view(kernel):
         p = prof.get(kernel)
         if not p:
             return None
-        return {"source": "profiles/ncu_r01_summary.md (ncu --set full, same kernel, not live)",
+        return {"source": f"profiles/{prof_name} (ncu --set full, same kernel, not live)",
                 "issue_slots_busy_pct": p.get("issue_active_pct"), "fma_pipe_pct": p.get("fma_pipe_pct"),
                 "alu_pipe_pct": p.get("alu_pipe_pct"), "dram_throughput_pct": p.get("dram_throughput_pct"),
-                "lanes_per_instruction": p.get("lanes_per_instruction")}
+                "lanes_per_instruction": p.get("lanes_per_instruction"),
+                "warp_instructions": p.get("inst_executed"),
+                "shared_bank_conflict_share": p.get("bank_conflict_share")}
 
+    sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+    roofline = {
+        "kernel": "check_culled_kernel", "bound": "fp32",
+        "achieved": exe_flop / step_s / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+        "frac": exe_flop / step_s / 1e12 / fp32_peak, "traffic": None,
+        "peak_source": "FP32 FMA rate measured live by rc_measure_fp32_peak (MEASURED_PEAKS.json "
+                       "has no FP32 entry)",
+        "note": "EXECUTED flops of one launch (device counters of the statistics build x flop per event, "
+                "bench.py FLOP_*) over the event-timed step; the kernel is bound by instruction issue on "
+                "non-FP work (queues, votes, shared-memory gathers), see hw and issue",
+        "executed": {k: st[k] for k in ("node_pairs", "leaf_pairs", "tri_pairs", "prefilter_pairs",
+                                        "plane1_pairs", "tail_pairs", "overflow")},
+        "executed_gflop": exe_flop / 1e9,
+        "work_avoided_x": alg_flop / max(exe_flop, 1.0),
+        "algorithmic_tflops_reference_formulation": alg_flop / step_s / 1e12,
+        "mix": {k: st[k] for k in ("broad_cleared", "sphere_cleared", "narrow_valid", "narrow_invalid")},
+    }
     if prof.get("check_culled_kernel"):
-        roofline["traffic"] = prof["check_culled_kernel"].get("dram_bytes")
+        pk = prof["check_culled_kernel"]
+        roofline["traffic"] = pk.get("dram_bytes")
         roofline["traffic_unit"] = "bytes per launch (ncu dram__bytes_read+write, 100,000 configurations)"
         roofline["hw"] = hw_view("check_culled_kernel")
+        if pk.get("inst_executed"):
+            sms = peaks.get("sm_count", 148)
+            roofline["issue"] = {
+                "warp_instructions_per_launch": pk["inst_executed"],
+                "frac_of_issue_slots": pk["inst_executed"] / (sms * 4 * sm_mhz * 1e6 * step_s),
+                "note": "ncu smsp__inst_executed.sum of the committed capture / (SMs x 4 schedulers x SM clock "
+                        "x live step time)"}
     out = {
         "metric": "collision-checked configs/sec", "value": value, "unit": "configs/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -414,9 +582,10 @@ def main():
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "configs_per_gpu": n, "mode": "culled fused kernel",
                    "l2": "flushed before every timed step (256 MiB fill, outside the event pair)",
-                   "collective": gather_note, "collective_check": gather_check},
+                   "preheat_s": args.preheat,
+                   "collective": head.note, "collective_check": gather_check},
         "e2e": {"value": e2e_value, "unit": "configs/s", "h2d_bytes_per_step": n * 24,
-                "d2h_bytes_per_step": n, "api": "rc_check_host (pinned host buffers)",
+                "d2h_bytes_per_step": d2h_bytes, "api": e2e_api,
                 "timing": "median of 3 runs of K synchronous steps each (wall clock, max over ranks)",
                 "runs_configs_per_s": [world * n * args.steps / t for t in e2e_runs],
                 "pipelined": {"value": e2e_pipelined, "unit": "configs/s",
@@ -426,6 +595,7 @@ def main():
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
         "valid_fraction": float(d_valid.float().mean().item()),
     }
+    out.update(scale)
 
     if not args.no_extras and world == 1:
         # un-culled kernel on a bounded sample: the FP32-bound formulation of SURVEY 8(d)
@@ -491,11 +661,49 @@ def main():
                       "descent + the reference's per-pair arithmetic (stand-in for FCL's BVH path)",
             "single_core_value": n1 / dt_one,
             "single_core_sample": f"first {n1} configurations, {dt_one:.2f} s"}
+        out["vs_cpu_tree"] = {"device_resident_x": value / (n / dt_all), "e2e_x": e2e_value / (n / dt_all),
+                              "note": "value and e2e.value over cpu_baseline_tree.value (same box, all host cores)"}
+        out["vs_cpu_reference_brute_force"] = {
+            "device_resident_x": value / out["cpu_baseline"]["value"], "e2e_x": e2e_value / out["cpu_baseline"]["value"],
+            "note": "over cpu_baseline.value: the reference's narrowPhaseBaseline, an exhaustive sweep -- a weak "
+                    "comparator, quoted because it is the reference's own CPU code"}
+        out["fcl"] = {
+            "available": False,
+            "reason": "FCL, libccd and Eigen are not installed in this image and cannot be installed (no network); "
+                      "the 100 k and 1 M sets therefore carry no FCL verdicts, only the two shipped 10 k sets do "
+                      "(frozen tags, 0 disagreements of 20,000 in tests/)",
+            "published_other_hardware": {"value": 206600.0, "unit": "configs/s", "what": "FCL -O3, hard 100 k, one "
+                                         "core of an i7-8700K (BASELINE.md)"},
+            "vs_published_x": {"device_resident": value / 206600.0, "e2e": e2e_value / 206600.0},
+            "stand_ins_same_box": ["cpu_baseline (reference brute force, all cores)",
+                                   "cpu_baseline_tree (tree-culled CPU checker, all cores)"]}
+        # parity of the timed workload against checkers that do NOT share the kernel's culling:
+        # the exhaustive kernel, and the unmodified reference pipeline run on this GPU
         ctx.check(d_confs, n, d_valid, d_mask, rc.RC_MODE_CULLED, stream); torch.cuda.synchronize()
         gpu_flags = d_valid.cpu().numpy()
-        out["parity"] = {"checker": "oracle/oracle_bvh.c (CPU), every configuration of the workload",
-                         "configs": n, "flag_mismatches": int((gpu_flags != cpu_flags).sum()),
-                         "e2e_flag_mismatches": int((np_valid != cpu_flags).sum())}
+        ctx.check(d_confs, n, d_valid, None, rc.RC_MODE_BRUTE, stream); torch.cuda.synchronize()
+        brute_flags = d_valid.cpu().numpy()
+        parity = {"checker": "oracle/oracle_bvh.c (CPU, tree-culled), every configuration of the workload",
+                  "configs": n, "flag_mismatches": int((gpu_flags != cpu_flags).sum()),
+                  "e2e_flag_mismatches": int((np_valid != cpu_flags).sum()),
+                  "brute_flag_mismatches": int((gpu_flags != brute_flags).sum()),
+                  "brute_checker": "RC_MODE_BRUTE: every one of the 1008 x 1008 pairs of every configuration"}
+        d_cnt = torch.zeros(n, dtype=torch.int32, device=dev)
+        nf, nc, _ = ctx.audit(d_confs, n, cap=0)
+        parity["audit"] = {"flags_differ": nf, "hit_pair_counts_differ": nc,
+                           "what": "rc_audit: culled vs exhaustive, flags and per-configuration hitting-pair counts"}
+        del d_cnt
+        if po.ref_available():
+            try:
+                from tests import refpipe
+                t0 = time.perf_counter()
+                ref_flags = refpipe.oracle_gpu_flags(rc, po, confs)
+                parity["reference_gpu_flag_mismatches"] = int((gpu_flags != ref_flags).sum())
+                parity["reference_gpu_checker"] = ("broadPhaseFused_sep of the unmodified reference (oracle/_ref), "
+                                                   f"run on this GPU: {time.perf_counter() - t0:.1f} s")
+            except Exception as exc:  # the checker is optional evidence, never the product
+                parity["reference_gpu_checker"] = f"failed: {type(exc).__name__}: {exc}"
+        out["parity"] = parity
 
     emit(out)
 

@@ -172,6 +172,16 @@ int rc_obstacle_tri_aabbs(const rc_ctx *ctx, rc_aabb *h_out);
 int rc_conf_generate_device(rc_ctx *ctx, rc_config *d_out, long n, float x_min, float x_max,
                             float y_min, float y_max, float z_min, float z_max, uint64_t seed,
                             void *stream);
+/* The same generator for ONE global set produced in pieces (one piece per rank, BASELINE config 5:
+ * 10 M configurations, no 240 MB host-to-device copy): configuration i of this call is number
+ * first + i of the set, so every split of the set over calls or ranks yields the same
+ * configurations.  Blocks of `block` consecutive configurations whose block number is period - 1
+ * modulo period are drawn from box_b, all others from box_a (period 0: box_a only); boxes are
+ * {x_min, x_max, y_min, y_max, z_min, z_max}.  rc_alpha_box gives the reference's two boxes
+ * (createAlphaBotConfigurations, Utils_rai.cu:111-136: hard = +-range/200, easy = +-10*range). */
+int rc_conf_generate_device_mix(rc_ctx *ctx, rc_config *d_out, long first, long n, const float *box_a,
+                                const float *box_b, int block, int period, uint64_t seed, void *stream);
+int rc_alpha_box(int hard, float box[6]);
 /* Order-preserving compaction: indices i < n whose flag equals `want` (1 = valid), ascending, and
  * their count.  Flags come from d_bitmask if it is not NULL, else from d_valid.  d_indices needs
  * room for n entries; d_count is one device word.  Asynchronous. */
@@ -290,6 +300,9 @@ typedef struct {
     unsigned long long watchdog, watchdog_where; /* waits that gave up: must be 0.  Inside the check kernels a
                                                   * give-up costs parallelism only, never a flag; a gather wait
                                                   * that gave up (bit 3) left *d_result incomplete */
+    /* leaf rounds of RC_MODE_CULLED: of the tri_pairs looked at, those whose triangle boxes overlap, and
+     * those that then pass the first plane test (tail_pairs pass both) */
+    unsigned long long prefilter_pairs, plane1_pairs;
 } rc_stats;
 /* Statistics of rc_check calls since the last reset; counting is off by default. */
 int rc_stats_enable(rc_ctx *ctx, int on);

@@ -52,6 +52,11 @@ int rco_pair_hits(const float r[9], const float o[9], int variant, int *coplanar
 
 int rco_check(const rco_mesh *rob, const rco_mesh *obs, const rco_config *confs, long n,
               int variant, int nthreads, int early_exit, uint8_t *valid, rco_stats *stats);
+/* No early exit: counts[i] = pairs of configuration i the reference arithmetic reports. */
+int rco_check_counts(const rco_mesh *rob, const rco_mesh *obs, const rco_config *confs, long n,
+                     int variant, int nthreads, uint8_t *valid, uint32_t *counts);
+/* la_solve with the FMA placement of the CUDA kernel (the GPU variant's; rco_la_solve is the host's) */
+void rco_la_solve_gpu(float A1, float A2, float A3, float A4, float b1, float b2, float *x1, float *x2);
 /* Same flags as rco_check (early exit), pairs enumerated by a dual-tree descent (oracle_bvh.c):
  * whole BASELINE-size sets in seconds.  In its statistics pairs_stage1 counts box pairs tested
  * and pairs_full triangle pairs decided. */

@@ -73,6 +73,63 @@ def check(rob, obs, confs, variant=VARIANT_GPU, nthreads=None, early_exit=True, 
     return valid
 
 
+def check_counts(rob, obs, confs, variant=VARIANT_GPU, nthreads=None):
+    """(flags, hitting pairs per configuration): the exhaustive sweep without its early exit."""
+    confs = _f(confs).reshape(-1, 6)
+    valid = np.zeros(len(confs), np.uint8)
+    counts = np.zeros(len(confs), np.uint32)
+    rc = lib().rco_check_counts(C.byref(rob.c), C.byref(obs.c), _p(confs), C.c_long(len(confs)), variant,
+                                nthreads or os.cpu_count() or 1, _p(valid), _p(counts))
+    assert rc == 0
+    return valid, counts
+
+
+def pair_intermediates(r9, o9):
+    """Every intermediate of the GPU variant for one pair, laid out like rc_kat_pairs' 32 floats,
+    and the verdict word (plane test O | plane test R << 1 | tail << 2; tail 0 miss, 1 hit, 2 coplanar)."""
+    L = lib()
+    F3, F9 = C.c_float * 3, C.c_float * 9
+    r, o = F9(*_f(r9)), F9(*_f(o9))
+    out = np.zeros(32, np.float32)
+    Nr, No, dO, dR, D, O = F3(), F3(), F3(), F3(), F3(), F3()
+    dr, do_ = C.c_float(), C.c_float()
+    L.rco_plane(r, 1, Nr, C.byref(dr))
+    L.rco_plane(o, 1, No, C.byref(do_))
+    L.rco_signed_dists(Nr, dr, o, 1, dO)
+    L.rco_signed_dists(No, do_, r, 1, dR)
+    out[0:3], out[3], out[4:7] = list(Nr), dr.value, list(dO)
+    out[7:10], out[10], out[11:14] = list(No), do_.value, list(dR)
+    sO, sR = int(not L.rco_no_overlap(dO, 1)), int(not L.rco_no_overlap(dR, 1))
+    tail = 0
+    if sO and sR:
+        if L.rco_is_coplanar(Nr, dr, No, do_):
+            tail = 2
+        else:
+            L.rco_intersect_line(Nr, dr, No, do_, 1, D, O)
+            ri, oi = (C.c_int * 3)(), (C.c_int * 3)()
+            L.rco_canonicalize(dR, ri)
+            L.rco_canonicalize(dO, oi)
+            rv = np.asarray(_f(r9)).reshape(3, 3)
+            ov = np.asarray(_f(o9)).reshape(3, 3)
+
+            def param(v, idx, d, a, b):
+                return L.rco_param(F3(*v[idx[a]]), F3(*v[idx[b]]), C.c_float(d[idx[a]]), C.c_float(d[idx[b]]), D, O, 1)
+
+            t = [param(rv, ri, dR, 0, 1), param(rv, ri, dR, 1, 2), param(ov, oi, dO, 0, 1), param(ov, oi, dO, 1, 2)]
+            out[14:17], out[17:20], out[20:24] = list(D), list(O), t
+            tail = 1
+            with np.errstate(invalid="ignore"):
+                if min(t[0], t[1]) >= max(t[2], t[3]) or min(t[2], t[3]) >= max(t[0], t[1]):
+                    tail = 0
+    return out, sO | (sR << 1) | (tail << 2)
+
+
+def la_solve_gpu(A1, A2, A3, A4, b1, b2):
+    x1, x2 = C.c_float(), C.c_float()
+    lib().rco_la_solve_gpu(*(C.c_float(v) for v in (A1, A2, A3, A4, b1, b2)), C.byref(x1), C.byref(x2))
+    return x1.value, x2.value
+
+
 def check_bvh(rob, obs, confs, variant=VARIANT_GPU, nthreads=None, want_stats=False):
     """Same flags as check(), pairs enumerated by a dual-tree descent (oracle_bvh.c): fast enough for
     the full BASELINE sizes."""

@@ -13,8 +13,13 @@ launches)
 full)
   python profiles/prof_driver.py all > gpurun_out/plain.log 2>&1 &&
   ncu --set full --clock-control none --import-source on \
-      -k regex:"classify|check_culled|check_brute|transform_soa|transform_aos|aabb_|narrow_soa|broad_kernel" -c 18 \
+      -k regex:"classify|check_culled|check_brute|check_spheres|transform_soa|transform_aos|aabb_|narrow_soa|broad_kernel|gather_|compact_|conf_generate" -c 60 \
       -o gpurun_out/prof_full python profiles/prof_driver.py all > gpurun_out/ncu_full.log 2>&1
+  ;;
+one)  # collect.sh one <driver mode> <kernel regex> <count>: one kernel family, e.g. `one gobs check_culled 3`
+  python profiles/prof_driver.py $2 > gpurun_out/plain.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:"$3" -c ${4:-3} \
+      -o gpurun_out/prof_$2 python profiles/prof_driver.py $2 > gpurun_out/ncu_$2.log 2>&1
   ;;
 esac
 tail -n 3 gpurun_out/*.log

@@ -55,7 +55,8 @@ class rc_stats(C.Structure):
     _fields_ = [(k, C.c_ulonglong) for k in (
         "broad_cleared", "sphere_cleared", "narrow_valid", "narrow_invalid", "node_pairs",
         "leaf_pairs", "tri_pairs", "tail_pairs", "overflow", "launches", "node_rounds",
-        "leaf_rounds", "tail_rounds", "shared_pieces", "watchdog", "watchdog_where")]
+        "leaf_rounds", "tail_rounds", "shared_pieces", "watchdog", "watchdog_where", "prefilter_pairs",
+        "plane1_pairs")]
 
 
 # every symbol include/robocheck.h declares: (name, restype, argtypes)
@@ -97,6 +98,8 @@ ABI = [
     ("rc_megakernel", _i, [_vp, _vp, _vp, _vp, _vp, _i, _vp]),
     ("rc_obstacle_tri_aabbs", _i, [_vp, _vp]),
     ("rc_conf_generate_device", _i, [_vp, _vp, _l] + [_f] * 6 + [C.c_uint64, _vp]),
+    ("rc_conf_generate_device_mix", _i, [_vp, _vp, _l, _l, _vp, _vp, _i, _i, C.c_uint64, _vp]),
+    ("rc_alpha_box", _i, [_i, _vp]),
     ("rc_compact", _i, [_vp, _vp, _vp, _l, _i, _vp, _vp, _vp]),
     ("rc_set_robot_spheres", _i, [_vp, _vp, _i]),
     ("rc_robot_spheres", _i, [_vp, _vp, C.POINTER(_i)]),
@@ -137,6 +140,8 @@ def _load():
             "g.build()'` or `make -C robo-check_b200`.  There is no CPU fallback.")
     lib = C.CDLL(LIB_PATH)
     for name, res, args in ABI:
+        if os.environ.get("RC_LIB") and not hasattr(lib, name):
+            continue  # an older build under A/B comparison (profiles/tools): newer entry points are absent
         fn = getattr(lib, name)  # AttributeError here = the library does not export the ABI
         fn.restype = res
         fn.argtypes = args
@@ -359,6 +364,13 @@ def generateConfs(n, x_min, x_max, y_min, y_max, z_min, z_max, seed):
     return out
 
 
+def alpha_box(hard):
+    """The reference's sampling box of createAlphaBotConfigurations (x_min, x_max, y_min, ...)."""
+    out = np.zeros(6, np.float32)
+    _check(_lib.rc_alpha_box(1 if hard else 0, _ptr(out)))
+    return out
+
+
 def createAlphaBotConfigurations(n, hard, seed):
     """Utils_rai.cu:111-136 with an explicit seed."""
     out = np.zeros((n, 6), np.float32)
@@ -539,6 +551,13 @@ class Context:
     def generate_device(self, d_out, n, box, seed, stream=None):
         _check(_lib.rc_conf_generate_device(self._h, _ptr(d_out), int(n), *[float(v) for v in box],
                                             int(seed), _stream_ptr(stream)), self._h)
+
+    def generate_device_mix(self, d_out, first, n, box_a, box_b=None, block=1024, period=0, seed=0, stream=None):
+        """rc_conf_generate_device_mix: configurations first .. first + n - 1 of one global set."""
+        a = np.ascontiguousarray(box_a, dtype=np.float32)
+        b = np.ascontiguousarray(box_b if box_b is not None else box_a, dtype=np.float32)
+        _check(_lib.rc_conf_generate_device_mix(self._h, _ptr(d_out), int(first), int(n), _ptr(a), _ptr(b),
+                                                int(block), int(period), int(seed), _stream_ptr(stream)), self._h)
 
     def compact(self, n, d_indices, d_count, d_valid=None, d_bitmask=None, want=1, stream=None):
         _check(_lib.rc_compact(self._h, _ptr(d_valid), _ptr(d_bitmask), int(n), int(want),

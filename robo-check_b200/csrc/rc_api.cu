@@ -457,6 +457,7 @@ int rc_create(rc_ctx **out, const float *rob_x, const float *rob_y, const float 
             (e = dev_alloc(ctx, &ctx->d_counters, RC_NUM_COUNTERS)) ||
             (e = dev_alloc(ctx, &ctx->d_queues, kHostChunks)) ||
             (e = dev_alloc(ctx, &ctx->d_work_count, kWorkCounters)) ||
+            (e = dev_alloc(ctx, &ctx->d_gmail, kGMailBytes)) ||
             (e = dev_alloc(ctx, &ctx->d_obs_box, 1)) ||
             (e = cudaMemcpy(ctx->d_obs_box, &t.obs_box, sizeof(rc_aabb), cudaMemcpyHostToDevice))) {
             rcode = check_cuda(ctx, e, "table upload");
@@ -1052,6 +1053,18 @@ int rc_conf_generate_device(rc_ctx *ctx, rc_config *d_out, long n, float x_min, 
                       "rc_conf_generate_device");
 }
 
+int rc_conf_generate_device_mix(rc_ctx *ctx, rc_config *d_out, long first, long n, const float *box_a,
+                                const float *box_b, int block, int period, uint64_t seed, void *stream)
+{
+    if (!ctx || n < 0 || first < 0 || (n > 0 && !d_out) || !box_a || period < 0 || (period > 0 && (!box_b || block <= 0)))
+        return RC_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    ctx->launches++;
+    return check_cuda(ctx, launch_conf_generate_mix(d_out, first, n, box_a, box_b ? box_b : box_a, block, period,
+                                                    seed, stream_of(ctx, stream)),
+                      "rc_conf_generate_device_mix");
+}
+
 int rc_compact(rc_ctx *ctx, const uint8_t *d_valid, const uint32_t *d_bitmask, long n, int want,
                uint32_t *d_indices, unsigned long long *d_count, void *stream)
 {
@@ -1197,6 +1210,9 @@ int rc_hit_counts(rc_ctx *ctx, const rc_config *d_confs, long n, int mode, uint8
         if (r2 != RC_OK) return r2;
         flags = ctx->d_stage_valid;
     }
+    // configurations the cheap bounds of step 1 clear never reach the counting kernel: their count is 0
+    const cudaError_t e = cudaMemsetAsync(d_counts, 0, (size_t)n * sizeof(uint32_t), s);
+    if (e != cudaSuccess) return check_cuda(ctx, e, "rc_hit_counts memset");
     rc::CheckExtras x;
     x.hit_counts = d_counts;
     return check_on_stream(ctx, d_confs, n, flags, nullptr, mode, s, &x, "rc_hit_counts launch");
@@ -1334,6 +1350,7 @@ int rc_stats_read(rc_ctx *ctx, rc_stats *out, int reset)
     out->tail_rounds = h[CNT_TAIL_ROUNDS];
     out->shared_pieces = h[CNT_SHARED];
     out->watchdog = h[CNT_WATCHDOG]; out->watchdog_where = h[CNT_WATCHDOG_WHERE];
+    out->prefilter_pairs = h[CNT_PREFILTER]; out->plane1_pairs = h[CNT_PLANE1];
     if (reset) {
         ctx->launches = 0;
         if ((e = cudaMemset(ctx->d_counters, 0, sizeof h))) return check_cuda(ctx, e, "rc_stats reset");

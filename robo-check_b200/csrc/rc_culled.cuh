@@ -53,6 +53,28 @@ struct __align__(16) Mail {
     uint32_t kind;       // 0 node pairs, 1 leaf pairs, 2 triangle pairs for the tail
 };
 
+// Mail between CTAs (production kernels): once the work list is dry, a warp with a deep descent whose
+// own CTA has no free slot left hands a piece to a slot in GLOBAL memory, and warps of CTAs that have
+// run out of work pick it up -- every CTA holds the same tables, so any warp of the grid can work on
+// any piece.  Pieces never report back (the flags are written optimistically: valid first, whoever
+// finds a hit overwrites), so the protocol is a one-way hand-over: state 0 empty, 1 being filled,
+// 2 full, 3 being emptied.  `idle` counts the CTAs of the grid whose warps are all polling for work;
+// when it reaches the number of CTAs nobody can produce work any more and everybody leaves.
+constexpr int kGMailSlots = 64;
+struct __align__(16) GMailRec {
+    float4 m[3];
+    uint32_t pairs[32];
+    uint32_t conf, cnt, kind, pad;
+};
+struct GMailBox {
+    uint32_t state[kGMailSlots];
+    uint32_t idle;
+    uint32_t pad[63];
+    GMailRec rec[kGMailSlots];
+};
+static_assert(sizeof(GMailBox) <= kGMailBytes, "rc_create allocates kGMailBytes for the mail box");
+constexpr int kNarrowPop = 192;  // node pairs of head room below which a node round pops one pair instead of 32
+
 __device__ __forceinline__ uint32_t ld_volatile(const uint32_t *p) { return *(const volatile uint32_t *)p; }
 __device__ __forceinline__ void st_volatile(uint32_t *p, uint32_t v) { *(volatile uint32_t *)p = v; }
 
@@ -86,6 +108,7 @@ struct CulledArgs {
     uint32_t seed_r3[8], seed_o3[8];
     int n_seed_r3, n_seed_o3;
     uint32_t *hit_counts;            // STATS kernels: hitting pairs per configuration, no early exit (rc_hit_counts)
+    GMailBox *gmail;                 // production kernels: hand-over between CTAs (zero outside a launch)
     GatherArgs g;                    // g.world > 1: the last CTA pushes the bitmask slot to the peers (rc_gather.cuh)
 };
 
@@ -330,8 +353,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
     Mail *s_mail = reinterpret_cast<Mail *>(s_work + WARPS * kWarpWork);
     uint32_t *s_pend = reinterpret_cast<uint32_t *>(s_mail + kMailSlots);
     uint32_t *s_idle = s_pend + WARPS;
-    uint32_t *s_misc = s_idle + 1;   // [0] split shift  [1] this CTA finished last  [2] spare
-    uint32_t *s_bin = s_misc + 3;    // [kWorkBins + 1] first list position of each cost class, dearest class first
+    uint32_t *s_misc = s_idle + 1;   // [0] split shift  [1] this CTA finished last  [2] the grid has gone quiet  [3] scout lock
+                                     // [4] warps of this CTA that are polling  [5] spare
+    uint32_t *s_bin = s_misc + 6;    // [kWorkBins + 1] first list position of each cost class, dearest class first
     uint32_t *s_wait = s_bin + kWorkBins + 1;  // [2 * WARPS] configuration a warp has finished but for its pieces: index, hit
     // obstacle accessors: shared memory, or the read-only global path
     auto obs_node = [&](int nb, int half) -> float4 {
@@ -348,7 +372,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
         mbar_fence_init();
     }
     if (threadIdx.x < kMailSlots) s_mail[threadIdx.x].state = 0u;
-    if (threadIdx.x <= WARPS) s_pend[threadIdx.x] = 0u;  // the last one is s_idle
+    if (threadIdx.x <= WARPS + 6) s_pend[threadIdx.x] = 0u;  // s_pend, s_idle, s_misc
     __syncthreads();
     if (threadIdx.x == 0) {
         const uint32_t bv = c.n_rob_v_pad * 16u, bo = c.n_obs_t * 16u,
@@ -380,7 +404,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
         // split: as many parts per configuration (a power of two) as keep the entries at or below
         // split_load per warp of the grid -- 1 for the large sets the kernel is tuned for
         uint32_t gs = 0;
-        if (!STATS && a.optimistic)
+        if (!STATS)
             while ((2u << gs) <= (uint32_t)a.split_max &&
                    ((unsigned long long)acc << (gs + 1)) <= (unsigned long long)a.split_load * gridDim.x * WARPS)
                 gs++;
@@ -395,20 +419,26 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
     uint32_t *leafq = stack + kStack;
     uint32_t *tailq = leafq + kLeafQCap;
     unsigned long long st_broad = 0, st_valid = 0, st_invalid = 0, st_nodes = 0,
-                       st_leaves = 0, st_tris = 0, st_over = 0, st_tails = 0, st_nr = 0, st_lr = 0, st_tr = 0, st_shared = 0;
+                       st_leaves = 0, st_tris = 0, st_over = 0, st_tails = 0, st_nr = 0, st_lr = 0, st_tr = 0, st_shared = 0,
+                       st_pre = 0, st_pl1 = 0;
     const bool counting = STATS && a.hit_counts != nullptr;  // audit: every hitting pair, no early exit
+    // OPT: the production protocol.  Flags are optimistic (classify_kernel marked every listed
+    // configuration valid, whoever finds a hit overwrites), so a piece of a descent that one warp
+    // hands to another never reports back: one-way mail, inside the CTA (shared memory) and between
+    // CTAs (global memory).  The statistics kernels (!OPT) keep the rendezvous protocol -- the owner
+    // of a configuration collects the verdict of its pieces and writes the flag once -- because they
+    // count per configuration.
+    constexpr bool OPT = !STATS;
+    GMailBox *const g = a.gmail;
 
     // Guided self-scheduling over the work list: chunks while plenty of work is left, single
     // entries near the end so that no warp is left holding a long chunk.  The cost of one
     // configuration is heavy-tailed (median 9 k cycles, 1 % above 120 k, maximum 280 k = 40 % of
-    // the whole kernel), so once the list is dry the warps of a CTA SHARE what is left: a warp whose
-    // pair stack is deep hands its 32 oldest entries (the largest subtrees) to a mail slot in shared
-    // memory, warps without work of their own pick slots up and run the same descent on them.
-    // A configuration collides iff any of its pieces finds a hit; the owner collects the verdict of
-    // its pieces (s_pend: piece count + hit bit) and publishes the flag.  While it waits it serves
-    // the mail slots itself -- its own pieces included -- so every piece that was ever handed out is
-    // worked on even if no other warp picks it up: no wait of this protocol can give up on work, and
-    // no descent is ever abandoned.
+    // the whole kernel), so once the list is dry the warps SHARE what is left: a warp whose
+    // pair stack is deep hands its 32 oldest entries (the largest subtrees) to a mail slot, warps
+    // without work of their own pick slots up and run the same descent on them.  No wait of either
+    // protocol can give up on work, and no descent is ever abandoned: a piece that nobody picks up
+    // is worked off by the warp that posted it once it has nothing else to do.
     const uint32_t gs = s_misc[0];
     const uint32_t n_work = s_bin[kWorkBins] << gs;  // entries: (configuration, part)
     const uint32_t chunk = max(1u, min(16u, n_work / (gridDim.x * WARPS * 32u)));
@@ -430,8 +460,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
         }
         Mat34 m;
         long i = 0;
-        int owner = -1;       // >= 0: this warp works on a piece of that warp's configuration
-        bool sharing = false;  // pieces of the current configuration are (or were) out
+        int owner = -1;       // !OPT, >= 0: this warp works on a piece of that warp's configuration
+        bool sharing = false;  // !OPT: pieces of the current configuration are (or were) out
         int sp = 0, lq = 0, tq = 0;
         long long t_begin = 0;
         uint32_t tr_nodes = 0, tr_leaves = 0, tr_tails = 0, tr_maxsp = 0;  // rounds of the owner itself
@@ -447,24 +477,97 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
                 a.trace[4 * i + 3] = (tr_tails << 16) | min(tr_maxsp, 0xffffu);
             }
         };
-        // verdict of a whole configuration (or, split, of one part of it) -> flags
-        auto finalize = [&](long ci, bool h) {
-            if constexpr (!STATS) {
-                // the reference's broad phase comes first: what it clears is valid whatever the
-                // narrow phase would say
-                if (h && exact_broad_clears(a.work_mat, ci, s_rob_v, c.n_rob_v_pad, a.probe_stride, c.obs_box, lane)) h = false;
+        if (OPT && dry) {
+            // ---- one-way mail: poll the slots of the CTA, every fourth time those of the grid ----
+            // the grid counts CTAs whose warps are ALL polling (a few thousand warps bumping one word
+            // would take longer than a short kernel lasts)
+            if (lane == 0 && atomicAdd(&s_misc[4], 1u) == (uint32_t)WARPS - 1u) atomicAdd(&g->idle, 1u);
+            int k;  // 0 .. kMailSlots - 1: slot of the CTA; kMailSlots + q: slot q of the grid; -2: leave
+            for (uint32_t spins = 0;; spins++) {
+                k = -1;
+                int scout = 0;
+                if (lane == 0) {
+                    for (int q = 0; q < a.mail_slots; q++)
+                        if (ld_volatile(&s_mail[q].state) == 2u && atomicCAS(&s_mail[q].state, 2u, 3u) == 2u) {
+                            k = q;
+                            break;
+                        }
+                    if (k < 0) {
+                        if (ld_volatile(&s_misc[2]) != 0u) k = -2;  // a scout of this CTA has seen the grid go quiet
+                        // ONE warp of the CTA at a time looks at the grid (a few thousand warps polling the
+                        // same two cache lines would slow down the warps that still work)
+                        else scout = atomicCAS(&s_misc[3], 0u, 1u) == 0u ? 1 : 0;
+                    }
+                }
+                k = __shfl_sync(kFull, k, 0);
+                if (k == -1 && __shfl_sync(kFull, scout, 0)) {
+                    const unsigned f0 = __ballot_sync(kFull, ld_volatile(&g->state[lane]) == 2u);
+                    const unsigned f1 = __ballot_sync(kFull, ld_volatile(&g->state[32 + lane]) == 2u);
+                    if (f0 | f1) {
+                        const int q = f0 ? __ffs(f0) - 1 : 31 + __ffs(f1);
+                        int got = 0;
+                        if (lane == 0) got = atomicCAS(&g->state[q], 2u, 3u) == 2u ? 1 : 0;
+                        if (__shfl_sync(kFull, got, 0)) k = kMailSlots + q;
+                    } else {
+                        // nothing anywhere: leave once every warp of the grid is polling (only a warp
+                        // that works can post).  A poll that gives up costs parallelism, never work.
+                        uint32_t idle = 0;
+                        if (lane == 0) {
+                            idle = ld_volatile(&g->idle);
+                            if (idle != gridDim.x && spins > kWatchdogSpins) {
+                                atomicAdd(c.counters + CNT_WATCHDOG, 1ULL);
+                                atomicOr(c.counters + CNT_WATCHDOG_WHERE, 1ULL);
+                                idle = gridDim.x;
+                            }
+                            if (idle == gridDim.x) st_volatile(&s_misc[2], 1u);
+                        }
+                        if (__shfl_sync(kFull, idle, 0) == gridDim.x) k = -2;
+                    }
+                    if (lane == 0) st_volatile(&s_misc[3], 0u);
+                }
+                if (k != -1) break;
+                __nanosleep(200);
             }
-            if (a.optimistic) {
-                if (h) publish_invalid(c, ci, lane);
+            if (k == -2) break;
+            if (lane == 0 && atomicSub(&s_misc[4], 1u) == (uint32_t)WARPS) atomicSub(&g->idle, 1u);
+            int cnt, kind;
+            uint32_t e;
+            if (k < kMailSlots) {
+                __threadfence_block();
+                Mail &b = s_mail[k];
+                i = (long)b.owner;  // the configuration the piece belongs to
+                cnt = (int)b.cnt; kind = (int)b.kind;
+                e = b.pairs[lane];
+                m.r00 = b.m[0].x; m.r01 = b.m[0].y; m.r02 = b.m[0].z; m.tx = b.m[0].w;
+                m.r10 = b.m[1].x; m.r11 = b.m[1].y; m.r12 = b.m[1].z; m.ty = b.m[1].w;
+                m.r20 = b.m[2].x; m.r21 = b.m[2].y; m.r22 = b.m[2].z; m.tz = b.m[2].w;
+                __syncwarp();
+                __threadfence_block();
+                if (lane == 0) st_volatile(&s_mail[k].state, 0u);
             } else {
-                publish(c, ci, !h, lane);
+                __threadfence();
+                const GMailRec *b = g->rec + (k - kMailSlots);
+                const float4 q0 = __ldcg(b->m), q1 = __ldcg(b->m + 1), q2 = __ldcg(b->m + 2);
+                i = (long)__ldcg(&b->conf);
+                cnt = (int)__ldcg(&b->cnt); kind = (int)__ldcg(&b->kind);
+                e = __ldcg(b->pairs + lane);
+                m.r00 = q0.x; m.r01 = q0.y; m.r02 = q0.z; m.tx = q0.w;
+                m.r10 = q1.x; m.r11 = q1.y; m.r12 = q1.z; m.ty = q1.w;
+                m.r20 = q2.x; m.r21 = q2.y; m.r22 = q2.z; m.tz = q2.w;
+                __syncwarp();
+                __threadfence();
+                if (lane == 0) st_volatile(&g->state[k - kMailSlots], 0u);
             }
-            if (STATS) { if (h) st_invalid++; else st_valid++; }
-        };
-        if (dry || waiting) {
-            // no configuration to start: serve the mail slots.  A warp that waits for the pieces of
-            // its configuration leaves when they are all back; a warp that found the list dry leaves
-            // when every warp of the CTA is in that state and no slot is full.
+            {
+                uint32_t *dst = kind == 0 ? stack : kind == 1 ? leafq : tailq;
+                if (lane < cnt) dst[lane] = e;
+                if (kind == 0) sp = cnt; else if (kind == 1) lq = cnt; else tq = cnt;
+            }
+            __syncwarp();
+        } else if (!OPT && (dry || waiting)) {
+            // ---- rendezvous mail (statistics kernels): serve the slots of the CTA.  A warp that
+            // waits for the pieces of its configuration leaves when they are all back; a warp that
+            // found the list dry leaves when every warp of the CTA is in that state.
             int k;
             for (uint32_t spins = 0;; spins++) {
                 k = -1;
@@ -507,7 +610,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
                 wi = __shfl_sync(kFull, wi, 0);
                 wh = __shfl_sync(kFull, wh, 0);
                 waiting = false;
-                finalize((long)wi, wh != 0u || (v & kPendHit) != 0u);
+                const bool h = wh != 0u || (v & kPendHit) != 0u;
+                publish(c, (long)wi, !h, lane);
+                if (h) st_invalid++; else st_valid++;
                 continue;
             }
             __threadfence_block();
@@ -595,16 +700,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
             // configuration are out.  s_idle only ever grows, so the common case is one shared-memory
             // read and one vote.
             uint32_t seen = 0;
-            if (kind >= 0 || sharing) {
+            if (kind >= 0 || (!OPT && sharing)) {
                 if (__any_sync(kFull, ld_volatile(s_idle) != 0u)) {
                     if (lane == 0) {
                         seen = 1u;
-                        if (sharing && (ld_volatile(&s_pend[pend_slot]) & kPendHit) != 0u) seen = 3u;
+                        if (!OPT && sharing && (ld_volatile(&s_pend[pend_slot]) & kPendHit) != 0u) seen = 3u;
                     }
                     seen = __shfl_sync(kFull, seen, 0);
                 }
             }
-            if (seen & 2u) {
+            if (!OPT && (seen & 2u)) {
                 hit = true;  // another piece of this configuration has found a hit
                 break;
             }
@@ -617,8 +722,23 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
                             break;
                         }
                 k = __shfl_sync(kFull, k, 0);
+                if (OPT && k < 0 && ((sp + lq + tq) & 3) == 0) {
+                    // the slots of the CTA are full (its warps without work have all they can take):
+                    // the grid.  One read tells whether anybody out there is polling at all.
+                    uint32_t idle = 0;
+                    if (lane == 0) idle = ld_volatile(&g->idle);
+                    if (__shfl_sync(kFull, idle, 0) != 0u) {
+                        const unsigned f0 = __ballot_sync(kFull, ld_volatile(&g->state[lane]) == 0u);
+                        const unsigned f1 = __ballot_sync(kFull, ld_volatile(&g->state[32 + lane]) == 0u);
+                        if (f0 | f1) {
+                            const int q = f0 ? __ffs(f0) - 1 : 31 + __ffs(f1);
+                            int got = 0;
+                            if (lane == 0) got = atomicCAS(&g->state[q], 0u, 1u) == 0u ? 1 : 0;
+                            if (__shfl_sync(kFull, got, 0)) k = kMailSlots + q;
+                        }
+                    }
+                }
                 if (k >= 0) {
-                    Mail &b = s_mail[k];
                     const int cnt = kind == 2 ? min(tq, 32) : kind == 1 ? 8 : min(32, sp >> 1);  // node pairs: at most half
                     const int src = lane < cnt ? lane : 0;
                     uint32_t out;
@@ -635,21 +755,38 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
                         if (lane < cnt) stack[lane] = top;
                         sp -= cnt;
                     }
-                    if (lane < cnt) b.pairs[lane] = out;
-                    if (lane == 0) {
-                        b.m[0] = make_float4(m.r00, m.r01, m.r02, m.tx);
-                        b.m[1] = make_float4(m.r10, m.r11, m.r12, m.ty);
-                        b.m[2] = make_float4(m.r20, m.r21, m.r22, m.tz);
-                        b.owner = (uint32_t)pend_slot;
-                        b.cnt = (uint32_t)cnt;
-                        b.kind = (uint32_t)kind;
-                        atomicAdd(&s_pend[pend_slot], 1u);
+                    if (!OPT || k < kMailSlots) {
+                        Mail &b = s_mail[k];
+                        if (lane < cnt) b.pairs[lane] = out;
+                        if (lane == 0) {
+                            b.m[0] = make_float4(m.r00, m.r01, m.r02, m.tx);
+                            b.m[1] = make_float4(m.r10, m.r11, m.r12, m.ty);
+                            b.m[2] = make_float4(m.r20, m.r21, m.r22, m.tz);
+                            b.owner = OPT ? (uint32_t)i : (uint32_t)pend_slot;
+                            b.cnt = (uint32_t)cnt;
+                            b.kind = (uint32_t)kind;
+                            if (!OPT) atomicAdd(&s_pend[pend_slot], 1u);
+                        }
+                        if (STATS) st_shared++;
+                        sharing = true;
+                        __syncwarp();
+                        __threadfence_block();
+                        if (lane == 0) st_volatile(&s_mail[k].state, 2u);
+                    } else {
+                        GMailRec *b = g->rec + (k - kMailSlots);
+                        b->pairs[lane] = out;
+                        if (lane == 0) {
+                            b->m[0] = make_float4(m.r00, m.r01, m.r02, m.tx);
+                            b->m[1] = make_float4(m.r10, m.r11, m.r12, m.ty);
+                            b->m[2] = make_float4(m.r20, m.r21, m.r22, m.tz);
+                            b->conf = (uint32_t)i;
+                            b->cnt = (uint32_t)cnt;
+                            b->kind = (uint32_t)kind;
+                        }
+                        __threadfence();
+                        __syncwarp();
+                        if (lane == 0) st_volatile(&g->state[k - kMailSlots], 2u);
                     }
-                    if (STATS) st_shared++;
-                    sharing = true;
-                    __syncwarp();
-                    __threadfence_block();
-                    if (lane == 0) st_volatile(&s_mail[k].state, 2u);
                     __syncwarp();
                     continue;
                 }
@@ -729,9 +866,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
                                 fminf(fminf(oa.x, ob.x), oc.x) <= rhx && fmaxf(fmaxf(oa.x, ob.x), oc.x) >= rlx &&
                                 fminf(fminf(oa.y, ob.y), oc.y) <= rhy && fmaxf(fmaxf(oa.y, ob.y), oc.y) >= rly &&
                                 fminf(fminf(oa.z, ob.z), oc.z) <= rhz && fmaxf(fmaxf(oa.z, ob.z), oc.z) >= rlz;
+                    if (STATS) st_pre += __popc(__ballot_sync(kFull, pass));
                     if (pass)
                         pass = straddles(sdist(pr, oa.x, oa.y, oa.z), sdist(pr, ob.x, ob.y, ob.z),
                                          sdist(pr, oc.x, oc.y, oc.z));
+                    if (STATS) st_pl1 += __popc(__ballot_sync(kFull, pass));
                     if (pass) {
                         const Plane po = {oa.w, ob.w, oc.w, obs_D(k)};
                         pass = straddles(sdist(po, r.ax, r.ay, r.az), sdist(po, r.bx, r.by, r.bz),
@@ -745,8 +884,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
                 __syncwarp();
                 continue;
             }
-            // ---- B: pop up to 32 node pairs, test, push children
-            const int cnt = min(sp, 32);
+            // ---- B: pop up to 32 node pairs, test, push children.  A round that pops 32 pairs can
+            // push 128; close to the capacity of the stack the rounds pop ONE pair, i.e. turn into a
+            // depth-first walk whose stack grows by at most three per tree level, so the capacity is
+            // not reached in practice whatever the configuration (the exhaustive fallback stays).
+            const int cnt = (sp + kNarrowPop <= a.stack_cap || a.stack_cap < 2 * kNarrowPop) ? min(sp, 32) : 1;
             sp -= cnt;
             const bool act = lane < cnt;
             const uint32_t e = stack[sp + (act ? lane : 0)];
@@ -796,6 +938,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
             if (STATS && counting) n_hits = 0xffffffffu;  // the fallback does not count: the audit reports it
         }
         __syncwarp();
+        if constexpr (OPT) {
+            // whoever finds a hit writes "invalid" -- unless the reference's broad phase, which comes
+            // first, clears the configuration: then it is valid whatever the narrow phase says
+            if (hit && !exact_broad_clears(a.work_mat, i, s_rob_v, c.n_rob_v_pad, a.probe_stride, c.obs_box, lane))
+                publish_invalid(c, i, lane);
+            continue;
+        }
         if (owner >= 0) {
             // a piece: report to the owner of the configuration
             if (lane == 0) {
@@ -819,7 +968,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
             waiting = true;
             continue;
         }
-        finalize(i, hit);
+        publish(c, i, !hit, lane);
+        if (hit) st_invalid++; else st_valid++;
     }
     if (STATS) {
 #pragma unroll
@@ -837,6 +987,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
             atomicAdd(c.counters + CNT_LEAF_ROUNDS, st_lr);
             atomicAdd(c.counters + CNT_TAIL_ROUNDS, st_tr);
             atomicAdd(c.counters + CNT_SHARED, st_shared);
+            atomicAdd(c.counters + CNT_PREFILTER, st_pre);
+            atomicAdd(c.counters + CNT_PLANE1, st_pl1);
         }
     }
     // the last CTA to finish leaves the list counters at zero for the next call (no memset per
@@ -847,8 +999,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
     if (threadIdx.x == 0) {
         __threadfence();
         const bool last = atomicAdd(a.work_count + kWorkBins + 1, 1ULL) == (unsigned long long)gridDim.x - 1ULL;
-        if (last)
+        if (last) {
             for (int q = 0; q < kWorkBins + 2; q++) a.work_count[q] = 0;
+            if (!STATS) a.gmail->idle = 0u;  // every slot is empty again by construction
+        }
         __threadfence();
         s_misc[1] = last ? 1u : 0u;
     }
@@ -865,7 +1019,7 @@ static size_t culled_smem_bytes(const DeviceTables &t, int warps, bool gobs)
     if (!gobs)
         b += (size_t)t.n_obs_nodes * 32 + (size_t)t.n_obs_t * 48 + (size_t)pad4(t.n_obs_t) * 4;
     b += (size_t)warps * (stack_cap_of(warps, gobs) + kLeafQCap + kTailQCap) * 4;
-    b = (b + 15) / 16 * 16 + kMailSlots * sizeof(Mail) + (3 * (size_t)warps + 4 + kWorkBins + 1) * 4;  // + s_pend, s_idle, s_misc, s_bin, s_wait
+    b = (b + 15) / 16 * 16 + kMailSlots * sizeof(Mail) + (3 * (size_t)warps + 7 + kWorkBins + 1 + 2) * 4;  // + s_pend, s_idle, s_misc, s_bin, s_wait
     return b;
 }
 
@@ -931,6 +1085,7 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
     // flags: written once per configuration by its warp (statistics kernels), or optimistically --
     // marked valid by step 1, overwritten by whichever part of the descent finds a hit
     a.optimistic = want_stats ? 0 : 1;
+    a.gmail = reinterpret_cast<GMailBox *>(ctx->d_gmail);
     a.split_max = max(1, min(kSplitMax, ctx->knob_split_max));
     a.split_load = max(1, ctx->knob_split_load);
     a.tri_margin = 2.f * t.box_margin;

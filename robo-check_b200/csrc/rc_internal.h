@@ -56,6 +56,7 @@ struct DeviceTables {
 // of the robot lies inside the obstacle AABB); the descent takes the dearest class first so that
 // the long descents are under way early and the work list ends with cheap ones
 constexpr int kWorkBins = 8;
+constexpr size_t kGMailBytes = 16384;  // >= sizeof(rc::GMailBox)
 constexpr int kWorkCounters = 16;  // [0..7] entries per class, [8] next entry, [9] CTAs finished
 
 // one of the two batches rc_check_host_submit may have in flight
@@ -110,6 +111,7 @@ struct rc_ctx {
     uint32_t *d_work_idx = nullptr;            // [kWorkBins][work_cap]: configuration indices per cost class
     float4 *d_work_mat = nullptr;
     unsigned long long *d_work_count = nullptr;
+    unsigned char *d_gmail = nullptr;          // rc::GMailBox: mail between CTAs (rc_culled.cuh), all zero outside a launch
     long work_cap = 0;
     uint32_t *d_block_counts = nullptr;        // scratch of rc_compact, grown on demand
     long block_counts_cap = 0;
@@ -151,7 +153,9 @@ enum Counter {
     CNT_TAIL_ROUNDS,
     CNT_SHARED,           // pieces of a descent handed from one warp to another
     CNT_WATCHDOG,         // spin loops of the hand-over protocol that gave up (always counted; must stay 0)
-    CNT_WATCHDOG_WHERE,   // bit 0: serve loop, bit 1: owner waiting for its pieces
+    CNT_WATCHDOG_WHERE,   // bit 0: serve loop of a warp without work, bit 3: gather wait
+    CNT_PREFILTER,        // triangle pairs whose boxes overlap (leaf rounds)
+    CNT_PLANE1,           // ... that also pass the first plane test
     RC_NUM_COUNTERS = 24
 };
 constexpr int kHostChunks = 8;
@@ -200,6 +204,9 @@ cudaError_t launch_kat_la_solve(const float *d_in, int n, float *d_out, cudaStre
 cudaError_t launch_fma_peak(float *d_out, int grid, int iters, cudaStream_t stream);
 cudaError_t launch_conf_generate(rc_config *d_out, long n, const float box[6], uint64_t seed,
                                  cudaStream_t stream);
+cudaError_t launch_conf_generate_mix(rc_config *d_out, long first, long n, const float box_a[6],
+                                     const float box_b[6], int block, int period, uint64_t seed,
+                                     cudaStream_t stream);
 cudaError_t launch_compact(const uint8_t *d_valid, const uint32_t *d_mask, long n, int want,
                            uint32_t *d_indices, unsigned long long *d_count, uint32_t *d_block_counts,
                            cudaStream_t stream);

@@ -435,6 +435,45 @@ __global__ void __launch_bounds__(256) conf_generate_kernel(rc_config *out, long
     }
 }
 
+// One global set generated in pieces: element numbers count from configuration `first`, blocks of
+// `block` configurations with number (period - 1) mod period come from box b (period 0: never).
+struct GenMixArgs {
+    float lo_a[3], hi_a[3], lo_b[3], hi_b[3];
+    long first, n;
+    int block, period;
+    uint64_t seed;
+};
+__global__ void __launch_bounds__(256) conf_generate_mix_kernel(rc_config *out, const GenMixArgs a)
+{
+    float *f = reinterpret_cast<float *>(out);
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < 6 * a.n; e += (long)gridDim.x * blockDim.x) {
+        const long g = a.first + e / 6;
+        const int k = (int)(e % 6);
+        const bool b = a.period > 0 && (g / a.block) % a.period == a.period - 1;
+        const float lo = k >= 3 ? -3.14159265358979f : (b ? a.lo_b[k] : a.lo_a[k]);
+        const float hi = k >= 3 ? 3.14159265358979f : (b ? a.hi_b[k] : a.hi_a[k]);
+        const uint64_t h = mix64(a.seed * 0x9E3779B97F4A7C15ull + (uint64_t)(6 * g + k) + 1);
+        const float u = (float)(h >> 40) * (1.0f / 16777216.0f);  // [0, 1)
+        f[e] = fmaf(u, hi - lo, lo);
+    }
+}
+
+cudaError_t launch_conf_generate_mix(rc_config *d_out, long first, long n, const float box_a[6],
+                                     const float box_b[6], int block, int period, uint64_t seed,
+                                     cudaStream_t stream)
+{
+    if (n <= 0) return cudaSuccess;
+    GenMixArgs a;
+    for (int k = 0; k < 3; k++) {
+        a.lo_a[k] = box_a[2 * k]; a.hi_a[k] = box_a[2 * k + 1];
+        a.lo_b[k] = box_b[2 * k]; a.hi_b[k] = box_b[2 * k + 1];
+    }
+    a.first = first; a.n = n; a.block = block > 0 ? block : 1; a.period = period; a.seed = seed;
+    const int grid = (int)min((6 * n + 255) / 256, 148L * 16);
+    conf_generate_mix_kernel<<<grid, 256, 0, stream>>>(d_out, a);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_conf_generate(rc_config *d_out, long n, const float box[6], uint64_t seed,
                                  cudaStream_t stream)
 {

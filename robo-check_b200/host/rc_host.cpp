@@ -460,16 +460,25 @@ int rc_conf_generate(rc_config *out, long n, float x_min, float x_max, float y_m
     return RC_OK;
 }
 
-int rc_conf_generate_alpha(rc_config *out, long n, int hard, uint32_t seed)
+int rc_alpha_box(int hard, float box[6])
 {
+    if (!box) return RC_ERR_INVALID;
     // extents of alpha1.0/robot.obj as hard-coded by the reference (Utils_rai.cu:113-118)
     const float x_min = 3.72119f, y_min = -11.0518f, z_min = -0.608012f;
     const float x_max = 65.9453f, y_max = 26.0984f, z_max = 18.6984f;
-    const float xr = x_max - x_min, yr = y_max - y_min, zr = z_max - z_min;
-    if (hard)
-        return rc_conf_generate(out, n, -xr / 200, xr / 200, -yr / 200, yr / 200, -zr / 200,
-                                zr / 200, seed);
-    return rc_conf_generate(out, n, -xr * 10, xr * 10, -yr * 10, yr * 10, -zr * 10, zr * 10, seed);
+    const float r[3] = {x_max - x_min, y_max - y_min, z_max - z_min};
+    for (int k = 0; k < 3; k++) {
+        box[2 * k] = hard ? -r[k] / 200 : -r[k] * 10;
+        box[2 * k + 1] = hard ? r[k] / 200 : r[k] * 10;
+    }
+    return RC_OK;
+}
+
+int rc_conf_generate_alpha(rc_config *out, long n, int hard, uint32_t seed)
+{
+    float b[6];
+    rc_alpha_box(hard, b);
+    return rc_conf_generate(out, n, b[0], b[1], b[2], b[3], b[4], b[5], seed);
 }
 
 }  // extern "C"

@@ -70,6 +70,19 @@ class PeerGather:
         torch.cuda.synchronize(device)
         dist.barrier()  # every buffer is zeroed before anybody delivers into it
 
+    def check_host(self, ctx, h_confs, d_confs, n, h_mask, stream):
+        """Host buffers in, gathered bitmask of ALL ranks in host memory out: the rank's `n`
+        configurations travel from the page-locked tensor `h_confs` to `d_confs`, are checked and
+        gathered (rc_check_gather), and the gathered words come back into the page-locked tensor
+        `h_mask` (world * words int32).  Returns when the words are there."""
+        import torch
+        with torch.cuda.stream(stream):
+            d_confs[: n * 6].copy_(h_confs[: n * 6], non_blocking=True)
+            words = self.check(ctx, d_confs, n, None, stream)
+            h_mask.copy_(words, non_blocking=True)
+        stream.synchronize()
+        return h_mask
+
     def check(self, ctx, d_confs, n, d_valid=None, stream=None):
         """Returns the gathered bitmask of this call: a view of world * words int32 words inside the
         own buffer, valid (in stream order) until the second next call."""

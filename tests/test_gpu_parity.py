@@ -717,3 +717,301 @@ def test_pipelined_host_calls(rc, ctx, po, omeshes):
     with pytest.raises(rc.RoboCheckError):
         ctx.check_host_wait(10 ** 6)
     assert ctx.stats()["watchdog"] == 0
+
+
+# ---- round 2: the exact BASELINE workloads against exhaustive ground truth ---------------------
+def test_bench_workload_vs_reference_gpu_pipeline_and_brute(rc, ctx, po):
+    """The bench workload itself (BASELINE configs[1]: 100,000 hard configurations, seed 508) against
+    the UNMODIFIED reference pipeline run on this GPU (broadPhaseFused_sep from oracle/_ref, an
+    exhaustive sweep with the reference's own kernels) and against RC_MODE_BRUTE: no checker in this
+    test shares the culling of the kernel under test."""
+    confs = rc.createAlphaBotConfigurations(100_000, True, 508)
+    culled, bits = run_check(ctx, confs, rc.RC_MODE_CULLED, bitmask=True)
+    brute = run_check(ctx, confs, rc.RC_MODE_BRUTE)
+    assert int((culled != brute).sum()) == 0 and np.array_equal(bits, culled)
+    assert np.array_equal(ctx.check_host(confs), brute)
+    if not po.ref_available():
+        pytest.skip("oracle/_ref/libref.so not built (needs /root/reference at build time)")
+    from tests import refpipe
+    want = refpipe.oracle_gpu_flags(rc, po, confs)
+    assert int((culled != want).sum()) == 0
+    assert int((brute != want).sum()) == 0
+
+
+def test_c4_first_300k_vs_reference_gpu_pipeline(rc, ctx, po):
+    """BASELINE configs[3] (1 M of the reference's sampler, seed 510): the first 300,000 against the
+    unmodified reference pipeline on this GPU, all 1 M culled == brute."""
+    confs = rc.createAlphaBotConfigurations(1_000_000, False, 510)
+    culled = run_check(ctx, confs, rc.RC_MODE_CULLED)
+    brute = run_check(ctx, confs, rc.RC_MODE_BRUTE)
+    assert int((culled != brute).sum()) == 0
+    if not po.ref_available():
+        pytest.skip("oracle/_ref/libref.so not built")
+    from tests import refpipe
+    want = refpipe.oracle_gpu_flags(rc, po, confs[:300_000])
+    assert int((culled[:300_000] != want).sum()) == 0
+
+
+def test_c5_level5_exhaustive_spot_check(rc, po, meshes):
+    """BASELINE configs[4] at its real obstacle size (1,032,192 triangles): 20 configurations -- near
+    contact, where the narrow phase decides -- against the EXHAUSTIVE CPU sweep (po.check: all
+    1008 x 1,032,192 pairs, no tree anywhere), plus their hitting-pair counts against the tree
+    descent's."""
+    torch = _torch()
+    rob, obs = meshes[0], meshes[1].subdivide(5)
+    assert obs.n_t == 1008 * 4 ** 5
+    confs = np.concatenate([rc.createAlphaBotConfigurations(14, True, 512),
+                            rc.createAlphaBotConfigurations(6, False, 511)]).astype(np.float32)
+    R, O = po.OracleMesh(*rob.arrays()), po.OracleMesh(*obs.arrays())
+    want, want_counts = po.check_counts(R, O, confs)
+    assert 0 < int(want.sum()) < len(want)
+    c = rc.Context(rob, obs, device=0)
+    try:
+        got = run_check(c, confs, rc.RC_MODE_CULLED)
+        assert np.array_equal(got, want)
+        d_confs = torch.from_numpy(confs).cuda()
+        d_cnt = torch.zeros(len(confs), dtype=torch.int32, device="cuda")
+        c.hit_counts(d_confs, len(confs), d_cnt, rc.RC_MODE_CULLED, stream=torch.cuda.current_stream())
+        torch.cuda.synchronize()
+        assert np.array_equal(d_cnt.cpu().numpy().view(np.uint32), want_counts)
+    finally:
+        c.close()
+
+
+def test_hit_pair_counts(rc, ctx, po, omeshes):
+    """SURVEY appendix A, closing rule: per-configuration number of hitting pairs from a sweep without
+    early exit.  Equal flags could hide compensating per-pair errors (a colliding configuration has
+    ~100 hitting pairs); equal COUNTS cannot.  (a) exhaustive kernel == exhaustive CPU oracle on 600
+    configurations, (b) tree descent == exhaustive kernel on the whole bench workload, i.e. the
+    culling skips no pair the reference arithmetic reports, (c) rc_audit says the same."""
+    torch = _torch()
+    s = torch.cuda.current_stream()
+    confs = rc.createAlphaBotConfigurations(100_000, True, 508)
+    n = len(confs)
+    d_confs = torch.from_numpy(confs).cuda()
+    d_cb = torch.full((n,), -1, dtype=torch.int32, device="cuda")
+    d_cc = torch.full((n,), -1, dtype=torch.int32, device="cuda")
+    d_fb = torch.full((n,), 7, dtype=torch.uint8, device="cuda")
+    d_fc = torch.full((n,), 7, dtype=torch.uint8, device="cuda")
+    ctx.hit_counts(d_confs, n, d_cb, rc.RC_MODE_BRUTE, d_fb, s)
+    ctx.hit_counts(d_confs, n, d_cc, rc.RC_MODE_CULLED, d_fc, s)
+    torch.cuda.synchronize()
+    cb, cc = d_cb.cpu().numpy().view(np.uint32), d_cc.cpu().numpy().view(np.uint32)
+    fb, fc = d_fb.cpu().numpy(), d_fc.cpu().numpy()
+    m = 600
+    want_flags, want_counts = po.check_counts(omeshes[0], omeshes[1], confs[:m])
+    assert np.array_equal(fb[:m], want_flags)
+    assert np.array_equal(cb[:m], want_counts), int((cb[:m] != want_counts).sum())
+    assert int((cc != cb).sum()) == 0 and int((fc != fb).sum()) == 0
+    assert np.array_equal(cb > 0, fb == 0)
+    assert 50 < cb[fb == 0].mean() < 300      # ~109 hitting pairs per colliding configuration (SURVEY 8a)
+    # the flags of the counting kernels are the flags of the production kernels
+    assert np.array_equal(fb, run_check(ctx, confs, rc.RC_MODE_CULLED))
+    nf, nc, idx = ctx.audit(d_confs, 20_000)
+    assert (nf, nc, len(idx)) == (0, 0, 0)
+    assert ctx.stats()["overflow"] == 0
+
+
+def test_audit_reports_the_coplanar_scene(rc, po):
+    """rc_audit on the scene where the exactness contract of RC_MODE_CULLED does NOT hold
+    (tests/coplanar_scene.py: the reference arithmetic reports triangle pairs that lie far apart in a
+    common plane): the audit must say so -- counts differ -- instead of 0."""
+    torch = _torch()
+    from tests import coplanar_scene
+    rob_a, obs_a, confs = coplanar_scene.build(po)
+    c = rc.Context(rc.Mesh.from_arrays(*rob_a), rc.Mesh.from_arrays(*obs_a), device=0)
+    try:
+        d_confs = torch.from_numpy(confs).cuda()
+        nf, nc, idx = c.audit(d_confs, len(confs), cap=16)
+        culled = run_check(c, confs, rc.RC_MODE_CULLED)
+        brute = run_check(c, confs, rc.RC_MODE_BRUTE)
+        assert nf == int((culled != brute).sum())
+        assert nc >= nf and nc > 0 and len(idx) > 0
+    finally:
+        c.close()
+
+
+def test_device_known_answer_tests(rc, ctx, po, omeshes):
+    """The reference's helper KATs (narrow-phase/test-narrow-phase.cu:7-626) run on the DEVICE
+    functions the kernels are built from (plane_of, sdist, straddles, is_coplanar, la_solve,
+    tri_interval ...), and every intermediate of ~20,000 real alpha1.0 pairs compared bit for bit with
+    the CPU oracle's helper chain."""
+    PTS = np.array([[1, 2, 3], [2, 2, 3.5], [2, 2.5, 3], [1, 3, 4], [4, 7, 2], [5, 1, 3],
+                    [100, 300, 400], [400, 700, 200], [500, 100, 300]], np.float32)
+    T1, T2, T3 = PTS[0:3].reshape(-1), PTS[3:6].reshape(-1), PTS[6:9].reshape(-1)
+    out, verdict = ctx.kat_pairs(np.stack([T1, T1, T1]), np.stack([T2, T3, T1]))
+    # test-narrow-phase.cu:85-160: plane of T1 = (-0.25, 0.5, 0.5 | -2.25), distances of T2 = 1, 1.25, -1.5
+    assert out[0, 0:4].tolist() == [-0.25, 0.5, 0.5, -2.25]
+    assert out[0, 4:7].tolist() == [1.0, 1.25, -1.5]
+    # :162-214 no_overlap: T2 straddles the plane of T1, T3 and T1 itself do not
+    assert verdict[0] & 1 == 1 and verdict[1] & 1 == 0 and verdict[2] & 1 == 0
+    # :522-575 parametric values of the pair (T1, T2) on the intersection line
+    assert (verdict[0] & 3) == 3
+    want_t = [108.607147, 143.744751, 130.328568, 88.860390]
+    assert np.allclose(out[0, 20:24], want_t, rtol=1e-6)
+    assert (verdict[0] >> 2) == 1                      # the intervals overlap: a hit
+    # :216-246 la_solve
+    ls = ctx.kat_la_solve([[2, 3, 4, 5, 12, 22], [0, 3, 4, 5, 12, 24]])
+    assert np.allclose(ls, [[3, 2], [1, 4]], rtol=1e-6)
+    assert ls[0].tolist() == list(po.la_solve_gpu(2, 3, 4, 5, 12, 22))
+    # :577-626 coplanarity: a triangle against a scaled copy of itself shifted inside its plane
+    shifted = (PTS[0:3] * 1 + (PTS[1] - PTS[0])).reshape(-1).astype(np.float32)
+    # real pairs: every robot triangle of four near-contact configurations against a stride of the obstacle
+    rob, obs = omeshes
+    confs = rc.createAlphaBotConfigurations(4, True, 508)
+    wx, wy, wz = po.transform(confs, rob.x, rob.y, rob.z)
+    ov = np.stack([obs.x, obs.y, obs.z], 1)
+    o9_all = np.concatenate([ov[obs.v1], ov[obs.v2], ov[obs.v3]], 1)          # [n_obs_t, 9]
+    r9s, o9s = [], []
+    rng = np.random.default_rng(3)
+    for ci in range(len(confs)):
+        w = np.stack([wx[ci], wy[ci], wz[ci]], 1)
+        r9_all = np.concatenate([w[rob.v1], w[rob.v2], w[rob.v3]], 1)
+        # nearby pairs are the interesting ones: pick, for a sample of robot triangles, the obstacle
+        # triangles whose boxes overlap, plus random ones
+        for j in rng.choice(len(r9_all), 160, replace=False):
+            r = r9_all[j].reshape(3, 3)
+            lo, hi = r.min(0) - 0.5, r.max(0) + 0.5
+            o = o9_all.reshape(-1, 3, 3)
+            near = np.nonzero(np.all(o.min(1) <= hi, 1) & np.all(o.max(1) >= lo, 1))[0][:24]
+            for k in list(near) + list(rng.choice(len(o9_all), 8, replace=False)):
+                r9s.append(r9_all[j]); o9s.append(o9_all[k])
+    r9s, o9s = np.array(r9s, np.float32), np.array(o9s, np.float32)
+    assert len(r9s) > 10_000
+    out, verdict = ctx.kat_pairs(r9s, o9s)
+    n_tail = n_hit = 0
+    for i in range(len(r9s)):
+        w_out, w_v = po.pair_intermediates(r9s[i], o9s[i])
+        assert verdict[i] == w_v, (i, int(verdict[i]), w_v)
+        assert np.array_equal(out[i].view(np.uint32), w_out.view(np.uint32)), (i, out[i], w_out)
+        n_tail += (w_v & 3) == 3
+        n_hit += (w_v >> 2) == 1
+    assert n_tail > 200 and n_hit > 20       # the sample reaches the intersection-line code and finds hits
+
+
+@pytest.mark.parametrize("knobs", [{}, {"RC_SPLIT_MAX": "1"}, {"RC_SPLIT_MAX": "4", "RC_SPLIT_LOAD": "64"}])
+def test_planner_sized_batches_split_descents(rc, meshes, knobs, monkeypatch):
+    """Short work lists: a configuration is cut into parts (subsets of the seed pairs) that warps of
+    the whole grid take; the flags are written optimistically (valid first, a part with a hit
+    overwrites).  Every size from one configuration up, against the exhaustive kernel, repeated (the
+    scheduling is timing dependent)."""
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    confs = rc.createAlphaBotConfigurations(12_000, True, 508)
+    c = rc.Context(meshes[0], meshes[1], device=0)
+    try:
+        want = run_check(c, confs, rc.RC_MODE_BRUTE)
+        for n in (1, 2, 31, 33, 100, 500, 2000, 4736, 10_000, 12_000):
+            for rep in range(3):
+                got, bits = run_check(c, confs[:n], rc.RC_MODE_CULLED, bitmask=True)
+                assert np.array_equal(got, want[:n]), (n, rep, int((got != want[:n]).sum()))
+                assert np.array_equal(bits, want[:n])
+            assert np.array_equal(c.check_host(confs[:n]), want[:n])
+        assert c.stats()["watchdog"] == 0
+    finally:
+        c.close()
+
+
+def test_calls_on_different_streams_share_the_scratch_safely(rc, ctx):
+    """One context driven from two streams back to back without a host synchronisation in between
+    (rc_check on a side stream, then the host call on the context's own stream, then rc_check on the
+    default stream): the library orders the device work, every result is right."""
+    torch = _torch()
+    confs = rc.createAlphaBotConfigurations(60_000, True, 321)
+    want = run_check(ctx, confs, rc.RC_MODE_BRUTE)
+    d_confs = torch.from_numpy(confs).cuda()
+    side = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    for rep in range(4):
+        v1 = torch.full((len(confs),), 7, dtype=torch.uint8, device="cuda")
+        v3 = torch.full((len(confs),), 7, dtype=torch.uint8, device="cuda")
+        ctx.check(d_confs, len(confs), v1, None, rc.RC_MODE_CULLED, side)
+        v2 = ctx.check_host(confs[:30_000])
+        ctx.check(d_confs, len(confs), v3, None, rc.RC_MODE_CULLED, torch.cuda.current_stream())
+        torch.cuda.synchronize()
+        assert np.array_equal(v1.cpu().numpy(), want)
+        assert np.array_equal(v2, want[:30_000])
+        assert np.array_equal(v3.cpu().numpy(), want)
+
+
+def test_scaled_and_translated_scene(rc, meshes):
+    """The culling margin scales with the scene (a cell measured in millimetres, far from the origin):
+    alpha1.0 blown up 40 times and moved 3,000 units away -- culled == exhaustive on every flag."""
+    x, y, z, v1, v2, v3 = meshes[0].arrays()
+    ox, oy, oz, o1, o2, o3 = meshes[1].arrays()
+    k, t = np.float32(40.0), np.float32([3000.0, -2000.0, 1000.0])
+    obs = rc.Mesh.from_arrays(ox * k + t[0], oy * k + t[1], oz * k + t[2], o1, o2, o3)
+    rob = rc.Mesh.from_arrays(x * k, y * k, z * k, v1, v2, v3)
+    base = rc.createAlphaBotConfigurations(6000, True, 99)
+    confs = base.copy()
+    confs[:, :3] = base[:, :3] * k + t          # same relative poses, in the big frame
+    c = rc.Context(rob, obs, device=0)
+    try:
+        a = run_check(c, confs, rc.RC_MODE_CULLED)
+        b = run_check(c, confs, rc.RC_MODE_BRUTE)
+    finally:
+        c.close()
+    assert int((a != b).sum()) == 0
+    assert 0.1 < b.mean() < 0.95
+
+
+def test_gather_two_ranks_on_one_device(rc, ctx, meshes):
+    """rc_check_gather's device path on ONE GPU (the multi-GPU tests are skipped on a 1-GPU box): two
+    contexts play rank 0 and rank 1, their gather buffers are two plain device allocations that are
+    each other's "peer".  Kernels that wait for one another must not share a GPU, so the two-phase
+    form is used: begin for rank 0, begin for rank 1 (each pushes its slot into both buffers and
+    signals), then end for both (the waits find the signals already there).  Three calls (both gather
+    areas, call numbers), ragged sizes with a short last shard, then a FRESH context on the used
+    buffers (the numbering continues from the buffer's header), then the one-call form with world 1."""
+    torch = _torch()
+    from robocheck_b200 import sharding as sh
+    s = torch.cuda.current_stream()
+    n_all = 50_001
+    confs = np.concatenate([rc.createAlphaBotConfigurations(n_all // 2, True, 41),
+                            rc.createAlphaBotConfigurations(n_all - n_all // 2, False, 42)])
+    confs = confs[np.random.default_rng(8).permutation(n_all)]
+    single = run_check(ctx, confs, rc.RC_MODE_CULLED)
+    world = 2
+    words = sh.words_per_shard(n_all, world)
+    total = int(rc.lib().rc_gather_buffer_words(world, words))
+    bufs = [torch.zeros(total, dtype=torch.int32, device="cuda") for _ in range(world)]
+    ptrs = [b.data_ptr() for b in bufs]
+    ranks = [rc.Context(meshes[0], meshes[1], device=0) for _ in range(world)]
+
+    def one_call(ctxs, m):
+        offs = []
+        for r in range(world):
+            lo, hi = min(m, r * words * 32), min(m, (r + 1) * words * 32)
+            d = torch.from_numpy(np.ascontiguousarray(confs[lo:hi])).cuda() if hi > lo else None
+            offs.append(ctxs[r].check_gather_begin(d, hi - lo, None, ptrs, r, words, s))
+        for r in range(world):
+            ctxs[r].gather_end(ptrs, r, words, s)
+        torch.cuda.synchronize()
+        for r in range(world):
+            got = sh.unpack_bitmask(bufs[r][offs[r]:offs[r] + world * words].cpu().numpy(), world * words * 32)[:m]
+            assert np.array_equal(got, single[:m]), (r, m, int((got != single[:m]).sum()))
+
+    try:
+        for m in (n_all, n_all - 4097, 70):
+            one_call(ranks, m)
+        for r in range(world):
+            assert ranks[r].gather_status(ptrs[r], world, words) == (3, 0)
+            assert ranks[r].stats()["watchdog"] == 0
+        fresh = [rc.Context(meshes[0], meshes[1], device=0) for _ in range(world)]
+        try:
+            one_call(fresh, 30_000)
+            for r in range(world):
+                assert fresh[r].gather_status(ptrs[r], world, words) == (4, 0)
+        finally:
+            for c in fresh:
+                c.close()
+        # world = 1: nothing to push or wait for, the result is the own slot
+        w1 = (n_all + 31) // 32
+        b1 = torch.zeros(int(rc.lib().rc_gather_buffer_words(1, w1)), dtype=torch.int32, device="cuda")
+        d_all = torch.from_numpy(confs).cuda()
+        off = ranks[0].check_gather(d_all, n_all, None, [b1.data_ptr()], 0, w1, s)
+        torch.cuda.synchronize()
+        assert np.array_equal(sh.unpack_bitmask(b1[off:off + w1].cpu().numpy(), w1 * 32)[:n_all], single)
+    finally:
+        for c in ranks:
+            c.close()
