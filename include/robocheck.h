@@ -285,9 +285,9 @@ int rc_audit(rc_ctx *ctx, const rc_config *d_confs, long n, long *n_flags_differ
  * (robot triangle, obstacle triangle) pairs of 9 floats each (the role of the reference's host-side
  * unit tests, narrow-phase/test-narrow-phase.cu:7-626).  h_out32[32 * i ...]: 0-2 Nr, 3 dr, 4-6
  * signed distances of the obstacle vertices, 7-9 No, 10 do, 11-13 signed distances of the robot
- * vertices, 14-16 D, 17-19 O, 20-23 t_r01 t_r12 t_o01 t_o12 (14-23 only when both plane tests pass
- * and the pair is not coplanar).  h_verdict[i] = plane test O | plane test R << 1 | tail << 2, tail:
- * 0 miss, 1 hit, 2 coplanar.  rc_kat_la_solve: la_solve on (A1 A2 A3 A4 b1 b2) -> (x1 x2). */
+ * vertices, 14-16 D, 17-19 O, 20-23 t_r01 t_r12 t_o01 t_o12 (14-23 unless the planes are coplanar).
+ * h_verdict[i] = plane test O | plane test R << 1 | tail << 2, tail: 0 miss, 1 hit, 2 coplanar (what
+ * the tail would say; the kernels only ask it when both plane tests pass).  rc_kat_la_solve: la_solve on (A1 A2 A3 A4 b1 b2) -> (x1 x2). */
 int rc_kat_pairs(rc_ctx *ctx, const float *h_rob9, const float *h_obs9, int n, float *h_out32, int *h_verdict);
 int rc_kat_la_solve(rc_ctx *ctx, const float *h_in6, int n, float *h_out2);
 

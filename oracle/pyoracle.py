@@ -101,7 +101,7 @@ def pair_intermediates(r9, o9):
     out[7:10], out[10], out[11:14] = list(No), do_.value, list(dR)
     sO, sR = int(not L.rco_no_overlap(dO, 1)), int(not L.rco_no_overlap(dR, 1))
     tail = 0
-    if sO and sR:
+    if True:  # the tail is evaluated unconditionally (rc_kat_pairs does the same); it matters when sO and sR
         if L.rco_is_coplanar(Nr, dr, No, do_):
             tail = 2
         else:

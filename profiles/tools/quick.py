@@ -37,7 +37,8 @@ def timeit(ctx, confs, reps, mode=rc.RC_MODE_CULLED):
 
 ctx = rc.Context(device=0)
 rows = []
-for name, n, hard, seed, reps in (("hard100k", 100_000, True, 508, 40), ("hard10k", 10_000, True, 508, 40),
+for name, n, hard, seed, reps in (("easy2k_floor", 2_000, False, 510, 40), ("hard64", 64, True, 508, 40),
+                                  ("hard100k", 100_000, True, 508, 40), ("hard10k", 10_000, True, 508, 40),
                                   ("hard2k", 2_000, True, 508, 40), ("hard1M", 1_000_000, True, 512, 8),
                                   ("easy1M", 1_000_000, False, 510, 20)):
     med, best, nv = timeit(ctx, rc.createAlphaBotConfigurations(n, hard, seed), reps)

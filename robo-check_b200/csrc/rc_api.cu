@@ -142,6 +142,11 @@ int upload_obstacle(rc_ctx *ctx, const GatheredTris &g, float4 **a, float4 **b, 
         (e = dev_alloc(ctx, a, n)) || (e = dev_alloc(ctx, b, n)) || (e = dev_alloc(ctx, c, n)) ||
         (e = dev_alloc(ctx, d, (n + 3) & ~(size_t)3)))
         return check_cuda(ctx, e, "obstacle upload");
+    // dev_alloc clears with cudaMemset on the legacy default stream, which does NOT order against the
+    // context's non-blocking stream: without this the clear of a large table could land after the
+    // kernel below has filled it (seen once in a few hundred context builds on the 16,128-triangle
+    // obstacle: part of the table read back as zeros, collisions missed)
+    if ((e = cudaDeviceSynchronize())) return check_cuda(ctx, e, "obstacle upload sync");
     if ((e = launch_obstacle_planes(ra, rb, rcv, *a, *b, *c, *d, (int)n, ctx->own_stream)))
         return check_cuda(ctx, e, "obstacle planes");
     return check_cuda(ctx, cudaStreamSynchronize(ctx->own_stream), "obstacle planes sync");
@@ -339,6 +344,7 @@ int rc_create(rc_ctx **out, const float *rob_x, const float *rob_y, const float 
         ctx->knob_split_max = knob("RC_SPLIT_MAX", 16);
         ctx->knob_split_load = knob("RC_SPLIT_LOAD", 8);
         ctx->knob_host_chunks = knob("RC_HOST_CHUNKS", 0);
+        ctx->knob_gmail = knob("RC_GMAIL", 8);
     }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
@@ -424,9 +430,17 @@ int rc_create(rc_ctx **out, const float *rob_x, const float *rob_y, const float 
             for (int k = 0; k < 3; k++) ext = std::max(ext, (double)std::fabs(t.rob_center[k]) + t.rob_radius);
             t.box_margin = std::max(kBoxMargin, (float)(4e-6 * ext));
         }
-        const Bvh rb = build_bvh(rob_x, rob_y, rob_z, rob_v1, rob_v2, rob_v3, n_rob_t, t.box_margin);
         const Bvh ob = build_bvh(obs_x, obs_y, obs_z, obs_v1, obs_v2, obs_v3, n_obs_t, t.box_margin);
+        Bvh rb = build_bvh(rob_x, rob_y, rob_z, rob_v1, rob_v2, rob_v3, n_rob_t, t.box_margin);
         t.n_rob_nodes = rb.n_nodes; t.n_obs_nodes = ob.n_nodes;
+        // An obstacle that does not fit into shared memory stays in global memory; it is then much
+        // finer than the robot, whose tree gets one triangle per leaf (node indices are 11 bits there)
+        t.gobs = !culled_obstacle_in_shared(ctx);
+        if (t.gobs && 2 * n_rob_t - 1 < (1 << 11)) {
+            rb = build_bvh(rob_x, rob_y, rob_z, rob_v1, rob_v2, rob_v3, n_rob_t, t.box_margin, 1);
+            t.rob_leaf = 1;
+            t.n_rob_nodes = rb.n_nodes;
+        }
         for (int d = 0; d < 4; d++) {
             const std::vector<int> cr = rb.cut(d), co = ob.cut(d);
             t.n_seed_r[d] = (int)std::min<size_t>(cr.size(), 8);
@@ -435,6 +449,18 @@ int rc_create(rc_ctx **out, const float *rob_x, const float *rob_y, const float 
                 t.seed_r[d][q] = (uint32_t)(q < (int)cr.size() ? cr[q] : 0);
                 t.seed_o[d][q] = (uint32_t)(q < (int)co.size() ? co[q] : 0);
             }
+        }
+        // plane of every robot triangle in the robot frame, leaf order: n = (b - a) x (c - b), s = n . a
+        std::vector<float4> rpl((size_t)n_rob_t);
+        for (int p = 0; p < n_rob_t; p++) {
+            const int k = rb.order[p];
+            const double a[3] = {rob_x[rob_v1[k]], rob_y[rob_v1[k]], rob_z[rob_v1[k]]};
+            const double b[3] = {rob_x[rob_v2[k]], rob_y[rob_v2[k]], rob_z[rob_v2[k]]};
+            const double c3[3] = {rob_x[rob_v3[k]], rob_y[rob_v3[k]], rob_z[rob_v3[k]]};
+            const double e1[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, e2[3] = {c3[0] - b[0], c3[1] - b[1], c3[2] - b[2]};
+            const double nn[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+            rpl[p] = make_float4((float)nn[0], (float)nn[1], (float)nn[2],
+                                 (float)(nn[0] * a[0] + nn[1] * a[1] + nn[2] * a[2]));
         }
         std::vector<uint2> rts((size_t)n_rob_t);
         for (int p = 0; p < n_rob_t; p++) rts[p] = rt[rb.order[p]];
@@ -454,6 +480,7 @@ int rc_create(rc_ctx **out, const float *rob_x, const float *rob_y, const float 
         if ((e = upload(ctx, &t.rob_v, rv)) || (e = upload(ctx, &t.rob_aos, raos)) ||
             (e = upload(ctx, &t.rob_t, rt, rt_pad)) || (e = upload(ctx, &t.rob_t_sorted, rts, rt_pad)) ||
             (e = upload(ctx, &t.rob_bvh, rbn)) || (e = upload(ctx, &t.obs_bvh, obn)) ||
+            (e = upload(ctx, &t.rob_plane, rpl)) ||
             (e = dev_alloc(ctx, &ctx->d_counters, RC_NUM_COUNTERS)) ||
             (e = dev_alloc(ctx, &ctx->d_queues, kHostChunks)) ||
             (e = dev_alloc(ctx, &ctx->d_work_count, kWorkCounters)) ||
@@ -473,6 +500,9 @@ int rc_create(rc_ctx **out, const float *rob_x, const float *rob_y, const float 
             break;
     } while (0);
 
+    // every table and every cleared scratch word is in place before the first launch, whatever stream
+    // (blocking or not) the caller brings
+    if (rcode == RC_OK && (e = cudaDeviceSynchronize()) != cudaSuccess) rcode = check_cuda(ctx, e, "rc_create sync");
     if (rcode != RC_OK) {  // the context is discarded; the code says what failed (never prints)
         rc_destroy(ctx);
         return rcode;
@@ -495,6 +525,8 @@ void rc_destroy(rc_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     for (void *p : ctx->allocations) cudaFree(p);
+    for (cudaEvent_t ev : ctx->ev_wave)
+        if (ev) cudaEventDestroy(ev);
     if (ctx->h_pinned_confs) cudaFreeHost(ctx->h_pinned_confs);
     if (ctx->h_pinned_valid) cudaFreeHost(ctx->h_pinned_valid);
     if (ctx->d_stage_confs) cudaFree(ctx->d_stage_confs);
@@ -715,17 +747,62 @@ int rc_check_host(rc_ctx *ctx, const rc_config *h_confs, long n, uint8_t *h_vali
         }
         cudaGetLastError();
     }
-    if ((e = cudaMemcpyAsync(ctx->d_stage_confs, src, (size_t)n * sizeof(rc_config),
-                             cudaMemcpyHostToDevice, s)))
-        return check_cuda(ctx, e, "H2D configurations");
-    cudaEventRecord(ctx->ev0, s);
-    if ((rcode = check_on_stream(ctx, ctx->d_stage_confs, n, d_out, nullptr, mode, s, nullptr,
-                                 "rc_check_host launch")) != RC_OK)
-        return rcode;
-    cudaEventRecord(ctx->ev1, s);
-    if ((!direct && (e = cudaMemcpyAsync(dst, ctx->d_stage_valid, (size_t)n, cudaMemcpyDeviceToHost, s))) ||
-        (e = cudaStreamSynchronize(s)))
-        return check_cuda(ctx, e, "D2H flags");
+    // Waves (RC_HOST_CHUNKS = 2 .. 4; default 1 = off): the batch is cut into contiguous pieces; the
+    // configurations of piece k+1 travel on the copy stream while the kernels of piece k run, and the
+    // flags of piece k travel back while piece k+1 is being checked.  Measured on 100,000 hard
+    // configurations (profiles/host_waves_r02.txt): 208 M configs/s in one piece, 184 M in two, 130 M
+    // in four -- every piece pays the two launches, the stream hand-overs and the fixed start-up of the
+    // descent again, which is more than the 25-50 us of copy it hides.  A caller that wants the copy
+    // hidden keeps two whole batches in flight instead (rc_check_host_submit / _wait: 0.96 of the
+    // device-resident rate).
+    int waves = ctx->knob_host_chunks > 0 ? std::min(ctx->knob_host_chunks, kHostWaves) : 1;
+    if (direct || n < 4096) waves = 1;
+    if (waves <= 1) {
+        if ((e = cudaMemcpyAsync(ctx->d_stage_confs, src, (size_t)n * sizeof(rc_config),
+                                 cudaMemcpyHostToDevice, s)))
+            return check_cuda(ctx, e, "H2D configurations");
+        cudaEventRecord(ctx->ev0, s);
+        if ((rcode = check_on_stream(ctx, ctx->d_stage_confs, n, d_out, nullptr, mode, s, nullptr,
+                                     "rc_check_host launch")) != RC_OK)
+            return rcode;
+        cudaEventRecord(ctx->ev1, s);
+        if ((!direct && (e = cudaMemcpyAsync(dst, ctx->d_stage_valid, (size_t)n, cudaMemcpyDeviceToHost, s))) ||
+            (e = cudaStreamSynchronize(s)))
+            return check_cuda(ctx, e, "D2H flags");
+    } else {
+        cudaStream_t copy = ctx->own_stream2;
+        for (int w = 0; w < 2 * waves; w++)
+            if (!ctx->ev_wave[w] && (e = cudaEventCreateWithFlags(&ctx->ev_wave[w], cudaEventDisableTiming)))
+                return check_cuda(ctx, e, "wave events");
+        const long per = ((n + waves - 1) / waves + 31) / 32 * 32;
+        // the copy stream first waits for whatever the compute stream still reads from the staging area
+        if ((e = cudaEventRecord(ctx->ev_join, s)) || (e = cudaStreamWaitEvent(copy, ctx->ev_join, 0)))
+            return check_cuda(ctx, e, "wave join");
+        for (int w = 0; w < waves; w++) {
+            const long lo = std::min(n, w * per), cnt = std::min(n, lo + per) - lo;
+            if (cnt <= 0) continue;
+            if ((e = cudaMemcpyAsync(ctx->d_stage_confs + lo, src + lo, (size_t)cnt * sizeof(rc_config),
+                                     cudaMemcpyHostToDevice, copy)) ||
+                (e = cudaEventRecord(ctx->ev_wave[w], copy)))
+                return check_cuda(ctx, e, "H2D configurations (wave)");
+        }
+        for (int w = 0; w < waves; w++) {
+            const long lo = std::min(n, w * per), cnt = std::min(n, lo + per) - lo;
+            if (cnt <= 0) continue;
+            if ((e = cudaStreamWaitEvent(s, ctx->ev_wave[w], 0))) return check_cuda(ctx, e, "wave wait");
+            if (w == 0) cudaEventRecord(ctx->ev0, s);
+            if ((rcode = check_on_stream(ctx, ctx->d_stage_confs + lo, cnt, ctx->d_stage_valid + lo, nullptr, mode, s,
+                                         nullptr, "rc_check_host launch (wave)")) != RC_OK)
+                return rcode;
+            if ((e = cudaEventRecord(ctx->ev_wave[waves + w], s)) ||
+                (e = cudaStreamWaitEvent(copy, ctx->ev_wave[waves + w], 0)) ||
+                (e = cudaMemcpyAsync(dst + lo, ctx->d_stage_valid + lo, (size_t)cnt, cudaMemcpyDeviceToHost, copy)))
+                return check_cuda(ctx, e, "D2H flags (wave)");
+        }
+        cudaEventRecord(ctx->ev1, s);
+        if ((e = cudaStreamSynchronize(copy)) || (e = cudaStreamSynchronize(s)))
+            return check_cuda(ctx, e, "wave synchronise");
+    }
     cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev0, ctx->ev1);
     if (!out_pinned) std::memcpy(h_valid, ctx->h_pinned_valid, (size_t)n);
     return RC_OK;
@@ -1353,7 +1430,8 @@ int rc_stats_read(rc_ctx *ctx, rc_stats *out, int reset)
     out->prefilter_pairs = h[CNT_PREFILTER]; out->plane1_pairs = h[CNT_PLANE1];
     if (reset) {
         ctx->launches = 0;
-        if ((e = cudaMemset(ctx->d_counters, 0, sizeof h))) return check_cuda(ctx, e, "rc_stats reset");
+        if ((e = cudaMemset(ctx->d_counters, 0, sizeof h)) || (e = cudaDeviceSynchronize()))
+            return check_cuda(ctx, e, "rc_stats reset");
     }
     return RC_OK;
 }

@@ -33,7 +33,8 @@ constexpr int kStackCapGlobal = 1536;  // obstacle tables in global memory: deep
 // the deepest stack seen on alpha1.0 is ~200 pairs, so more warps per CTA can live with smaller stacks
 __host__ __device__ constexpr int stack_cap_of(int warps, bool gobs)
 {
-    return gobs ? (warps > 24 ? 1024 : kStackCapGlobal) : (warps > 28 ? 512 : warps > 24 ? 768 : kStackCap);
+    // (rounds pop a single pair near the capacity, see kNarrowPop, so small stacks do not overflow)
+    return gobs ? (warps > 24 ? 640 : warps > 16 ? 1024 : kStackCapGlobal) : (warps > 28 ? 512 : warps > 24 ? 768 : kStackCap);
 }
 constexpr int kLeafTrisDev = 4;  // must match rc::kLeafTris of the host builder (rc_bvh.h)
 constexpr int kClassifyBoxes = 32;  // vertex groups of the robot bounded in classify_kernel
@@ -109,6 +110,8 @@ struct CulledArgs {
     int n_seed_r3, n_seed_o3;
     uint32_t *hit_counts;            // STATS kernels: hitting pairs per configuration, no early exit (rc_hit_counts)
     GMailBox *gmail;                 // production kernels: hand-over between CTAs (zero outside a launch)
+    int gmail_min_load;              // ... used when the list holds at least this many entries per warp of the grid (< 0: never)
+    const float4 *rob_plane;         // RL1 kernels: plane of every robot triangle in the robot frame, leaf order
     GatherArgs g;                    // g.world > 1: the last CTA pushes the bitmask slot to the peers (rc_gather.cuh)
 };
 
@@ -331,9 +334,15 @@ __device__ __forceinline__ void publish_invalid(const CheckArgs &a, long i, int 
     }
 }
 
-template <bool STATS, int WARPS, bool GOBS, bool COP>
+// RL1 (with GOBS) = every leaf of the robot tree holds ONE triangle and the kernel knows its plane in
+// the robot frame: for an obstacle much finer than the robot (the subdivided obstacle: a robot triangle
+// is a thousand times the area of an obstacle triangle) the box of a four-triangle robot leaf is a poor
+// bound, while the slab of ONE robot triangle's plane culls every obstacle box that stays on one side
+// of it -- exactly the pairs the reference's first plane test rejects.
+template <bool STATS, int WARPS, bool GOBS, bool COP, bool RL1>
 __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __grid_constant__ CulledArgs a)
 {
+    static_assert(!RL1 || GOBS, "one-triangle robot leaves are used with the obstacle in global memory");
     constexpr int SH = GOBS ? 21 : 16;
     constexpr uint32_t LOW = (1u << SH) - 1u;
     constexpr int kStack = stack_cap_of(WARPS, GOBS);
@@ -349,7 +358,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
     float4 *s_obs_c = s_obs_b + (GOBS ? 0 : c.n_obs_t);
     float *s_obs_d = reinterpret_cast<float *>(s_obs_c + (GOBS ? 0 : c.n_obs_t));
     uint2 *s_rob_t = reinterpret_cast<uint2 *>(s_obs_d + (GOBS ? 0 : pad4(c.n_obs_t)));
-    uint32_t *s_work = reinterpret_cast<uint32_t *>(s_rob_t + c.n_rob_t + (c.n_rob_t & 1));
+    float4 *s_rob_plane = reinterpret_cast<float4 *>(s_rob_t + c.n_rob_t + (c.n_rob_t & 1));  // RL1: (n, s) per triangle, robot frame
+    uint32_t *s_work = reinterpret_cast<uint32_t *>(s_rob_plane + (RL1 ? c.n_rob_t : 0));
     Mail *s_mail = reinterpret_cast<Mail *>(s_work + WARPS * kWarpWork);
     uint32_t *s_pend = reinterpret_cast<uint32_t *>(s_mail + kMailSlots);
     uint32_t *s_idle = s_pend + WARPS;
@@ -372,17 +382,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
         mbar_fence_init();
     }
     if (threadIdx.x < kMailSlots) s_mail[threadIdx.x].state = 0u;
-    if (threadIdx.x <= WARPS + 6) s_pend[threadIdx.x] = 0u;  // s_pend, s_idle, s_misc
+    if (threadIdx.x <= WARPS + 6) s_pend[threadIdx.x] = 0u;  // s_pend, s_idle, s_misc[0..5]
     __syncthreads();
     if (threadIdx.x == 0) {
         const uint32_t bv = c.n_rob_v_pad * 16u, bo = c.n_obs_t * 16u,
                        bt = (c.n_rob_t + (c.n_rob_t & 1)) * 8u;
         const uint32_t brn = a.n_rob_nodes * 32u, bon = a.n_obs_nodes * 32u;
         const uint32_t bd = pad4(c.n_obs_t) * 4u;
-        mbar_expect_tx(bar, bv + bt + brn + (GOBS ? 0u : 3u * bo + bd + bon));
+        mbar_expect_tx(bar, bv + bt + brn + (GOBS ? 0u : 3u * bo + bd + bon) + (RL1 ? c.n_rob_t * 16u : 0u));
         tma_load_1d(s_rob_v, c.rob_v, bv, bar);
         tma_load_1d(s_rob_bvh, a.rob_bvh, brn, bar);
         tma_load_1d(s_rob_t, c.rob_t, bt, bar);
+        if (RL1) tma_load_1d(s_rob_plane, a.rob_plane, c.n_rob_t * 16u, bar);
         if (!GOBS) {
             tma_load_1d(s_obs_bvh, a.obs_bvh, bon, bar);
             tma_load_1d(s_obs_a, c.obs_a, bo, bar);
@@ -409,6 +420,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
                    ((unsigned long long)acc << (gs + 1)) <= (unsigned long long)a.split_load * gridDim.x * WARPS)
                 gs++;
         s_misc[0] = gs;
+        // mail between CTAs pays when the list is long (the end of a 100,000-configuration launch: -3 %,
+        // of a million: -6 %); on a short list the warps of one CTA keep each other busy and waiting for
+        // the whole grid to go quiet would only add latency (measured: +10 us on 2,000 configurations)
+        s_misc[5] = (!STATS && a.gmail_min_load >= 0 &&
+                     ((unsigned long long)acc << gs) >= (unsigned long long)a.gmail_min_load * gridDim.x * WARPS) ? 1u : 0u;
     }
     __syncthreads();
     mbar_wait(bar, 0);
@@ -430,6 +446,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
     // count per configuration.
     constexpr bool OPT = !STATS;
     GMailBox *const g = a.gmail;
+#define use_gmail (OPT && ld_volatile(&s_misc[5]) != 0u)  /* read where needed: not worth a register across the descent loop */
 
     // Guided self-scheduling over the work list: chunks while plenty of work is left, single
     // entries near the end so that no warp is left holding a long chunk.  The cost of one
@@ -481,7 +498,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
             // ---- one-way mail: poll the slots of the CTA, every fourth time those of the grid ----
             // the grid counts CTAs whose warps are ALL polling (a few thousand warps bumping one word
             // would take longer than a short kernel lasts)
-            if (lane == 0 && atomicAdd(&s_misc[4], 1u) == (uint32_t)WARPS - 1u) atomicAdd(&g->idle, 1u);
+            if (use_gmail && lane == 0 && atomicAdd(&s_misc[4], 1u) == (uint32_t)WARPS - 1u) atomicAdd(&g->idle, 1u);
             int k;  // 0 .. kMailSlots - 1: slot of the CTA; kMailSlots + q: slot q of the grid; -2: leave
             for (uint32_t spins = 0;; spins++) {
                 k = -1;
@@ -493,10 +510,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
                             break;
                         }
                     if (k < 0) {
-                        if (ld_volatile(&s_misc[2]) != 0u) k = -2;  // a scout of this CTA has seen the grid go quiet
-                        // ONE warp of the CTA at a time looks at the grid (a few thousand warps polling the
-                        // same two cache lines would slow down the warps that still work)
-                        else scout = atomicCAS(&s_misc[3], 0u, 1u) == 0u ? 1 : 0;
+                        if (!use_gmail) {
+                            // mail inside the CTA only: leave when every warp of the CTA has found the list dry
+                            // (a warp that still works on a piece picks up whatever it posts itself)
+                            if (ld_volatile(s_idle) == (uint32_t)WARPS) k = -2;
+                        } else if (ld_volatile(&s_misc[2]) != 0u) {
+                            k = -2;  // a scout of this CTA has seen the grid go quiet
+                        } else {
+                            // ONE warp of the CTA at a time looks at the grid (a few thousand warps polling
+                            // the same two cache lines would slow down the warps that still work)
+                            scout = atomicCAS(&s_misc[3], 0u, 1u) == 0u ? 1 : 0;
+                        }
                     }
                 }
                 k = __shfl_sync(kFull, k, 0);
@@ -529,7 +553,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
                 __nanosleep(200);
             }
             if (k == -2) break;
-            if (lane == 0 && atomicSub(&s_misc[4], 1u) == (uint32_t)WARPS) atomicSub(&g->idle, 1u);
+            if (use_gmail && lane == 0 && atomicSub(&s_misc[4], 1u) == (uint32_t)WARPS) atomicSub(&g->idle, 1u);
             int cnt, kind;
             uint32_t e;
             if (k < kMailSlots) {
@@ -722,7 +746,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
                             break;
                         }
                 k = __shfl_sync(kFull, k, 0);
-                if (OPT && k < 0 && ((sp + lq + tq) & 3) == 0) {
+                if (OPT && use_gmail && k < 0 && ((sp + lq + tq) & 3) == 0) {
                     // the slots of the CTA are full (its warps without work have all they can take):
                     // the grid.  One read tells whether anybody out there is polling at all.
                     uint32_t idle = 0;
@@ -827,7 +851,53 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
                 __syncwarp();
                 continue;
             }
-            if (lq >= a.leaf_thresh || sp == 0) {
+            if (RL1 && (lq >= a.leaf_thresh || sp == 0)) {
+                // ---- C (one-triangle robot leaves): up to eight leaf pairs, lane = (slot, obstacle
+                // triangle of the leaf); the four lanes of a slot share the robot triangle
+                const int cnt = min(lq, 8);
+                lq -= cnt;
+                const int slot = lane >> 2, q = lane & 3;
+                bool act = slot < cnt;
+                const uint32_t e = leafq[lq + (act ? slot : 0)];
+                const int na = (int)(e >> SH), nb = (int)(e & LOW);
+                const uint32_t j = __float_as_uint(s_rob_bvh[2 * na].w) & 0x7fffffffu;
+                const uint32_t ofirst = __float_as_uint(obs_node(nb, 0).w) & 0x7fffffffu;
+                const int ocount = (int)__float_as_uint(obs_node(nb, 1).w);
+                act = act && q < ocount;
+                const int k = (int)ofirst + (act ? q : 0);
+                const float4 oa = obs_A(k), ob = obs_B(k), oc = obs_C(k);
+                const uint2 ti = s_rob_t[j];
+                const float4 A = s_rob_v[ti.x & 0xffffu], B = s_rob_v[ti.x >> 16], C = s_rob_v[ti.y];
+                Tri r;
+                xform(m, A.x, A.y, A.z, r.ax, r.ay, r.az);
+                xform(m, B.x, B.y, B.z, r.bx, r.by, r.bz);
+                xform(m, C.x, C.y, C.z, r.cx, r.cy, r.cz);
+                const Plane pr = plane_of(r);
+                bool pass = act &&
+                            fminf(fminf(oa.x, ob.x), oc.x) <= fmaxf(fmaxf(r.ax, r.bx), r.cx) + a.tri_margin &&
+                            fmaxf(fmaxf(oa.x, ob.x), oc.x) >= fminf(fminf(r.ax, r.bx), r.cx) - a.tri_margin &&
+                            fminf(fminf(oa.y, ob.y), oc.y) <= fmaxf(fmaxf(r.ay, r.by), r.cy) + a.tri_margin &&
+                            fmaxf(fmaxf(oa.y, ob.y), oc.y) >= fminf(fminf(r.ay, r.by), r.cy) - a.tri_margin &&
+                            fminf(fminf(oa.z, ob.z), oc.z) <= fmaxf(fmaxf(r.az, r.bz), r.cz) + a.tri_margin &&
+                            fmaxf(fmaxf(oa.z, ob.z), oc.z) >= fminf(fminf(r.az, r.bz), r.cz) - a.tri_margin;
+                if (STATS) st_pre += __popc(__ballot_sync(kFull, pass));
+                if (pass)
+                    pass = straddles(sdist(pr, oa.x, oa.y, oa.z), sdist(pr, ob.x, ob.y, ob.z),
+                                     sdist(pr, oc.x, oc.y, oc.z));
+                if (STATS) st_pl1 += __popc(__ballot_sync(kFull, pass));
+                if (pass) {
+                    const Plane po = {oa.w, ob.w, oc.w, obs_D(k)};
+                    pass = straddles(sdist(po, r.ax, r.ay, r.az), sdist(po, r.bx, r.by, r.bz),
+                                     sdist(po, r.cx, r.cy, r.cz));
+                }
+                const unsigned mp = __ballot_sync(kFull, pass);
+                if (pass) tailq[tq + __popc(mp & lt)] = (j << SH) | (uint32_t)k;
+                tq += __popc(mp);
+                if (STATS) { st_leaves += cnt; st_tris += (act ? 1 : 0); st_lr++; tr_leaves++; }
+                __syncwarp();
+                continue;
+            }
+            if (!RL1 && (lq >= a.leaf_thresh || sp == 0)) {
                 // ---- C: up to eight leaf pairs, lane = (slot, robot triangle of the leaf)
                 const int cnt = min(lq, 8);
                 lq -= cnt;
@@ -895,10 +965,28 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
             const int na = (int)(e >> SH), nb = (int)(e & LOW);
             const float4 r0 = s_rob_bvh[2 * na], r1 = s_rob_bvh[2 * na + 1];
             const float4 o0 = obs_node(nb, 0), o1 = obs_node(nb, 1);
-            const bool ov = act && boxes_overlap(m, r0, r1, o0, o1);
+            bool ov = act && boxes_overlap(m, r0, r1, o0, o1);
             const uint32_t ra = __float_as_uint(r0.w), rb = __float_as_uint(r1.w);
             const uint32_t oa = __float_as_uint(o0.w), ob = __float_as_uint(o1.w);
             const bool la = (ra & 0x80000000u) != 0, lb = (oa & 0x80000000u) != 0;
+            if constexpr (RL1) {
+                if (ov && la) {
+                    // the robot node is ONE triangle: an obstacle box that stays on one side of its plane
+                    // holds no triangle whose vertices straddle that plane (the reference's first test).
+                    // World normal n = R n_local, n . p = s_local + n . t on the triangle; the box is cut
+                    // by the plane iff |n . c - s| <= |n| . e.  e carries the box margin (the clearance);
+                    // the slack covers the rounding of these few operations at scene scale.
+                    const float4 pl = s_rob_plane[ra & 0x7fffffffu];
+                    const float nx = fmaf(m.r02, pl.z, fmaf(m.r01, pl.y, m.r00 * pl.x));
+                    const float ny = fmaf(m.r12, pl.z, fmaf(m.r11, pl.y, m.r10 * pl.x));
+                    const float nz = fmaf(m.r22, pl.z, fmaf(m.r21, pl.y, m.r20 * pl.x));
+                    const float sw = fmaf(nz, m.tz, fmaf(ny, m.ty, fmaf(nx, m.tx, pl.w)));
+                    const float dist = fmaf(nz, o0.z, fmaf(ny, o0.y, nx * o0.x)) - sw;
+                    const float rad = fmaf(fabsf(nz), o1.z, fmaf(fabsf(ny), o1.y, fabsf(nx) * o1.x));
+                    const float mag = fmaf(fabsf(nz), fabsf(o0.z), fmaf(fabsf(ny), fabsf(o0.y), fabsf(nx * o0.x))) + fabsf(sw);
+                    if (fabsf(dist) > fmaf(1e-5f, mag, rad)) ov = false;
+                }
+            }
             if (STATS) { st_nodes += cnt; st_nr++; tr_nodes++; tr_maxsp = max(tr_maxsp, (uint32_t)(sp + cnt)); }
             __syncwarp();  // everybody has read its entry before the slots are reused
             const bool ll = ov && la && lb;
@@ -1012,25 +1100,38 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
     }
 }
 
+#undef use_gmail
+
 static size_t culled_smem_bytes(const DeviceTables &t, int warps, bool gobs)
 {
     size_t b = 16 + (size_t)t.n_rob_v_pad * 16 + (size_t)t.n_rob_nodes * 32 +
                (size_t)(t.n_rob_t + (t.n_rob_t & 1)) * 8;
     if (!gobs)
         b += (size_t)t.n_obs_nodes * 32 + (size_t)t.n_obs_t * 48 + (size_t)pad4(t.n_obs_t) * 4;
+    else if (t.rob_leaf == 1)
+        b += (size_t)t.n_rob_t * 16;  // robot triangle planes
     b += (size_t)warps * (stack_cap_of(warps, gobs) + kLeafQCap + kTailQCap) * 4;
     b = (b + 15) / 16 * 16 + kMailSlots * sizeof(Mail) + (3 * (size_t)warps + 7 + kWorkBins + 1 + 2) * 4;  // + s_pend, s_idle, s_misc, s_bin, s_wait
     return b;
 }
 
-template <bool GOBS, bool COP>
+template <bool GOBS, bool COP, bool RL1>
 static void (*pick_culled(int warps, int want_stats))(const CulledArgs)
 {
-    if (warps == 16) return want_stats ? check_culled_kernel<true, 16, GOBS, COP> : check_culled_kernel<false, 16, GOBS, COP>;
-    if (warps == 20) return want_stats ? check_culled_kernel<true, 20, GOBS, COP> : check_culled_kernel<false, 20, GOBS, COP>;
-    if (warps == 28) return want_stats ? check_culled_kernel<true, 28, GOBS, COP> : check_culled_kernel<false, 28, GOBS, COP>;
-    if (warps == 32) return want_stats ? check_culled_kernel<true, 32, GOBS, COP> : check_culled_kernel<false, 32, GOBS, COP>;
-    return want_stats ? check_culled_kernel<true, 24, GOBS, COP> : check_culled_kernel<false, 24, GOBS, COP>;
+    if (warps == 16) return want_stats ? check_culled_kernel<true, 16, GOBS, COP, RL1> : check_culled_kernel<false, 16, GOBS, COP, RL1>;
+    if (warps == 32) return want_stats ? check_culled_kernel<true, 32, GOBS, COP, RL1> : check_culled_kernel<false, 32, GOBS, COP, RL1>;
+    return want_stats ? check_culled_kernel<true, 24, GOBS, COP, RL1> : check_culled_kernel<false, 24, GOBS, COP, RL1>;
+}
+
+// Obstacle tables go to shared memory when everything fits with at least 16 warps per CTA; otherwise
+// they stay in global memory (any obstacle size, the robot tables must still fit).  Decided once, when
+// the context is built (the robot tree of a global-obstacle context has one triangle per leaf).
+bool culled_obstacle_in_shared(const rc_ctx *ctx)
+{
+    const DeviceTables &t = ctx->t;
+    if (ctx->knob_global_obstacle) return false;
+    return culled_smem_bytes(t, 16, false) <= (size_t)ctx->max_smem_optin && t.n_obs_nodes <= 65535 &&
+           t.n_rob_nodes <= 65535;
 }
 
 cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, long n,
@@ -1039,14 +1140,9 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
 {
     const DeviceTables &t = ctx->t;
     int warps = ctx->knob_warps;
-    if (warps != 16 && warps != 20 && warps != 24 && warps != 28 && warps != 32) warps = kCulledWarpsDefault;
-    // Obstacle tables go to shared memory when everything fits with at least 16 warps per CTA;
-    // otherwise they stay in global memory (any obstacle size, robot tables must still fit).
-    bool gobs = ctx->knob_global_obstacle;
-    if (!gobs && (culled_smem_bytes(t, 16, false) > (size_t)ctx->max_smem_optin ||
-                  t.n_obs_nodes > 65535 || t.n_rob_nodes > 65535))
-        gobs = true;
-    while (warps > 16 && culled_smem_bytes(t, warps, gobs) > (size_t)ctx->max_smem_optin) warps -= 4;
+    if (warps != 16 && warps != 24 && warps != 32) warps = kCulledWarpsDefault;
+    const bool gobs = t.gobs, rl1 = t.gobs && t.rob_leaf == 1;
+    while (warps > 16 && culled_smem_bytes(t, warps, gobs) > (size_t)ctx->max_smem_optin) warps -= 8;
     const size_t smem = culled_smem_bytes(t, warps, gobs);
     if (smem > (size_t)ctx->max_smem_optin || t.n_rob_v > 65535) return cudaErrorInvalidConfiguration;
     if (gobs && (t.n_rob_nodes >= (1 << 11) || t.n_rob_t >= (1 << 11) || t.n_obs_nodes >= (1 << 21) ||
@@ -1086,6 +1182,8 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
     // marked valid by step 1, overwritten by whichever part of the descent finds a hit
     a.optimistic = want_stats ? 0 : 1;
     a.gmail = reinterpret_cast<GMailBox *>(ctx->d_gmail);
+    a.gmail_min_load = ctx->knob_gmail;
+    a.rob_plane = t.rob_plane;
     a.split_max = max(1, min(kSplitMax, ctx->knob_split_max));
     a.split_load = max(1, ctx->knob_split_load);
     a.tri_margin = 2.f * t.box_margin;
@@ -1114,9 +1212,11 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
     k.optimistic = a.optimistic;
     void (*kern)(const CulledArgs);
     if (ctx->coplanar_mode)
-        kern = gobs ? pick_culled<true, true>(warps, want_stats) : pick_culled<false, true>(warps, want_stats);
+        kern = rl1 ? pick_culled<true, true, true>(warps, want_stats)
+               : gobs ? pick_culled<true, true, false>(warps, want_stats) : pick_culled<false, true, false>(warps, want_stats);
     else
-        kern = gobs ? pick_culled<true, false>(warps, want_stats) : pick_culled<false, false>(warps, want_stats);
+        kern = rl1 ? pick_culled<true, false, true>(warps, want_stats)
+               : gobs ? pick_culled<true, false, false>(warps, want_stats) : pick_culled<false, false, false>(warps, want_stats);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     // small blocks: 100,000 configurations are only 21 warps per SM, spread them evenly

@@ -37,6 +37,9 @@ struct DeviceTables {
     int n_rob_nodes = 0, n_obs_nodes = 0;
     int n_rob_v_pad = 0;        // n_rob_v rounded up to 32 (padding repeats vertex 0)
     float box_margin = 1e-3f;   // inflation of every tree box; scales with the scene (rc_create)
+    bool gobs = false;          // obstacle tables stay in global memory (too large for shared memory)
+    int rob_leaf = 4;           // triangles per leaf of the robot tree: 1 with a global-memory obstacle
+    float4 *rob_plane = nullptr;  // [n_rob_t] plane (n, s = n . p1) of every robot triangle, robot frame, leaf order
     rc_aabb obs_box;
     float rob_center[3];        // bounding sphere of the robot in its local frame
     float rob_radius;
@@ -57,6 +60,7 @@ struct DeviceTables {
 // the long descents are under way early and the work list ends with cheap ones
 constexpr int kWorkBins = 8;
 constexpr size_t kGMailBytes = 16384;  // >= sizeof(rc::GMailBox)
+constexpr int kHostWaves = 4;           // rc_check_host cuts a large batch into at most this many waves
 constexpr int kWorkCounters = 16;  // [0..7] entries per class, [8] next entry, [9] CTAs finished
 
 // one of the two batches rc_check_host_submit may have in flight
@@ -90,6 +94,7 @@ struct rc_ctx {
     int stats_on = 0;
     uint32_t gather_calls = 0;                 // number of the last rc_check_gather call on gather_buf (all ranks in lock-step)
     uint32_t *gather_buf = nullptr;            // the own gather buffer that numbering belongs to
+    cudaEvent_t ev_wave[2 * 4] = {};           // rc_check_host waves: copied (first half), checked (second half)
     cudaEvent_t ev_scratch = nullptr;          // behind the last launch that used the scratch below
     cudaStream_t scratch_stream = nullptr;
     bool scratch_used = false;
@@ -129,6 +134,7 @@ struct rc_ctx {
     int knob_host_direct = 0; // RC_HOST_DIRECT=1: rc_check_host stores the flags into the pinned buffer from the kernels instead of copying them back
     int knob_share = 1;      // RC_SHARE=0: warps of a CTA do not hand pieces of a deep descent to each other
     int knob_split_max = 16;  // RC_SPLIT_MAX: parts a configuration may be cut into when the work list is short (1 = never)
+    int knob_gmail = 8;       // RC_GMAIL: mail between CTAs when the list holds >= this many entries per warp (-1 = never, 0 = always)
     int knob_split_load = 8;  // RC_SPLIT_LOAD: split while entries <= this many per warp of the grid
     std::string last_error;
     std::vector<void *> allocations;
@@ -195,6 +201,7 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
 cudaError_t launch_check_spheres(const rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_valid,
                                  uint32_t *d_bitmask, int want_stats, cudaStream_t stream,
                                  unsigned long long *queue);
+bool culled_obstacle_in_shared(const rc_ctx *ctx);
 cudaError_t launch_gather_push(const rc_ctx *ctx, const GatherArgs &a, cudaStream_t stream);
 cudaError_t launch_gather_wait(const rc_ctx *ctx, const GatherArgs &a, cudaStream_t stream);
 // device known-answer tests of the per-pair helpers (rc_kat.cuh)

@@ -13,8 +13,8 @@ namespace rc {
 
 // One thread per (robot triangle, obstacle triangle) pair, 9 floats each (a, b, c).  out[32 * i ..]:
 //   0-2 Nr  3 dr  4-6 distO   7-9 No  10 do  11-13 distR   14-16 D  17-19 O  20-23 t_r01 t_r12 t_o01 t_o12
-// verdict[i] = straddleO | straddleR << 1 | tail << 2   (tail: 0 miss, 1 hit, 2 coplanar; only
-// evaluated when both plane tests pass, like narrowPhaseKernel_coarse, narrow-phase.cu:619-670)
+// verdict[i] = straddleO | straddleR << 1 | tail << 2   (tail: 0 miss, 1 hit, 2 coplanar; the kernels
+// evaluate it only when both plane tests pass, like narrowPhaseKernel_coarse, narrow-phase.cu:619-670)
 __global__ void kat_pairs_kernel(const float *r9, const float *o9, int n, float *out, int *verdict)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -32,8 +32,10 @@ __global__ void kat_pairs_kernel(const float *r9, const float *o9, int n, float 
     w[7] = po.nx; w[8] = po.ny; w[9] = po.nz; w[10] = -po.s;
     w[11] = dR0; w[12] = dR1; w[13] = dR2;
     const bool sO = straddles(dO0, dO1, dO2), sR = straddles(dR0, dR1, dR2);
-    int tail = 0;
-    if (sO && sR) tail = pair_tail_core<true>(r, pr, dR0, dR1, dR2, o, po, dO0, dO1, dO2, w + 14);
+    // the tail runs unconditionally here (the reference's unit tests exercise the intersection line and
+    // the parametric values on pairs that do not pass both plane tests); the kernels only reach it when
+    // sO && sR, and only then does the verdict's tail field mean anything
+    const int tail = pair_tail_core<true>(r, pr, dR0, dR1, dR2, o, po, dO0, dO1, dO2, w + 14);
     verdict[i] = (sO ? 1 : 0) | (sR ? 2 : 0) | (tail << 2);
 }
 

@@ -16,6 +16,7 @@ constexpr int kSahMaxPrims = 16384;  // nodes larger than this are split at the 
 struct Builder {
     const float *plo, *phi;  // primitive boxes, 3 floats each
     float margin;
+    int leaf;                // primitives per leaf (1 .. kLeafTris)
     std::vector<float> cen;  // 3 per primitive
     Bvh out;
 
@@ -42,7 +43,7 @@ struct Builder {
             // half extent measured from the rounded centre, then inflated
             node[4 + k] = std::max(hi[k] - node[k], node[k] - lo[k]) + margin;
         }
-        if (n <= kLeafTris) {
+        if (n <= leaf) {
             const int first = (int)out.order.size();
             for (int i = 0; i < n; i++) out.order.push_back(tris[i]);
             node[3] = bits(kLeafFlag | (uint32_t)first);
@@ -77,7 +78,7 @@ struct Builder {
                 for (int i = 0; i + 1 < n; i++) {
                     tri_bounds(sorted[i], plo, phi2);
                     const int k = i + 1;  // left gets k primitives
-                    if (k % kLeafTris) continue;
+                    if (k % leaf) continue;
                     const double cost = area(plo, phi2) * k + area(&suf[(size_t)k * 6], &suf[(size_t)k * 6 + 3]) * (n - k);
                     if (cost < best) { best = cost; best_ax = ax; half = k; }
                 }
@@ -98,7 +99,7 @@ struct Builder {
             if (chi[2] - clo[2] > chi[ax] - clo[ax]) ax = 2;
             // left half rounded up to a multiple of the leaf size, so leaves are full
             half = n / 2;
-            half = std::max(kLeafTris, (half + kLeafTris - 1) / kLeafTris * kLeafTris);
+            half = std::max(leaf, (half + leaf - 1) / leaf * leaf);
             if (half >= n) half = n / 2;
             std::nth_element(tris, tris + half, tris + n, [&](int a, int b) {
                 const float ca = cen[3 * (size_t)a + ax], cb = cen[3 * (size_t)b + ax];
@@ -137,9 +138,9 @@ std::vector<int> Bvh::cut(int d) const
     return out;
 }
 
-Bvh build_bvh_boxes(const float *lo, const float *hi, const float *centre, int n, float margin)
+Bvh build_bvh_boxes(const float *lo, const float *hi, const float *centre, int n, float margin, int leaf_tris)
 {
-    Builder b{lo, hi, margin, {}, {}};
+    Builder b{lo, hi, margin, std::max(1, std::min(leaf_tris, kLeafTris)), {}, {}};
     b.cen.assign(centre, centre + 3 * (size_t)std::max(n, 0));
     std::vector<int> prims((size_t)std::max(n, 0));
     std::iota(prims.begin(), prims.end(), 0);
@@ -148,7 +149,7 @@ Bvh build_bvh_boxes(const float *lo, const float *hi, const float *centre, int n
 }
 
 Bvh build_bvh(const float *x, const float *y, const float *z, const int *v1, const int *v2,
-              const int *v3, int n_t, float margin)
+              const int *v3, int n_t, float margin, int leaf_tris)
 {
     std::vector<float> lo(3 * (size_t)std::max(n_t, 1)), hi(lo.size()), cen(lo.size());
     for (int t = 0; t < n_t; t++) {
@@ -161,7 +162,7 @@ Bvh build_bvh(const float *x, const float *y, const float *z, const int *v1, con
             cen[3 * (size_t)t + k] = (a + b2 + d) / 3.0f;
         }
     }
-    return build_bvh_boxes(lo.data(), hi.data(), cen.data(), n_t, margin);
+    return build_bvh_boxes(lo.data(), hi.data(), cen.data(), n_t, margin, leaf_tris);
 }
 
 void triangle_spheres(const float *x, const float *y, const float *z, const int *v1, const int *v2,

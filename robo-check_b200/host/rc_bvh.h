@@ -23,10 +23,13 @@ struct Bvh {
     std::vector<int> cut(int d) const;
 };
 
+// leaf_tris: triangles per leaf, 1 .. kLeafTris (the robot tree of a context whose obstacle is much
+// finer than the robot is built with one triangle per leaf: a leaf box is then a triangle box)
 Bvh build_bvh(const float *x, const float *y, const float *z, const int *v1, const int *v2,
-              const int *v3, int n_t, float margin);
+              const int *v3, int n_t, float margin, int leaf_tris = kLeafTris);
 // Same tree over arbitrary primitives given by their boxes (3 floats each) and sort keys.
-Bvh build_bvh_boxes(const float *lo, const float *hi, const float *centre, int n, float margin);
+Bvh build_bvh_boxes(const float *lo, const float *hi, const float *centre, int n, float margin,
+                    int leaf_tris = kLeafTris);
 
 // Bounding sphere of every triangle (smallest enclosing: mid-point of the longest edge if the
 // triangle is obtuse, circumsphere otherwise), radius rounded up.  out = n_t x (x, y, z, r).
