@@ -22,7 +22,11 @@ WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "dram__throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__t_sector_hit_rate.pct", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
-        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"]
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "smsp__inst_executed_op_branch.sum", "sass__inst_executed_register_spilling",
+        "lts__t_bytes.sum", "lts__t_sectors_srcunit_tex_op_read.sum"]
 STALL = [h for h in hdr if "pcsamp_warps_issue_stalled" in h and "not_issued" not in h]
 print(f"# {title}\n")
 print("`ncu --set full --clock-control none --import-source on`, run after the same command exited 0 "
@@ -54,9 +58,24 @@ if len(sys.argv) > 3:
         scale = {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
         return None if v is None else v * scale
 
+    def short(name):
+        # check_culled_kernel<stats, warps, obstacle in global memory, coplanar, one-triangle robot leaves>
+        base = name.split("<")[0].replace("rc::", "")
+        if base == "check_culled_kernel" and "<" in name:
+            args = [a.strip() for a in name.split("<", 1)[1].rstrip(">").split(",")]
+            if len(args) >= 3 and args[2] in ("1", "true", "(bool)1"):
+                base += "_gobs"
+        return base
+
     out = {}
     for name, r in last.items():
-        out[name.split("<")[0].replace("rc::", "")] = {
+        conf, wave = num(r, "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"), num(r, "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum")
+        out[short(name)] = {
+            "kernel": name,
+            "inst_executed": num(r, "smsp__inst_executed.sum"),
+            "bank_conflict_share": (conf / wave) if conf is not None and wave else None,
+            "lsu_pipe_pct": num(r, "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"),
+            "occupancy_pct": num(r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
             "duration_ms_under_ncu": num(r, "gpu__time_duration.sum"),
             "dram_bytes": (to_bytes(r, "dram__bytes_read.sum") or 0) + (to_bytes(r, "dram__bytes_write.sum") or 0),
             "issue_active_pct": num(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),

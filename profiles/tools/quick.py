@@ -37,6 +37,10 @@ def timeit(ctx, confs, reps, mode=rc.RC_MODE_CULLED):
 
 ctx = rc.Context(device=0)
 rows = []
+far = rc.createAlphaBotConfigurations(2_000, False, 510)
+far[:, :3] += 5000.0   # every configuration cleared by step 1: the fixed cost of the two launches
+med, best, nv = timeit(ctx, far, 40)
+rows.append(("far2k_fixed", 2_000, med, best, nv))
 for name, n, hard, seed, reps in (("easy2k_floor", 2_000, False, 510, 40), ("hard64", 64, True, 508, 40),
                                   ("hard100k", 100_000, True, 508, 40), ("hard10k", 10_000, True, 508, 40),
                                   ("hard2k", 2_000, True, 508, 40), ("hard1M", 1_000_000, True, 512, 8),

@@ -344,7 +344,6 @@ int rc_create(rc_ctx **out, const float *rob_x, const float *rob_y, const float 
         ctx->knob_split_max = knob("RC_SPLIT_MAX", 16);
         ctx->knob_split_load = knob("RC_SPLIT_LOAD", 8);
         ctx->knob_host_chunks = knob("RC_HOST_CHUNKS", 0);
-        ctx->knob_gmail = knob("RC_GMAIL", 8);
     }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
@@ -450,6 +449,15 @@ int rc_create(rc_ctx **out, const float *rob_x, const float *rob_y, const float 
                 t.seed_o[d][q] = (uint32_t)(q < (int)co.size() ? co[q] : 0);
             }
         }
+        {
+            const std::vector<int> cr = rb.cut(4), co = ob.cut(4);
+            t.n_seed_r4 = (int)std::min<size_t>(cr.size(), 16);
+            t.n_seed_o4 = (int)std::min<size_t>(co.size(), 16);
+            for (int q = 0; q < 16; q++) {
+                t.seed_r4[q] = (uint32_t)(q < (int)cr.size() ? cr[q] : 0);
+                t.seed_o4[q] = (uint32_t)(q < (int)co.size() ? co[q] : 0);
+            }
+        }
         // plane of every robot triangle in the robot frame, leaf order: n = (b - a) x (c - b), s = n . a
         std::vector<float4> rpl((size_t)n_rob_t);
         for (int p = 0; p < n_rob_t; p++) {
@@ -484,7 +492,6 @@ int rc_create(rc_ctx **out, const float *rob_x, const float *rob_y, const float 
             (e = dev_alloc(ctx, &ctx->d_counters, RC_NUM_COUNTERS)) ||
             (e = dev_alloc(ctx, &ctx->d_queues, kHostChunks)) ||
             (e = dev_alloc(ctx, &ctx->d_work_count, kWorkCounters)) ||
-            (e = dev_alloc(ctx, &ctx->d_gmail, kGMailBytes)) ||
             (e = dev_alloc(ctx, &ctx->d_obs_box, 1)) ||
             (e = cudaMemcpy(ctx->d_obs_box, &t.obs_box, sizeof(rc_aabb), cudaMemcpyHostToDevice))) {
             rcode = check_cuda(ctx, e, "table upload");

@@ -54,26 +54,6 @@ struct __align__(16) Mail {
     uint32_t kind;       // 0 node pairs, 1 leaf pairs, 2 triangle pairs for the tail
 };
 
-// Mail between CTAs (production kernels): once the work list is dry, a warp with a deep descent whose
-// own CTA has no free slot left hands a piece to a slot in GLOBAL memory, and warps of CTAs that have
-// run out of work pick it up -- every CTA holds the same tables, so any warp of the grid can work on
-// any piece.  Pieces never report back (the flags are written optimistically: valid first, whoever
-// finds a hit overwrites), so the protocol is a one-way hand-over: state 0 empty, 1 being filled,
-// 2 full, 3 being emptied.  `idle` counts the CTAs of the grid whose warps are all polling for work;
-// when it reaches the number of CTAs nobody can produce work any more and everybody leaves.
-constexpr int kGMailSlots = 64;
-struct __align__(16) GMailRec {
-    float4 m[3];
-    uint32_t pairs[32];
-    uint32_t conf, cnt, kind, pad;
-};
-struct GMailBox {
-    uint32_t state[kGMailSlots];
-    uint32_t idle;
-    uint32_t pad[63];
-    GMailRec rec[kGMailSlots];
-};
-static_assert(sizeof(GMailBox) <= kGMailBytes, "rc_create allocates kGMailBytes for the mail box");
 constexpr int kNarrowPop = 192;  // node pairs of head room below which a node round pops one pair instead of 32
 
 __device__ __forceinline__ uint32_t ld_volatile(const uint32_t *p) { return *(const volatile uint32_t *)p; }
@@ -106,11 +86,9 @@ struct CulledArgs {
     // "invalid" (optimistic != 0; the statistics kernels keep the one-warp-one-flag protocol).
     int optimistic, split_max, split_load;
     float tri_margin;                // triangle-box clearance of step C = the two inflated tree boxes
-    uint32_t seed_r3[8], seed_o3[8];
+    uint32_t seed_r3[16], seed_o3[16];   // the cut at depth 4 of both trees: up to 256 seed pairs, dealt out to the parts
     int n_seed_r3, n_seed_o3;
     uint32_t *hit_counts;            // STATS kernels: hitting pairs per configuration, no early exit (rc_hit_counts)
-    GMailBox *gmail;                 // production kernels: hand-over between CTAs (zero outside a launch)
-    int gmail_min_load;              // ... used when the list holds at least this many entries per warp of the grid (< 0: never)
     const float4 *rob_plane;         // RL1 kernels: plane of every robot triangle in the robot frame, leaf order
     GatherArgs g;                    // g.world > 1: the last CTA pushes the bitmask slot to the peers (rc_gather.cuh)
 };
@@ -363,10 +341,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
     Mail *s_mail = reinterpret_cast<Mail *>(s_work + WARPS * kWarpWork);
     uint32_t *s_pend = reinterpret_cast<uint32_t *>(s_mail + kMailSlots);
     uint32_t *s_idle = s_pend + WARPS;
-    uint32_t *s_misc = s_idle + 1;   // [0] split shift  [1] this CTA finished last  [2] the grid has gone quiet  [3] scout lock
-                                     // [4] warps of this CTA that are polling  [5] spare
+    uint32_t *s_misc = s_idle + 1;   // [0] split shift  [1] this CTA finished last  [2..5] spare
     uint32_t *s_bin = s_misc + 6;    // [kWorkBins + 1] first list position of each cost class, dearest class first
     uint32_t *s_wait = s_bin + kWorkBins + 1;  // [2 * WARPS] configuration a warp has finished but for its pieces: index, hit
+    uint32_t *s_fetch = s_wait + 2 * WARPS;    // [2 * WARPS] entries of the list a warp has drawn: next, end
     // obstacle accessors: shared memory, or the read-only global path
     auto obs_node = [&](int nb, int half) -> float4 {
         if constexpr (GOBS) return __ldg(a.obs_bvh + 2 * nb + half);
@@ -420,11 +398,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
                    ((unsigned long long)acc << (gs + 1)) <= (unsigned long long)a.split_load * gridDim.x * WARPS)
                 gs++;
         s_misc[0] = gs;
-        // mail between CTAs pays when the list is long (the end of a 100,000-configuration launch: -3 %,
-        // of a million: -6 %); on a short list the warps of one CTA keep each other busy and waiting for
-        // the whole grid to go quiet would only add latency (measured: +10 us on 2,000 configurations)
-        s_misc[5] = (!STATS && a.gmail_min_load >= 0 &&
-                     ((unsigned long long)acc << gs) >= (unsigned long long)a.gmail_min_load * gridDim.x * WARPS) ? 1u : 0u;
     }
     __syncthreads();
     mbar_wait(bar, 0);
@@ -440,13 +413,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
     const bool counting = STATS && a.hit_counts != nullptr;  // audit: every hitting pair, no early exit
     // OPT: the production protocol.  Flags are optimistic (classify_kernel marked every listed
     // configuration valid, whoever finds a hit overwrites), so a piece of a descent that one warp
-    // hands to another never reports back: one-way mail, inside the CTA (shared memory) and between
-    // CTAs (global memory).  The statistics kernels (!OPT) keep the rendezvous protocol -- the owner
-    // of a configuration collects the verdict of its pieces and writes the flag once -- because they
-    // count per configuration.
+    // hands to another never reports back: one-way mail through the slots of the CTA.  The statistics
+    // kernels (!OPT) keep the rendezvous protocol -- the owner of a configuration collects the verdict
+    // of its pieces and writes the flag once -- because they count per configuration.
+    // (Mail between CTAs through slots in global memory was built and measured in round 2: the end of
+    // a launch is not where the time goes -- 100,000 configurations 0.2835 ms with it, 0.2796 without,
+    // a million 2.474 / 2.471 -- so it was taken out again; profiles/ab_r02.txt.)
     constexpr bool OPT = !STATS;
-    GMailBox *const g = a.gmail;
-#define use_gmail (OPT && ld_volatile(&s_misc[5]) != 0u)  /* read where needed: not worth a register across the descent loop */
 
     // Guided self-scheduling over the work list: chunks while plenty of work is left, single
     // entries near the end so that no warp is left holding a long chunk.  The cost of one
@@ -456,27 +429,40 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
     // without work of their own pick slots up and run the same descent on them.  No wait of either
     // protocol can give up on work, and no descent is ever abandoned: a piece that nobody picks up
     // is worked off by the warp that posted it once it has nothing else to do.
-    const uint32_t gs = s_misc[0];
-    const uint32_t n_work = s_bin[kWorkBins] << gs;  // entries: (configuration, part)
-    const uint32_t chunk = max(1u, min(16u, n_work / (gridDim.x * WARPS * 32u)));
-    uint32_t w_next = 0, w_end = 0;
+    // The bookkeeping of the list (what this warp has drawn, the list length, the chunk size) lives in
+    // shared memory and is looked at once per configuration: the descent loop is at the 64-register
+    // limit of a 1,024-thread CTA, and every value kept alive across it costs spills.
+    if (lane == 0) { s_fetch[2 * warp] = 0u; s_fetch[2 * warp + 1] = 0u; }
+    __syncwarp();
     bool dry = false, waiting = false;
     for (;;) {
-        if (!dry && !waiting && w_next >= w_end) {
-            const uint32_t take = ((unsigned long long)w_end + a.tail_begin < n_work) ? chunk : 1u;
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(a.work_count + kWorkBins, (unsigned long long)take);
-            base = __shfl_sync(kFull, base, 0);
-            if (base >= n_work) {
-                dry = true;
-                if (lane == 0) atomicAdd(s_idle, 1u);
-            } else {
-                w_next = (uint32_t)base;
-                w_end = (uint32_t)min(base + take, (unsigned long long)n_work);
+        uint32_t w = 0;
+        if (!dry && !waiting) {
+            const uint32_t gs0 = s_misc[0];
+            const uint32_t n_work = s_bin[kWorkBins] << gs0;  // entries: (configuration, part)
+            uint32_t w_next = s_fetch[2 * warp], w_end = s_fetch[2 * warp + 1];
+            if (w_next >= w_end) {
+                const uint32_t chunk = max(1u, min(16u, n_work / (gridDim.x * WARPS * 32u)));
+                const uint32_t take = ((unsigned long long)w_end + a.tail_begin < n_work) ? chunk : 1u;
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(a.work_count + kWorkBins, (unsigned long long)take);
+                base = __shfl_sync(kFull, base, 0);
+                if (base >= n_work) {
+                    dry = true;
+                    if (lane == 0) atomicAdd(s_idle, 1u);
+                } else {
+                    w_next = (uint32_t)base;
+                    w_end = (uint32_t)min(base + take, (unsigned long long)n_work);
+                }
+            }
+            if (!dry) {
+                w = w_next;
+                __syncwarp();
+                if (lane == 0) { s_fetch[2 * warp] = w_next + 1u; s_fetch[2 * warp + 1] = w_end; }
             }
         }
         Mat34 m;
-        long i = 0;
+        uint32_t i = 0;
         int owner = -1;       // !OPT, >= 0: this warp works on a piece of that warp's configuration
         bool sharing = false;  // !OPT: pieces of the current configuration are (or were) out
         int sp = 0, lq = 0, tq = 0;
@@ -488,21 +474,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
             if (STATS && a.trace && lane == 0) {
                 unsigned long long ns;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
-                a.trace[4 * i] = (uint32_t)(clock64() - t_begin);
-                a.trace[4 * i + 1] = (uint32_t)ns;
-                a.trace[4 * i + 2] = (tr_nodes << 16) | min(tr_leaves, 0xffffu);
-                a.trace[4 * i + 3] = (tr_tails << 16) | min(tr_maxsp, 0xffffu);
+                a.trace[4 * (size_t)i] = (uint32_t)(clock64() - t_begin);
+                a.trace[4 * (size_t)i + 1] = (uint32_t)ns;
+                a.trace[4 * (size_t)i + 2] = (tr_nodes << 16) | min(tr_leaves, 0xffffu);
+                a.trace[4 * (size_t)i + 3] = (tr_tails << 16) | min(tr_maxsp, 0xffffu);
             }
         };
         if (OPT && dry) {
-            // ---- one-way mail: poll the slots of the CTA, every fourth time those of the grid ----
-            // the grid counts CTAs whose warps are ALL polling (a few thousand warps bumping one word
-            // would take longer than a short kernel lasts)
-            if (use_gmail && lane == 0 && atomicAdd(&s_misc[4], 1u) == (uint32_t)WARPS - 1u) atomicAdd(&g->idle, 1u);
-            int k;  // 0 .. kMailSlots - 1: slot of the CTA; kMailSlots + q: slot q of the grid; -2: leave
+            // ---- one-way mail: poll the slots of the CTA; leave when every warp of the CTA has found
+            // the list dry (a warp that still works on a piece picks up whatever it posts itself)
+            int k;
             for (uint32_t spins = 0;; spins++) {
                 k = -1;
-                int scout = 0;
                 if (lane == 0) {
                     for (int q = 0; q < a.mail_slots; q++)
                         if (ld_volatile(&s_mail[q].state) == 2u && atomicCAS(&s_mail[q].state, 2u, 3u) == 2u) {
@@ -510,78 +493,32 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
                             break;
                         }
                     if (k < 0) {
-                        if (!use_gmail) {
-                            // mail inside the CTA only: leave when every warp of the CTA has found the list dry
-                            // (a warp that still works on a piece picks up whatever it posts itself)
-                            if (ld_volatile(s_idle) == (uint32_t)WARPS) k = -2;
-                        } else if (ld_volatile(&s_misc[2]) != 0u) {
-                            k = -2;  // a scout of this CTA has seen the grid go quiet
-                        } else {
-                            // ONE warp of the CTA at a time looks at the grid (a few thousand warps polling
-                            // the same two cache lines would slow down the warps that still work)
-                            scout = atomicCAS(&s_misc[3], 0u, 1u) == 0u ? 1 : 0;
+                        if (ld_volatile(s_idle) == (uint32_t)WARPS) k = -2;
+                        else if (spins > kWatchdogSpins) {
+                            // cannot happen (every descent is finite).  Leaving costs parallelism only: a
+                            // piece nobody picks up is worked off by the warp that posted it.
+                            atomicAdd(c.counters + CNT_WATCHDOG, 1ULL);
+                            atomicOr(c.counters + CNT_WATCHDOG_WHERE, 1ULL);
+                            k = -2;
                         }
                     }
                 }
                 k = __shfl_sync(kFull, k, 0);
-                if (k == -1 && __shfl_sync(kFull, scout, 0)) {
-                    const unsigned f0 = __ballot_sync(kFull, ld_volatile(&g->state[lane]) == 2u);
-                    const unsigned f1 = __ballot_sync(kFull, ld_volatile(&g->state[32 + lane]) == 2u);
-                    if (f0 | f1) {
-                        const int q = f0 ? __ffs(f0) - 1 : 31 + __ffs(f1);
-                        int got = 0;
-                        if (lane == 0) got = atomicCAS(&g->state[q], 2u, 3u) == 2u ? 1 : 0;
-                        if (__shfl_sync(kFull, got, 0)) k = kMailSlots + q;
-                    } else {
-                        // nothing anywhere: leave once every warp of the grid is polling (only a warp
-                        // that works can post).  A poll that gives up costs parallelism, never work.
-                        uint32_t idle = 0;
-                        if (lane == 0) {
-                            idle = ld_volatile(&g->idle);
-                            if (idle != gridDim.x && spins > kWatchdogSpins) {
-                                atomicAdd(c.counters + CNT_WATCHDOG, 1ULL);
-                                atomicOr(c.counters + CNT_WATCHDOG_WHERE, 1ULL);
-                                idle = gridDim.x;
-                            }
-                            if (idle == gridDim.x) st_volatile(&s_misc[2], 1u);
-                        }
-                        if (__shfl_sync(kFull, idle, 0) == gridDim.x) k = -2;
-                    }
-                    if (lane == 0) st_volatile(&s_misc[3], 0u);
-                }
                 if (k != -1) break;
                 __nanosleep(200);
             }
             if (k == -2) break;
-            if (use_gmail && lane == 0 && atomicSub(&s_misc[4], 1u) == (uint32_t)WARPS) atomicSub(&g->idle, 1u);
-            int cnt, kind;
-            uint32_t e;
-            if (k < kMailSlots) {
-                __threadfence_block();
-                Mail &b = s_mail[k];
-                i = (long)b.owner;  // the configuration the piece belongs to
-                cnt = (int)b.cnt; kind = (int)b.kind;
-                e = b.pairs[lane];
-                m.r00 = b.m[0].x; m.r01 = b.m[0].y; m.r02 = b.m[0].z; m.tx = b.m[0].w;
-                m.r10 = b.m[1].x; m.r11 = b.m[1].y; m.r12 = b.m[1].z; m.ty = b.m[1].w;
-                m.r20 = b.m[2].x; m.r21 = b.m[2].y; m.r22 = b.m[2].z; m.tz = b.m[2].w;
-                __syncwarp();
-                __threadfence_block();
-                if (lane == 0) st_volatile(&s_mail[k].state, 0u);
-            } else {
-                __threadfence();
-                const GMailRec *b = g->rec + (k - kMailSlots);
-                const float4 q0 = __ldcg(b->m), q1 = __ldcg(b->m + 1), q2 = __ldcg(b->m + 2);
-                i = (long)__ldcg(&b->conf);
-                cnt = (int)__ldcg(&b->cnt); kind = (int)__ldcg(&b->kind);
-                e = __ldcg(b->pairs + lane);
-                m.r00 = q0.x; m.r01 = q0.y; m.r02 = q0.z; m.tx = q0.w;
-                m.r10 = q1.x; m.r11 = q1.y; m.r12 = q1.z; m.ty = q1.w;
-                m.r20 = q2.x; m.r21 = q2.y; m.r22 = q2.z; m.tz = q2.w;
-                __syncwarp();
-                __threadfence();
-                if (lane == 0) st_volatile(&g->state[k - kMailSlots], 0u);
-            }
+            __threadfence_block();
+            Mail &b = s_mail[k];
+            i = b.owner;  // the configuration the piece belongs to
+            const int cnt = (int)b.cnt, kind = (int)b.kind;
+            const uint32_t e = b.pairs[lane];
+            m.r00 = b.m[0].x; m.r01 = b.m[0].y; m.r02 = b.m[0].z; m.tx = b.m[0].w;
+            m.r10 = b.m[1].x; m.r11 = b.m[1].y; m.r12 = b.m[1].z; m.ty = b.m[1].w;
+            m.r20 = b.m[2].x; m.r21 = b.m[2].y; m.r22 = b.m[2].z; m.tz = b.m[2].w;
+            __syncwarp();
+            __threadfence_block();
+            if (lane == 0) st_volatile(&s_mail[k].state, 0u);
             {
                 uint32_t *dst = kind == 0 ? stack : kind == 1 ? leafq : tailq;
                 if (lane < cnt) dst[lane] = e;
@@ -657,16 +594,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
             if (lane == 0) st_volatile(&s_mail[k].state, 0u);
             __syncwarp();
         } else {
-            const uint32_t w = w_next++;
+            const uint32_t gs = s_misc[0];
             const uint32_t wl = w >> gs, part = w & ((1u << gs) - 1u);
             {
                 // list position -> (cost class, position in its list): dearest class first
                 const uint32_t o = __popc(__ballot_sync(kFull, lane >= 1 && lane < kWorkBins && wl >= s_bin[lane & (kWorkBins - 1)]));
-                i = (long)__ldcg(a.work_idx + (size_t)(kWorkBins - 1 - o) * a.work_cap + (wl - s_bin[o]));
+                i = __ldcg(a.work_idx + (size_t)(kWorkBins - 1 - o) * a.work_cap + (wl - s_bin[o]));
             }
             {
-                const float4 q0 = __ldcg(a.work_mat + 3 * i), q1 = __ldcg(a.work_mat + 3 * i + 1),
-                             q2 = __ldcg(a.work_mat + 3 * i + 2);
+                const float4 q0 = __ldcg(a.work_mat + 3 * (size_t)i), q1 = __ldcg(a.work_mat + 3 * (size_t)i + 1),
+                             q2 = __ldcg(a.work_mat + 3 * (size_t)i + 2);
                 m.r00 = q0.x; m.r01 = q0.y; m.r02 = q0.z; m.tx = q0.w;
                 m.r10 = q1.x; m.r11 = q1.y; m.r12 = q1.z; m.ty = q1.w;
                 m.r20 = q2.x; m.r21 = q2.y; m.r22 = q2.z; m.tz = q2.w;
@@ -690,7 +627,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
             }
             // the descent starts from a cut through both trees instead of (root, root): the top
             // levels almost always overlap here and would cost steps with a handful of lanes.
-            // Split: part p of 2^gs takes every 2^gs-th pair of the deeper cut.
+            // Split: part p of 2^gs takes every 2^gs-th pair of the deeper cut (depth 4: up to 256 pairs,
+            // so that the parts of one configuration carry similar shares of its descent).
             if (gs == 0) {
                 sp = a.n_seed_r * a.n_seed_o;
                 for (int q = lane; q < sp; q += 32)
@@ -746,22 +684,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
                             break;
                         }
                 k = __shfl_sync(kFull, k, 0);
-                if (OPT && use_gmail && k < 0 && ((sp + lq + tq) & 3) == 0) {
-                    // the slots of the CTA are full (its warps without work have all they can take):
-                    // the grid.  One read tells whether anybody out there is polling at all.
-                    uint32_t idle = 0;
-                    if (lane == 0) idle = ld_volatile(&g->idle);
-                    if (__shfl_sync(kFull, idle, 0) != 0u) {
-                        const unsigned f0 = __ballot_sync(kFull, ld_volatile(&g->state[lane]) == 0u);
-                        const unsigned f1 = __ballot_sync(kFull, ld_volatile(&g->state[32 + lane]) == 0u);
-                        if (f0 | f1) {
-                            const int q = f0 ? __ffs(f0) - 1 : 31 + __ffs(f1);
-                            int got = 0;
-                            if (lane == 0) got = atomicCAS(&g->state[q], 0u, 1u) == 0u ? 1 : 0;
-                            if (__shfl_sync(kFull, got, 0)) k = kMailSlots + q;
-                        }
-                    }
-                }
                 if (k >= 0) {
                     const int cnt = kind == 2 ? min(tq, 32) : kind == 1 ? 8 : min(32, sp >> 1);  // node pairs: at most half
                     const int src = lane < cnt ? lane : 0;
@@ -779,14 +701,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
                         if (lane < cnt) stack[lane] = top;
                         sp -= cnt;
                     }
-                    if (!OPT || k < kMailSlots) {
+                    {
                         Mail &b = s_mail[k];
                         if (lane < cnt) b.pairs[lane] = out;
                         if (lane == 0) {
                             b.m[0] = make_float4(m.r00, m.r01, m.r02, m.tx);
                             b.m[1] = make_float4(m.r10, m.r11, m.r12, m.ty);
                             b.m[2] = make_float4(m.r20, m.r21, m.r22, m.tz);
-                            b.owner = OPT ? (uint32_t)i : (uint32_t)pend_slot;
+                            b.owner = OPT ? i : (uint32_t)pend_slot;
                             b.cnt = (uint32_t)cnt;
                             b.kind = (uint32_t)kind;
                             if (!OPT) atomicAdd(&s_pend[pend_slot], 1u);
@@ -796,20 +718,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
                         __syncwarp();
                         __threadfence_block();
                         if (lane == 0) st_volatile(&s_mail[k].state, 2u);
-                    } else {
-                        GMailRec *b = g->rec + (k - kMailSlots);
-                        b->pairs[lane] = out;
-                        if (lane == 0) {
-                            b->m[0] = make_float4(m.r00, m.r01, m.r02, m.tx);
-                            b->m[1] = make_float4(m.r10, m.r11, m.r12, m.ty);
-                            b->m[2] = make_float4(m.r20, m.r21, m.r22, m.tz);
-                            b->conf = (uint32_t)i;
-                            b->cnt = (uint32_t)cnt;
-                            b->kind = (uint32_t)kind;
-                        }
-                        __threadfence();
-                        __syncwarp();
-                        if (lane == 0) st_volatile(&g->state[k - kMailSlots], 2u);
                     }
                     __syncwarp();
                     continue;
@@ -1048,7 +956,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
             // pieces of this configuration went out: it is published when they are all back; until
             // then this warp serves mail slots (top of the loop)
             if (lane == 0) {
-                s_wait[2 * warp] = (uint32_t)i;
+                s_wait[2 * warp] = i;
                 s_wait[2 * warp + 1] = hit ? 1u : 0u;
                 if (hit) atomicOr(&s_pend[warp], kPendHit);  // the pieces still out may stop
             }
@@ -1087,10 +995,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
     if (threadIdx.x == 0) {
         __threadfence();
         const bool last = atomicAdd(a.work_count + kWorkBins + 1, 1ULL) == (unsigned long long)gridDim.x - 1ULL;
-        if (last) {
+        if (last)
             for (int q = 0; q < kWorkBins + 2; q++) a.work_count[q] = 0;
-            if (!STATS) a.gmail->idle = 0u;  // every slot is empty again by construction
-        }
         __threadfence();
         s_misc[1] = last ? 1u : 0u;
     }
@@ -1099,8 +1005,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
         if (s_misc[1]) gather_tail(a.g);
     }
 }
-
-#undef use_gmail
 
 static size_t culled_smem_bytes(const DeviceTables &t, int warps, bool gobs)
 {
@@ -1111,7 +1015,7 @@ static size_t culled_smem_bytes(const DeviceTables &t, int warps, bool gobs)
     else if (t.rob_leaf == 1)
         b += (size_t)t.n_rob_t * 16;  // robot triangle planes
     b += (size_t)warps * (stack_cap_of(warps, gobs) + kLeafQCap + kTailQCap) * 4;
-    b = (b + 15) / 16 * 16 + kMailSlots * sizeof(Mail) + (3 * (size_t)warps + 7 + kWorkBins + 1 + 2) * 4;  // + s_pend, s_idle, s_misc, s_bin, s_wait
+    b = (b + 15) / 16 * 16 + kMailSlots * sizeof(Mail) + (5 * (size_t)warps + 7 + kWorkBins + 1 + 2) * 4;  // + s_pend, s_idle, s_misc, s_bin, s_wait
     return b;
 }
 
@@ -1181,14 +1085,12 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
     // flags: written once per configuration by its warp (statistics kernels), or optimistically --
     // marked valid by step 1, overwritten by whichever part of the descent finds a hit
     a.optimistic = want_stats ? 0 : 1;
-    a.gmail = reinterpret_cast<GMailBox *>(ctx->d_gmail);
-    a.gmail_min_load = ctx->knob_gmail;
     a.rob_plane = t.rob_plane;
     a.split_max = max(1, min(kSplitMax, ctx->knob_split_max));
     a.split_load = max(1, ctx->knob_split_load);
     a.tri_margin = 2.f * t.box_margin;
-    a.n_seed_r3 = t.n_seed_r[3]; a.n_seed_o3 = t.n_seed_o[3];
-    for (int q = 0; q < 8; q++) { a.seed_r3[q] = t.seed_r[3][q]; a.seed_o3[q] = t.seed_o[3][q]; }
+    a.n_seed_r3 = t.n_seed_r4; a.n_seed_o3 = t.n_seed_o4;
+    for (int q = 0; q < 16; q++) { a.seed_r3[q] = t.seed_r4[q]; a.seed_o3[q] = t.seed_o4[q]; }
     if (extras && extras->gather) a.g = *extras->gather;
     else { memset(&a.g, 0, sizeof a.g); a.g.world = 1; }
     a.mail_slots = max(1, min(kMailSlots, ctx->knob_mail_slots));

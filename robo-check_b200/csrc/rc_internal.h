@@ -50,7 +50,9 @@ struct DeviceTables {
     int n_rob_bound = 0;                       // 32, or 0 if the mesh is empty
     // traversal seeds: node cuts at depth 0..3 of both trees (<= 8 nodes each)
     uint32_t seed_r[4][8], seed_o[4][8];
-    int n_seed_r[4], n_seed_o[4];  // robot local AABB: centre and half extent (rounded up)
+    int n_seed_r[4], n_seed_o[4];
+    uint32_t seed_r4[16], seed_o4[16];  // the cut at depth 4 (<= 16 nodes each): seeds of a split descent
+    int n_seed_r4 = 0, n_seed_o4 = 0;
 };
 
 }  // namespace rc
@@ -59,7 +61,6 @@ struct DeviceTables {
 // of the robot lies inside the obstacle AABB); the descent takes the dearest class first so that
 // the long descents are under way early and the work list ends with cheap ones
 constexpr int kWorkBins = 8;
-constexpr size_t kGMailBytes = 16384;  // >= sizeof(rc::GMailBox)
 constexpr int kHostWaves = 4;           // rc_check_host cuts a large batch into at most this many waves
 constexpr int kWorkCounters = 16;  // [0..7] entries per class, [8] next entry, [9] CTAs finished
 
@@ -116,7 +117,6 @@ struct rc_ctx {
     uint32_t *d_work_idx = nullptr;            // [kWorkBins][work_cap]: configuration indices per cost class
     float4 *d_work_mat = nullptr;
     unsigned long long *d_work_count = nullptr;
-    unsigned char *d_gmail = nullptr;          // rc::GMailBox: mail between CTAs (rc_culled.cuh), all zero outside a launch
     long work_cap = 0;
     uint32_t *d_block_counts = nullptr;        // scratch of rc_compact, grown on demand
     long block_counts_cap = 0;
@@ -134,7 +134,6 @@ struct rc_ctx {
     int knob_host_direct = 0; // RC_HOST_DIRECT=1: rc_check_host stores the flags into the pinned buffer from the kernels instead of copying them back
     int knob_share = 1;      // RC_SHARE=0: warps of a CTA do not hand pieces of a deep descent to each other
     int knob_split_max = 16;  // RC_SPLIT_MAX: parts a configuration may be cut into when the work list is short (1 = never)
-    int knob_gmail = 8;       // RC_GMAIL: mail between CTAs when the list holds >= this many entries per warp (-1 = never, 0 = always)
     int knob_split_load = 8;  // RC_SPLIT_LOAD: split while entries <= this many per warp of the grid
     std::string last_error;
     std::vector<void *> allocations;

@@ -842,7 +842,7 @@ def test_audit_reports_the_coplanar_scene(rc, po):
 def test_device_known_answer_tests(rc, ctx, po, omeshes):
     """The reference's helper KATs (narrow-phase/test-narrow-phase.cu:7-626) run on the DEVICE
     functions the kernels are built from (plane_of, sdist, straddles, is_coplanar, la_solve,
-    tri_interval ...), and every intermediate of ~20,000 real alpha1.0 pairs compared bit for bit with
+    tri_interval ...), and every intermediate of several thousand real alpha1.0 pairs compared bit for bit with
     the CPU oracle's helper chain."""
     PTS = np.array([[1, 2, 3], [2, 2, 3.5], [2, 2.5, 3], [1, 3, 4], [4, 7, 2], [5, 1, 3],
                     [100, 300, 400], [400, 700, 200], [500, 100, 300]], np.float32)
@@ -879,15 +879,15 @@ def test_device_known_answer_tests(rc, ctx, po, omeshes):
         r9_all = np.concatenate([w[rob.v1], w[rob.v2], w[rob.v3]], 1)
         # nearby pairs are the interesting ones: pick, for a sample of robot triangles, the obstacle
         # triangles whose boxes overlap, plus random ones
-        for j in rng.choice(len(r9_all), 160, replace=False):
+        for j in rng.choice(len(r9_all), 400, replace=False):
             r = r9_all[j].reshape(3, 3)
-            lo, hi = r.min(0) - 0.5, r.max(0) + 0.5
+            lo, hi = r.min(0) - 0.05, r.max(0) + 0.05
             o = o9_all.reshape(-1, 3, 3)
-            near = np.nonzero(np.all(o.min(1) <= hi, 1) & np.all(o.max(1) >= lo, 1))[0][:24]
-            for k in list(near) + list(rng.choice(len(o9_all), 8, replace=False)):
+            near = np.nonzero(np.all(o.min(1) <= hi, 1) & np.all(o.max(1) >= lo, 1))[0][:32]
+            for k in list(near) + list(rng.choice(len(o9_all), 4, replace=False)):
                 r9s.append(r9_all[j]); o9s.append(o9_all[k])
     r9s, o9s = np.array(r9s, np.float32), np.array(o9s, np.float32)
-    assert len(r9s) > 10_000
+    assert len(r9s) > 4_000
     out, verdict = ctx.kat_pairs(r9s, o9s)
     n_tail = n_hit = 0
     for i in range(len(r9s)):
@@ -902,7 +902,7 @@ def test_device_known_answer_tests(rc, ctx, po, omeshes):
             assert np.array_equal(out[i].view(np.uint32), w_out.view(np.uint32)), (i, out[i], w_out)
         n_tail += both
         n_hit += both and (w_v >> 2) == 1
-    assert n_tail > 200 and n_hit > 20       # the sample reaches the intersection-line code and finds hits
+    assert n_tail > 60 and n_hit > 5         # the sample reaches the intersection-line code and finds hits
 
 
 @pytest.mark.parametrize("knobs", [{}, {"RC_SPLIT_MAX": "1"}, {"RC_SPLIT_MAX": "4", "RC_SPLIT_LOAD": "64"}])
