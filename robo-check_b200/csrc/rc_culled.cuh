@@ -435,6 +435,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
     if (lane == 0) { s_fetch[2 * warp] = 0u; s_fetch[2 * warp + 1] = 0u; }
     __syncwarp();
     bool dry = false, waiting = false;
+#ifdef RC_TIMELINE
+    // diagnostic build only (profiles/tools/timeline.py): per warp, when it started, found the list dry, left
+    uint32_t *tl = (!STATS && a.trace) ? a.trace + 8 * (size_t)(blockIdx.x * WARPS + warp) : nullptr;
+    uint32_t tl_entries = 0, tl_longest = 0, tl_rounds = 0, tl_given = 0, tl_got = 0, tl_t0 = 0, tl_nr = 0, tl_lr = 0, tl_tr = 0;
+    auto tl_now = []() { unsigned long long ns; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns)); return (uint32_t)ns; };
+    if (tl && lane == 0) tl[0] = tl_now();
+#endif
     for (;;) {
         uint32_t w = 0;
         if (!dry && !waiting) {
@@ -450,6 +457,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
                 if (base >= n_work) {
                     dry = true;
                     if (lane == 0) atomicAdd(s_idle, 1u);
+#ifdef RC_TIMELINE
+                    if (tl && lane == 0) tl[1] = tl_now();
+#endif
                 } else {
                     w_next = (uint32_t)base;
                     w_end = (uint32_t)min(base + take, (unsigned long long)n_work);
@@ -644,6 +654,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
             __syncwarp();
         }
         const int pend_slot = owner >= 0 ? owner : warp;
+#ifdef RC_TIMELINE
+        tl_entries++;
+        if (dry) tl_got++;
+        tl_t0 = tl_now(); tl_nr = tl_lr = tl_tr = 0;
+#endif
 
         // B + C + D
         bool hit = false, overflow = false;
@@ -714,6 +729,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
                             if (!OPT) atomicAdd(&s_pend[pend_slot], 1u);
                         }
                         if (STATS) st_shared++;
+#ifdef RC_TIMELINE
+                        tl_given++;
+#endif
                         sharing = true;
                         __syncwarp();
                         __threadfence_block();
@@ -750,6 +768,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
                     if (verdict == kPairCoplanar) h = coplanar_overlap(r, o, pr);
                 }
                 if (STATS) { st_tails += cnt; st_tr++; tr_tails++; }
+#ifdef RC_TIMELINE
+                tl_tr++;
+#endif
                 const unsigned mh = __ballot_sync(kFull, h);
                 if (mh) {
                     hit = true;
@@ -859,6 +880,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
                     tq += __popc(mp);
                 }
                 if (STATS) { st_leaves += cnt; st_tris += (act ? ocount : 0); st_lr++; tr_leaves++; }
+#ifdef RC_TIMELINE
+                tl_lr++;
+#endif
                 __syncwarp();
                 continue;
             }
@@ -896,6 +920,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
                 }
             }
             if (STATS) { st_nodes += cnt; st_nr++; tr_nodes++; tr_maxsp = max(tr_maxsp, (uint32_t)(sp + cnt)); }
+#ifdef RC_TIMELINE
+            tl_nr++;
+#endif
             __syncwarp();  // everybody has read its entry before the slots are reused
             const bool ll = ov && la && lb;
             const unsigned mll = __ballot_sync(kFull, ll);
@@ -934,6 +961,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
             if (STATS && counting) n_hits = 0xffffffffu;  // the fallback does not count: the audit reports it
         }
         __syncwarp();
+#ifdef RC_TIMELINE
+        { const uint32_t d = tl_now() - tl_t0; if (d > tl_longest) { tl_longest = d; tl_rounds = (min(tl_nr, 1023u) << 20) | (min(tl_lr, 1023u) << 10) | min(tl_tr, 1023u); } }
+#endif
         if constexpr (OPT) {
             // whoever finds a hit writes "invalid" -- unless the reference's broad phase, which comes
             // first, clears the configuration: then it is valid whatever the narrow phase says
@@ -967,6 +997,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
         publish(c, i, !hit, lane);
         if (hit) st_invalid++; else st_valid++;
     }
+#ifdef RC_TIMELINE
+    if (tl && lane == 0) { tl[2] = tl_now(); tl[3] = tl_entries; tl[4] = tl_longest; tl[5] = tl_rounds; tl[6] = tl_given; tl[7] = tl_got; }
+#endif
     if (STATS) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) st_tris += __shfl_xor_sync(kFull, st_tris, o);
@@ -1095,7 +1128,11 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
     else { memset(&a.g, 0, sizeof a.g); a.g.world = 1; }
     a.mail_slots = max(1, min(kMailSlots, ctx->knob_mail_slots));
     a.donate_min = max(40, ctx->knob_donate_min);
+#ifdef RC_TIMELINE
+    a.trace = ctx->d_trace;
+#else
     a.trace = want_stats ? ctx->d_trace : nullptr;
+#endif
     a.work_idx = ctx->d_work_idx; a.work_mat = ctx->d_work_mat; a.work_count = ctx->d_work_count;
     a.work_cap = ctx->work_cap;
     if (!ctx->d_work_idx || ctx->work_cap < n) return cudaErrorMemoryAllocation;  // rc_check sizes it
