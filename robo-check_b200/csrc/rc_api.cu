@@ -341,6 +341,7 @@ int rc_create(rc_ctx **out, const float *rob_x, const float *rob_y, const float 
         ctx->knob_bound = knob("RC_BOUND", 1);
         ctx->knob_mail_slots = knob("RC_MAIL_SLOTS", 4);
         ctx->knob_donate_min = knob("RC_DONATE_MIN", 40);
+        ctx->knob_donate_leaf = knob("RC_DONATE_LEAF", 16);
         ctx->knob_split_max = knob("RC_SPLIT_MAX", 16);
         ctx->knob_split_load = knob("RC_SPLIT_LOAD", 8);
         ctx->knob_host_chunks = knob("RC_HOST_CHUNKS", 0);

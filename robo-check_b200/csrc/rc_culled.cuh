@@ -72,7 +72,7 @@ struct CulledArgs {
     int tail_thresh, leaf_thresh;
     int stack_cap;                                         // <= compiled capacity (smaller only in tests)
     int share;                                             // 0: no hand-over between the warps of a CTA
-    int mail_slots, donate_min;                            // hand-over tuning (<= kMailSlots; node pairs kept before giving)
+    int mail_slots, donate_min, donate_leaf;               // hand-over tuning (<= kMailSlots; node / leaf pairs queued before giving)
     // work list written by classify_kernel: configurations the cheap tests could not clear
     const uint32_t *work_idx;                              // [kWorkBins][work_cap] configuration indices
     const float4 *work_mat;                                // three rows of [R | t] per CONFIGURATION
@@ -345,6 +345,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
     uint32_t *s_bin = s_misc + 6;    // [kWorkBins + 1] first list position of each cost class, dearest class first
     uint32_t *s_wait = s_bin + kWorkBins + 1;  // [2 * WARPS] configuration a warp has finished but for its pieces: index, hit
     uint32_t *s_fetch = s_wait + 2 * WARPS;    // [2 * WARPS] entries of the list a warp has drawn: next, end
+    uint32_t *s_seed = s_fetch + 2 * WARPS;    // [64] seed pairs of a whole descent  [256] seed pairs dealt out to split descents
     // obstacle accessors: shared memory, or the read-only global path
     auto obs_node = [&](int nb, int half) -> float4 {
         if constexpr (GOBS) return __ldg(a.obs_bvh + 2 * nb + half);
@@ -360,6 +361,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
         mbar_fence_init();
     }
     if (threadIdx.x < kMailSlots) s_mail[threadIdx.x].state = 0u;
+    {
+        // the seed pairs of every descent, encoded once per CTA (indexing the argument arrays per
+        // configuration cost ~80 instructions each time)
+        const int q = (int)threadIdx.x;
+        if (q < a.n_seed_r * a.n_seed_o) s_seed[q] = (a.seed_r[q / a.n_seed_o] << SH) | a.seed_o[q % a.n_seed_o];
+        if (q < a.n_seed_r3 * a.n_seed_o3) s_seed[64 + q] = (a.seed_r3[q / a.n_seed_o3] << SH) | a.seed_o3[q % a.n_seed_o3];
+    }
     if (threadIdx.x <= WARPS + 6) s_pend[threadIdx.x] = 0u;  // s_pend, s_idle, s_misc[0..5]
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -641,15 +649,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
             // so that the parts of one configuration carry similar shares of its descent).
             if (gs == 0) {
                 sp = a.n_seed_r * a.n_seed_o;
-                for (int q = lane; q < sp; q += 32)
-                    stack[q] = (a.seed_r[q / a.n_seed_o] << SH) | a.seed_o[q % a.n_seed_o];
+                for (int q = lane; q < sp; q += 32) stack[q] = s_seed[q];
             } else {
                 const int ns = a.n_seed_r3 * a.n_seed_o3;
                 sp = (int)part < ns ? (ns - (int)part + (1 << gs) - 1) >> gs : 0;
-                for (int j = lane; j < sp; j += 32) {
-                    const int q = (int)part + (j << gs);
-                    stack[j] = (a.seed_r3[q / a.n_seed_o3] << SH) | a.seed_o3[q % a.n_seed_o3];
-                }
+                for (int j = lane; j < sp; j += 32) stack[j] = s_seed[64 + (int)part + (j << gs)];
             }
             __syncwarp();
         }
@@ -668,17 +672,21 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
             // worth of leaf pairs, else up to half of the node pairs, oldest = largest subtrees
             // a warp always keeps work for itself, so what it receives is never passed on untouched
             // (a piece bouncing between idle warps would never be decided)
-            const int kind = !a.share ? -1
-                             : (tq >= a.tail_thresh && (sp > 0 || lq > 0 || tq > 32)) ? 2
-                             : lq >= 16 ? 1 : sp >= a.donate_min ? 0 : -1;
             // What other warps publish is agreed on by the whole warp (vote / broadcast: two lanes
             // reading the same word at different moments could otherwise take different branches of
-            // this loop), and only in rounds where it matters: something to give, or pieces of this
-            // configuration are out.  s_idle only ever grows, so the common case is one shared-memory
-            // read and one vote.
+            // this loop).  s_idle only ever grows and stays zero until the first warp of the CTA finds
+            // the list dry, so the common case is one shared-memory read and one vote; what there is
+            // to give is only worked out once somebody could take it.  With idle warps around, anything
+            // beyond the round this warp is about to run is worth giving: a round takes a lone warp
+            // ~0.8 us, a hand-over a fraction of that.
+            int kind = -1;
             uint32_t seen = 0;
-            if (kind >= 0 || (!OPT && sharing)) {
+            if (a.share || (!OPT && sharing)) {
                 if (__any_sync(kFull, ld_volatile(s_idle) != 0u)) {
+                    if (a.share)
+                        kind = (tq >= a.tail_thresh && (sp > 0 || lq > 0 || tq > 32)) ? 2
+                               : (lq >= a.donate_leaf && (sp > 0 || lq >= 16)) ? 1
+                               : sp >= a.donate_min ? 0 : -1;
                     if (lane == 0) {
                         seen = 1u;
                         if (!OPT && sharing && (ld_volatile(&s_pend[pend_slot]) & kPendHit) != 0u) seen = 3u;
@@ -1048,7 +1056,7 @@ static size_t culled_smem_bytes(const DeviceTables &t, int warps, bool gobs)
     else if (t.rob_leaf == 1)
         b += (size_t)t.n_rob_t * 16;  // robot triangle planes
     b += (size_t)warps * (stack_cap_of(warps, gobs) + kLeafQCap + kTailQCap) * 4;
-    b = (b + 15) / 16 * 16 + kMailSlots * sizeof(Mail) + (5 * (size_t)warps + 7 + kWorkBins + 1 + 2) * 4;  // + s_pend, s_idle, s_misc, s_bin, s_wait
+    b = (b + 15) / 16 * 16 + kMailSlots * sizeof(Mail) + (5 * (size_t)warps + 7 + kWorkBins + 1 + 2 + 320) * 4;  // + s_pend, s_idle, s_misc, s_bin, s_wait, s_fetch, s_seed
     return b;
 }
 
@@ -1127,7 +1135,8 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
     if (extras && extras->gather) a.g = *extras->gather;
     else { memset(&a.g, 0, sizeof a.g); a.g.world = 1; }
     a.mail_slots = max(1, min(kMailSlots, ctx->knob_mail_slots));
-    a.donate_min = max(40, ctx->knob_donate_min);
+    a.donate_min = max(4, ctx->knob_donate_min);
+    a.donate_leaf = max(8, ctx->knob_donate_leaf);
 #ifdef RC_TIMELINE
     a.trace = ctx->d_trace;
 #else

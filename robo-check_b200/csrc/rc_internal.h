@@ -130,7 +130,7 @@ struct rc_ctx {
     bool knob_global_obstacle = false;
     int knob_pdl = 1;        // RC_PDL=0: no programmatic dependent launch of the descent step
     int knob_bound = 1;      // RC_BOUND=0: classify without the vertex-group boxes
-    int knob_mail_slots = 4, knob_donate_min = 40;  // RC_MAIL_SLOTS, RC_DONATE_MIN
+    int knob_mail_slots = 4, knob_donate_min = 40, knob_donate_leaf = 16;  // RC_MAIL_SLOTS, RC_DONATE_MIN, RC_DONATE_LEAF
     int knob_host_direct = 0; // RC_HOST_DIRECT=1: rc_check_host stores the flags into the pinned buffer from the kernels instead of copying them back
     int knob_share = 1;      // RC_SHARE=0: warps of a CTA do not hand pieces of a deep descent to each other
     int knob_split_max = 16;  // RC_SPLIT_MAX: parts a configuration may be cut into when the work list is short (1 = never)
