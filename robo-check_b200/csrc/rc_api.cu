@@ -192,13 +192,29 @@ int ensure_work_list(rc_ctx *ctx, long n)
     cudaDeviceSynchronize();  // an earlier asynchronous check may still use the old list
     if (ctx->d_work_idx) cudaFree(ctx->d_work_idx);
     if (ctx->d_work_mat) cudaFree(ctx->d_work_mat);
-    ctx->d_work_idx = nullptr; ctx->d_work_mat = nullptr; ctx->work_cap = 0;
+    if (ctx->d_feed_slots) cudaFree(ctx->d_feed_slots);
+    ctx->d_work_idx = nullptr; ctx->d_work_mat = nullptr; ctx->d_feed_slots = nullptr; ctx->work_cap = 0;
     const long cap = std::max(n, 1L << 17);
     cudaError_t e;
     if ((e = cudaMalloc(&ctx->d_work_idx, (size_t)cap * kWorkBins * sizeof(uint32_t))) ||
         (e = cudaMalloc(&ctx->d_work_mat, (size_t)cap * 3 * sizeof(float4))))
         return check_cuda(ctx, e, "work list");
     ctx->work_cap = cap;
+    return RC_OK;
+}
+
+// Lists of the single-launch form (rc_culled.cuh: FeedArgs), sized like the work list, allocated the
+// first time that form is used.  Zeroed once: a slot counts as filled when its tag equals the call
+// number, which starts at 1.
+int ensure_feed(rc_ctx *ctx)
+{
+    cudaError_t e;
+    if (!ctx->d_feed_ctr && (e = cudaMalloc(&ctx->d_feed_ctr, 1024 * sizeof(uint32_t)))) return check_cuda(ctx, e, "feed counters");
+    if (!ctx->d_feed_slots) {
+        const size_t bytes = (size_t)ctx->work_cap * kWorkBins * sizeof(uint2);
+        if ((e = cudaMalloc(&ctx->d_feed_slots, bytes)) || (e = cudaMemset(ctx->d_feed_slots, 0, bytes)))
+            return check_cuda(ctx, e, "feed lists");
+    }
     return RC_OK;
 }
 
@@ -342,6 +358,8 @@ int rc_create(rc_ctx **out, const float *rob_x, const float *rob_y, const float 
         ctx->knob_mail_slots = knob("RC_MAIL_SLOTS", 4);
         ctx->knob_donate_min = knob("RC_DONATE_MIN", 40);
         ctx->knob_donate_leaf = knob("RC_DONATE_LEAF", 16);
+        ctx->knob_feed = knob("RC_FEED", 1);
+        ctx->knob_feed_cls = knob("RC_FEED_CLS", 0);
         ctx->knob_split_max = knob("RC_SPLIT_MAX", 16);
         ctx->knob_split_load = knob("RC_SPLIT_LOAD", 8);
         ctx->knob_host_chunks = knob("RC_HOST_CHUNKS", 0);
@@ -544,6 +562,8 @@ void rc_destroy(rc_ctx *ctx)
     if (ctx->d_block_counts) cudaFree(ctx->d_block_counts);
     if (ctx->d_work_idx) cudaFree(ctx->d_work_idx);
     if (ctx->d_work_mat) cudaFree(ctx->d_work_mat);
+    if (ctx->d_feed_slots) cudaFree(ctx->d_feed_slots);
+    if (ctx->d_feed_ctr) cudaFree(ctx->d_feed_ctr);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     free_lane(ctx->pipe[0]); free_lane(ctx->pipe[1]);
@@ -571,6 +591,8 @@ int rc_obstacle_aabb(const rc_ctx *ctx, rc_aabb *out)
     return RC_OK;
 }
 
+constexpr long kFeedMax = 1L << 22;  // configurations per call of the single-launch form (64 B of list per configuration)
+
 static int check_on_stream(rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_valid, uint32_t *d_bitmask,
                            int mode, cudaStream_t s, const rc::CheckExtras *extras, const char *what)
 {
@@ -581,7 +603,20 @@ static int check_on_stream(rc_ctx *ctx, const rc_config *d_confs, long n, uint8_
     int rcode = scratch_acquire(ctx, s);
     if (rcode != RC_OK) return rcode;
     const int stats = ctx->stats_on || (extras && extras->hit_counts);
-    cudaError_t e = launch_check(ctx, d_confs, n, d_valid, d_bitmask, mode, stats, s, nullptr, extras);
+    // single-launch form (the descent kernel classifies): asked for by the caller (rc_check_host reads the
+    // configurations in place), or for every culled check with RC_FEED=2
+    rc::CheckExtras x;
+    if (extras) x = *extras;
+    if (mode == RC_MODE_CULLED && !stats && !ctx->t.gobs && n <= kFeedMax && (x.feed || ctx->knob_feed >= 2)) {
+        if ((rcode = ensure_feed(ctx)) != RC_OK) { scratch_release(ctx, s); return rcode; }
+        x.feed = 1;
+        if (ctx->knob_feed_cls > 0) x.feed_cls_warps = ctx->knob_feed_cls;
+        if (++ctx->feed_gen == 0) ctx->feed_gen = 1;
+        x.feed_gen = ctx->feed_gen;
+    } else {
+        x.feed = 0;
+    }
+    cudaError_t e = launch_check(ctx, d_confs, n, d_valid, d_bitmask, mode, stats, s, nullptr, &x);
     scratch_release(ctx, s);
     if (e == cudaErrorInvalidConfiguration)
         return set_error(ctx, RC_ERR_UNSUPPORTED, "mesh tables do not fit in shared memory");
@@ -765,7 +800,31 @@ int rc_check_host(rc_ctx *ctx, const rc_config *h_confs, long n, uint8_t *h_vali
     // device-resident rate).
     int waves = ctx->knob_host_chunks > 0 ? std::min(ctx->knob_host_chunks, kHostWaves) : 1;
     if (direct || n < 4096) waves = 1;
-    if (waves <= 1) {
+    // Single launch, no host-to-device copy (RC_FEED >= 1, the default): the kernel reads the
+    // configurations where they lie -- the caller's page-locked buffer, or the pinned staging area a
+    // pageable one was copied to -- over PCIe, two warps per CTA classifying batches as they come in while
+    // the other warps already run descents on the ones that need them.  The copy (2.4 MB, ~50 us for
+    // 100,000 configurations), the classify step and the second launch no longer stand in front of the
+    // descents.
+    const rc_config *mapped_confs = nullptr;
+    if (ctx->knob_feed >= 1 && mode == RC_MODE_CULLED && !ctx->stats_on && !ctx->t.gobs && n <= kFeedMax && waves <= 1) {
+        void *mp = nullptr;
+        if (cudaHostGetDevicePointer(&mp, const_cast<rc_config *>(src), 0) == cudaSuccess && mp)
+            mapped_confs = static_cast<const rc_config *>(mp);
+        cudaGetLastError();
+    }
+    if (mapped_confs) {
+        rc::CheckExtras x;
+        x.feed = 1;
+        x.feed_cls_warps = 2;
+        cudaEventRecord(ctx->ev0, s);
+        if ((rcode = check_on_stream(ctx, mapped_confs, n, d_out, nullptr, mode, s, &x, "rc_check_host launch (single)")) != RC_OK)
+            return rcode;
+        cudaEventRecord(ctx->ev1, s);
+        if ((!direct && (e = cudaMemcpyAsync(dst, ctx->d_stage_valid, (size_t)n, cudaMemcpyDeviceToHost, s))) ||
+            (e = cudaStreamSynchronize(s)))
+            return check_cuda(ctx, e, "D2H flags");
+    } else if (waves <= 1) {
         if ((e = cudaMemcpyAsync(ctx->d_stage_confs, src, (size_t)n * sizeof(rc_config),
                                  cudaMemcpyHostToDevice, s)))
             return check_cuda(ctx, e, "H2D configurations");

@@ -59,6 +59,51 @@ constexpr int kNarrowPop = 192;  // node pairs of head room below which a node r
 __device__ __forceinline__ uint32_t ld_volatile(const uint32_t *p) { return *(const volatile uint32_t *)p; }
 __device__ __forceinline__ void st_volatile(uint32_t *p, uint32_t v) { *(volatile uint32_t *)p = v; }
 
+// ---- step 1 of rc_check: one THREAD per configuration ------------------------------------------
+// Matrix (six libdevice sin/cos), bounding-sphere and rotated-bounding-box tests against the
+// obstacle AABB.  A configuration either is provably cleared by the broad phase -- flag byte and a
+// whole bitmask word per warp are written here, 24 B read + 1 B written per configuration, so this
+// step is HBM-bound -- or goes, with its matrix, onto the work list of the warp-per-configuration
+// kernel below.  Doing this per thread instead of per warp computes the trigonometry once per
+// configuration instead of 32 times.
+struct ClassifyArgs {
+    const rc_config *confs;
+    long n;
+    uint8_t *valid;
+    uint32_t *bitmask;
+    rc_aabb obs_box;
+    float sph_x, sph_y, sph_z, sph_r;
+    float box_cx, box_cy, box_cz, box_ex, box_ey, box_ez;
+    float4 bound[2 * 32];  // (centre, half extent) of the vertex groups, local frame: kernel parameter =
+                           // constant bank, the unrolled loop reads them as instruction operands
+    int n_bound;           // kClassifyBoxes, or 0 to skip them
+    uint32_t *work_idx;
+    float4 *work_mat;
+    long work_cap;
+    unsigned long long *work_count;
+    unsigned long long *counters;
+    int optimistic;        // listed configurations are marked valid here; the descent only ever writes "invalid"
+};
+
+
+// Single-launch form of rc_check ("feed"): the descent kernel classifies the configurations itself --
+// a few warps per CTA take batches of 32, one configuration per lane, straight from wherever they
+// lie (device memory, or the caller's page-locked host buffer read over PCIe) -- and hands the ones
+// that need a descent to per-class lists that every warp draws from while later batches are still
+// arriving.  List slot = (call number, configuration index): a slot is filled once its tag equals the
+// call number of this launch, so the lists need no clearing between calls.
+struct FeedArgs {
+    int on;              // this launch classifies in the kernel (kernels instantiated with FEED only)
+    int gs;              // split shift (parts per configuration = 1 << gs), decided on the host from n
+    int cls_warps;       // warps per CTA that classify batches before they draw entries
+    uint32_t gen;        // call number (never 0)
+    uint2 *slots;        // [kWorkBins][work_cap]
+    uint32_t *ctr;       // kFeedStride words apart (one L2 line each): [0..7] configurations listed per class
+                         // [8..15] entries drawn per class  [16] next batch  [17] batches done
+};
+constexpr int kFeedStride = 32;
+constexpr int kFeedCounters = 18;
+
 struct CulledArgs {
     CheckArgs c;                  // rob_t / obs_* point at the BVH-ordered tables
     const float4 *rob_bvh, *obs_bvh;
@@ -91,6 +136,8 @@ struct CulledArgs {
     uint32_t *hit_counts;            // STATS kernels: hitting pairs per configuration, no early exit (rc_hit_counts)
     const float4 *rob_plane;         // RL1 kernels: plane of every robot triangle in the robot frame, leaf order
     GatherArgs g;                    // g.world > 1: the last CTA pushes the bitmask slot to the peers (rc_gather.cuh)
+    FeedArgs feed;                   // FEED kernels
+    ClassifyArgs k;                  // FEED kernels: what classify_kernel gets in the two-launch form
 };
 
 __device__ __forceinline__ bool boxes_overlap(const Mat34 &m, const float4 r0, const float4 r1,
@@ -175,31 +222,78 @@ __device__ __noinline__ bool narrow_exhaustive(const Mat34 m, const float4 *s_ro
     return hit;
 }
 
-// ---- step 1 of rc_check: one THREAD per configuration ------------------------------------------
-// Matrix (six libdevice sin/cos), bounding-sphere and rotated-bounding-box tests against the
-// obstacle AABB.  A configuration either is provably cleared by the broad phase -- flag byte and a
-// whole bitmask word per warp are written here, 24 B read + 1 B written per configuration, so this
-// step is HBM-bound -- or goes, with its matrix, onto the work list of the warp-per-configuration
-// kernel below.  Doing this per thread instead of per warp computes the trigonometry once per
-// configuration instead of 32 times.
-struct ClassifyArgs {
-    const rc_config *confs;
-    long n;
-    uint8_t *valid;
-    uint32_t *bitmask;
-    rc_aabb obs_box;
-    float sph_x, sph_y, sph_z, sph_r;
-    float box_cx, box_cy, box_cz, box_ex, box_ey, box_ez;
-    float4 bound[2 * 32];  // (centre, half extent) of the vertex groups, local frame: kernel parameter =
-                           // constant bank, the unrolled loop reads them as instruction operands
-    int n_bound;           // kClassifyBoxes, or 0 to skip them
-    uint32_t *work_idx;
-    float4 *work_mat;
-    long work_cap;
-    unsigned long long *work_count;
-    unsigned long long *counters;
-    int optimistic;        // listed configurations are marked valid here; the descent only ever writes "invalid"
-};
+// The three conservative tests of one configuration against the obstacle AABB (bounding sphere, rotated
+// local box, union of the rotated vertex-group boxes).  clear: provably cleared by the reference's broad
+// phase; inside: vertex groups whose box meets the obstacle AABB = the cost class of the descent.
+__device__ __forceinline__ void classify_one(const ClassifyArgs &a, const Mat34 &m, bool &clear, int &inside)
+{
+    const float sx = fmaf(m.r02, a.sph_z, fmaf(m.r01, a.sph_y, fmaf(m.r00, a.sph_x, m.tx)));
+    const float sy = fmaf(m.r12, a.sph_z, fmaf(m.r11, a.sph_y, fmaf(m.r10, a.sph_x, m.ty)));
+    const float sz = fmaf(m.r22, a.sph_z, fmaf(m.r21, a.sph_y, fmaf(m.r20, a.sph_x, m.tz)));
+    // the robot lies inside its bounding sphere; if the sphere's box clears the obstacle AABB
+    // with margin, so does the exact vertex AABB of the reference
+    const float hx = a.sph_r + 0.01f + 4e-6f * (fabsf(sx) + a.sph_r);
+    const float hy = a.sph_r + 0.01f + 4e-6f * (fabsf(sy) + a.sph_r);
+    const float hz = a.sph_r + 0.01f + 4e-6f * (fabsf(sz) + a.sph_r);
+    clear = sx - hx > a.obs_box.x_max || sx + hx < a.obs_box.x_min ||
+            sy - hy > a.obs_box.y_max || sy + hy < a.obs_box.y_min ||
+            sz - hz > a.obs_box.z_max || sz + hz < a.obs_box.z_min;
+    if (!clear) {
+        // ... and inside the world AABB of its rotated local bounding box
+        const float cx = fmaf(m.r02, a.box_cz, fmaf(m.r01, a.box_cy, fmaf(m.r00, a.box_cx, m.tx)));
+        const float cy = fmaf(m.r12, a.box_cz, fmaf(m.r11, a.box_cy, fmaf(m.r10, a.box_cx, m.ty)));
+        const float cz = fmaf(m.r22, a.box_cz, fmaf(m.r21, a.box_cy, fmaf(m.r20, a.box_cx, m.tz)));
+        const float ex = fmaf(fabsf(m.r02), a.box_ez, fmaf(fabsf(m.r01), a.box_ey, fabsf(m.r00) * a.box_ex));
+        const float ey = fmaf(fabsf(m.r12), a.box_ez, fmaf(fabsf(m.r11), a.box_ey, fabsf(m.r10) * a.box_ex));
+        const float ez = fmaf(fabsf(m.r22), a.box_ez, fmaf(fabsf(m.r21), a.box_ey, fabsf(m.r20) * a.box_ex));
+        const float gx = ex + 0.01f + 4e-6f * (fabsf(cx) + ex);
+        const float gy = ey + 0.01f + 4e-6f * (fabsf(cy) + ey);
+        const float gz = ez + 0.01f + 4e-6f * (fabsf(cz) + ez);
+        clear = cx - gx > a.obs_box.x_max || cx + gx < a.obs_box.x_min ||
+                cy - gy > a.obs_box.y_max || cy + gy < a.obs_box.y_min ||
+                cz - gz > a.obs_box.z_max || cz + gz < a.obs_box.z_min;
+    }
+    inside = 0;
+    if (!clear && a.n_bound == kClassifyBoxes) {
+        // ... and inside the union of the rotated boxes of its vertex groups: close to the exact
+        // vertex AABB, so all but a thin band of the configurations the reference's broad phase
+        // clears are decided here, by one thread, without transforming a single vertex.
+        float lox = FLT_MAX, loy = FLT_MAX, loz = FLT_MAX, hix = -FLT_MAX, hiy = -FLT_MAX, hiz = -FLT_MAX;
+        const float ax = fabsf(m.r00), ay = fabsf(m.r01), az = fabsf(m.r02);
+        const float bx = fabsf(m.r10), by = fabsf(m.r11), bz = fabsf(m.r12);
+        const float cx = fabsf(m.r20), cy = fabsf(m.r21), cz = fabsf(m.r22);
+#pragma unroll
+        for (int r = 0; r < kClassifyBoxes; r++) {
+            const float4 bc = a.bound[2 * r], be = a.bound[2 * r + 1];
+            const float px = fmaf(m.r02, bc.z, fmaf(m.r01, bc.y, fmaf(m.r00, bc.x, m.tx)));
+            const float py = fmaf(m.r12, bc.z, fmaf(m.r11, bc.y, fmaf(m.r10, bc.x, m.ty)));
+            const float pz = fmaf(m.r22, bc.z, fmaf(m.r21, bc.y, fmaf(m.r20, bc.x, m.tz)));
+            const float ex = fmaf(az, be.z, fmaf(ay, be.y, ax * be.x));
+            const float ey = fmaf(bz, be.z, fmaf(by, be.y, bx * be.x));
+            const float ez = fmaf(cz, be.z, fmaf(cy, be.y, cx * be.x));
+            const float l0 = px - ex, h0 = px + ex, l1 = py - ey, h1 = py + ey, l2 = pz - ez, h2 = pz + ez;
+            lox = fminf(lox, l0); hix = fmaxf(hix, h0);
+            loy = fminf(loy, l1); hiy = fmaxf(hiy, h1);
+            loz = fminf(loz, l2); hiz = fmaxf(hiz, h2);
+            inside += (l0 <= a.obs_box.x_max && h0 >= a.obs_box.x_min && l1 <= a.obs_box.y_max &&
+                       h1 >= a.obs_box.y_min && l2 <= a.obs_box.z_max && h2 >= a.obs_box.z_min) ? 1 : 0;
+        }
+        const float gx = 0.01f + 4e-6f * fmaxf(fabsf(lox), fabsf(hix));
+        const float gy = 0.01f + 4e-6f * fmaxf(fabsf(loy), fabsf(hiy));
+        const float gz = 0.01f + 4e-6f * fmaxf(fabsf(loz), fabsf(hiz));
+        clear = lox - gx > a.obs_box.x_max || hix + gx < a.obs_box.x_min ||
+                loy - gy > a.obs_box.y_max || hiy + gy < a.obs_box.y_min ||
+                loz - gz > a.obs_box.z_max || hiz + gz < a.obs_box.z_min;
+    }
+}
+
+// cost class from the share of the robot inside the obstacle AABB (edges ~ 1/64, 3/64, 7/64, 13/64,
+// 21/64, 31/64, 43/64 of the vertex groups)
+__device__ __forceinline__ int cost_class(int inside)
+{
+    const int f = inside * (64 / kClassifyBoxes);
+    return (f >= 1) + (f >= 3) + (f >= 7) + (f >= 13) + (f >= 21) + (f >= 31) + (f >= 43);
+}
 
 template <bool STATS>
 __global__ void __launch_bounds__(64) classify_kernel(const __grid_constant__ ClassifyArgs a)
@@ -213,64 +307,9 @@ __global__ void __launch_bounds__(64) classify_kernel(const __grid_constant__ Cl
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n32; i += (long)gridDim.x * blockDim.x) {
         const bool in = i < a.n;
         const Mat34 m = load_matrix(a.confs, in ? i : a.n - 1);
-        const float sx = fmaf(m.r02, a.sph_z, fmaf(m.r01, a.sph_y, fmaf(m.r00, a.sph_x, m.tx)));
-        const float sy = fmaf(m.r12, a.sph_z, fmaf(m.r11, a.sph_y, fmaf(m.r10, a.sph_x, m.ty)));
-        const float sz = fmaf(m.r22, a.sph_z, fmaf(m.r21, a.sph_y, fmaf(m.r20, a.sph_x, m.tz)));
-        // the robot lies inside its bounding sphere; if the sphere's box clears the obstacle AABB
-        // with margin, so does the exact vertex AABB of the reference
-        const float hx = a.sph_r + 0.01f + 4e-6f * (fabsf(sx) + a.sph_r);
-        const float hy = a.sph_r + 0.01f + 4e-6f * (fabsf(sy) + a.sph_r);
-        const float hz = a.sph_r + 0.01f + 4e-6f * (fabsf(sz) + a.sph_r);
-        bool clear = sx - hx > a.obs_box.x_max || sx + hx < a.obs_box.x_min ||
-                     sy - hy > a.obs_box.y_max || sy + hy < a.obs_box.y_min ||
-                     sz - hz > a.obs_box.z_max || sz + hz < a.obs_box.z_min;
-        if (!clear) {
-            // ... and inside the world AABB of its rotated local bounding box
-            const float cx = fmaf(m.r02, a.box_cz, fmaf(m.r01, a.box_cy, fmaf(m.r00, a.box_cx, m.tx)));
-            const float cy = fmaf(m.r12, a.box_cz, fmaf(m.r11, a.box_cy, fmaf(m.r10, a.box_cx, m.ty)));
-            const float cz = fmaf(m.r22, a.box_cz, fmaf(m.r21, a.box_cy, fmaf(m.r20, a.box_cx, m.tz)));
-            const float ex = fmaf(fabsf(m.r02), a.box_ez, fmaf(fabsf(m.r01), a.box_ey, fabsf(m.r00) * a.box_ex));
-            const float ey = fmaf(fabsf(m.r12), a.box_ez, fmaf(fabsf(m.r11), a.box_ey, fabsf(m.r10) * a.box_ex));
-            const float ez = fmaf(fabsf(m.r22), a.box_ez, fmaf(fabsf(m.r21), a.box_ey, fabsf(m.r20) * a.box_ex));
-            const float gx = ex + 0.01f + 4e-6f * (fabsf(cx) + ex);
-            const float gy = ey + 0.01f + 4e-6f * (fabsf(cy) + ey);
-            const float gz = ez + 0.01f + 4e-6f * (fabsf(cz) + ez);
-            clear = cx - gx > a.obs_box.x_max || cx + gx < a.obs_box.x_min ||
-                    cy - gy > a.obs_box.y_max || cy + gy < a.obs_box.y_min ||
-                    cz - gz > a.obs_box.z_max || cz + gz < a.obs_box.z_min;
-        }
-        int inside = 0;  // vertex groups whose box meets the obstacle AABB: the cost class of the descent
-        if (!clear && a.n_bound == kClassifyBoxes) {
-            // ... and inside the union of the rotated boxes of its vertex groups: close to the exact
-            // vertex AABB, so all but a thin band of the configurations the reference's broad phase
-            // clears are decided here, by one thread, without transforming a single vertex.
-            float lox = FLT_MAX, loy = FLT_MAX, loz = FLT_MAX, hix = -FLT_MAX, hiy = -FLT_MAX, hiz = -FLT_MAX;
-            const float ax = fabsf(m.r00), ay = fabsf(m.r01), az = fabsf(m.r02);
-            const float bx = fabsf(m.r10), by = fabsf(m.r11), bz = fabsf(m.r12);
-            const float cx = fabsf(m.r20), cy = fabsf(m.r21), cz = fabsf(m.r22);
-#pragma unroll
-            for (int r = 0; r < kClassifyBoxes; r++) {
-                const float4 bc = a.bound[2 * r], be = a.bound[2 * r + 1];
-                const float px = fmaf(m.r02, bc.z, fmaf(m.r01, bc.y, fmaf(m.r00, bc.x, m.tx)));
-                const float py = fmaf(m.r12, bc.z, fmaf(m.r11, bc.y, fmaf(m.r10, bc.x, m.ty)));
-                const float pz = fmaf(m.r22, bc.z, fmaf(m.r21, bc.y, fmaf(m.r20, bc.x, m.tz)));
-                const float ex = fmaf(az, be.z, fmaf(ay, be.y, ax * be.x));
-                const float ey = fmaf(bz, be.z, fmaf(by, be.y, bx * be.x));
-                const float ez = fmaf(cz, be.z, fmaf(cy, be.y, cx * be.x));
-                const float l0 = px - ex, h0 = px + ex, l1 = py - ey, h1 = py + ey, l2 = pz - ez, h2 = pz + ez;
-                lox = fminf(lox, l0); hix = fmaxf(hix, h0);
-                loy = fminf(loy, l1); hiy = fmaxf(hiy, h1);
-                loz = fminf(loz, l2); hiz = fmaxf(hiz, h2);
-                inside += (l0 <= a.obs_box.x_max && h0 >= a.obs_box.x_min && l1 <= a.obs_box.y_max &&
-                           h1 >= a.obs_box.y_min && l2 <= a.obs_box.z_max && h2 >= a.obs_box.z_min) ? 1 : 0;
-            }
-            const float gx = 0.01f + 4e-6f * fmaxf(fabsf(lox), fabsf(hix));
-            const float gy = 0.01f + 4e-6f * fmaxf(fabsf(loy), fabsf(hiy));
-            const float gz = 0.01f + 4e-6f * fmaxf(fabsf(loz), fabsf(hiz));
-            clear = lox - gx > a.obs_box.x_max || hix + gx < a.obs_box.x_min ||
-                    loy - gy > a.obs_box.y_max || hiy + gy < a.obs_box.y_min ||
-                    loz - gz > a.obs_box.z_max || hiz + gz < a.obs_box.z_min;
-        }
+        bool clear;
+        int inside;  // vertex groups whose box meets the obstacle AABB: the cost class of the descent
+        classify_one(a, m, clear, inside);
         clear = clear && in;
         const bool work = in && !clear;
         const unsigned mc = __ballot_sync(kFull, clear), mw = __ballot_sync(kFull, work);
@@ -280,10 +319,8 @@ __global__ void __launch_bounds__(64) classify_kernel(const __grid_constant__ Cl
         // in optimistic mode, clears the bits of the colliding configurations)
         if (lane == 0 && a.bitmask) a.bitmask[i >> 5] = a.optimistic ? (mc | mw) : mc;
         if (mw) {
-            // cost class from the share of the robot inside the obstacle AABB (edges ~ 1/64, 3/64, 7/64,
-            // 13/64, 21/64, 31/64, 43/64 of the groups), one list per class, warp-aggregated append
-            const int f = inside * (64 / kClassifyBoxes);
-            const int bin = (f >= 1) + (f >= 3) + (f >= 7) + (f >= 13) + (f >= 21) + (f >= 31) + (f >= 43);
+            // one list per cost class, warp-aggregated append
+            const int bin = cost_class(inside);
             const unsigned peers = __match_any_sync(kFull, work ? bin : kWorkBins);
             if (work) {
                 const int leader = __ffs(peers) - 1;
@@ -312,15 +349,235 @@ __device__ __forceinline__ void publish_invalid(const CheckArgs &a, long i, int 
     }
 }
 
+// FEED kernels: what a CTA keeps in shared memory.  Entries are drawn from the global lists a batch at
+// a time by whichever warp holds the lock and found the ring low (feed_refill); every warp of the CTA
+// pops its next entry from the ring.  Thousands of warps drawing one entry each from the same global
+// counters would queue up on their L2 lines -- and the dearest-first order needs the lengths of all
+// lists, which only one poller per CTA reads.
+constexpr int kFeedRing = 64;
+struct FeedShared {
+    uint2 ring[kFeedRing];          // (configuration, part)
+    uint32_t head, tail;            // popped (compare-and-swap by any warp), pushed (lock holder)
+    uint32_t lock, done, bex, first;  // refill lock; lists final and empty; no batch left to classify; warps that took their own first batch
+    uint32_t p_lo[kWorkBins], p_hi[kWorkBins];  // tickets drawn beyond the end of a list (a race with other CTAs while
+                                                // the classifiers were still listing): entries once the list reaches them
+};
+
+// Called by the warp that holds f->lock.  Reads the global counters, takes up to 32 tickets of the
+// dearest class that has entries (its own overshoot tickets first), waits for their slots, pushes the
+// entries onto the ring.  Sets f->done when every batch is classified and nothing is left for this CTA.
+__device__ __noinline__ void feed_refill(const CulledArgs &a, FeedShared *f, int lane)
+{
+    const uint32_t n_batches = (uint32_t)((a.k.n + 31) >> 5);
+    const uint32_t gs = (uint32_t)a.feed.gs;
+    const int cq = kWorkBins - 1 - lane;  // lane 0 looks at the dearest class
+    uint32_t h = 0, r = 0, lo = 0, hi = 0, d = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        if (lane < kWorkBins) {
+            r = ld_volatile(a.feed.ctr + cq * kFeedStride) << gs;
+            lo = f->p_lo[cq]; hi = f->p_hi[cq];
+            h = (lo == hi) ? ld_volatile(a.feed.ctr + (kWorkBins + cq) * kFeedStride) : r;
+        }
+        if (pass || __any_sync(kFull, (lo < hi && lo < r) || (lo == hi && h < r))) break;
+        // nothing to draw: are the lists final?  Batches done first, then the lengths once more -- if
+        // every batch was done before they were read, they are final
+        if (lane == 0) d = ld_volatile(a.feed.ctr + 17 * kFeedStride);
+        d = __shfl_sync(kFull, d, 0);
+        __threadfence();
+    }
+    uint32_t space = 0;
+    if (lane == 0) space = kFeedRing - (f->tail - ld_volatile(&f->head));
+    space = __shfl_sync(kFull, space, 0);
+    uint32_t want = min(32u, space), t0 = 0, k = 0;
+    int cl = -1;
+    const unsigned pv = __ballot_sync(kFull, lo < hi && lo < r);
+    const unsigned any_left = __ballot_sync(kFull, lo == hi && h < r);
+    if (pv && want > 0) {
+        const int l = __ffs(pv) - 1;
+        cl = kWorkBins - 1 - l;
+        t0 = __shfl_sync(kFull, lo, l);
+        k = min(want, min(__shfl_sync(kFull, hi, l), __shfl_sync(kFull, r, l)) - t0);
+        if (lane == 0) f->p_lo[cl] = t0 + k;
+    } else if (want > 0) {
+        const uint32_t mine = (lo == hi && h < r) ? r - h : 0u;
+        uint32_t total = mine;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) total += __shfl_xor_sync(kFull, total, o);
+        total = __shfl_sync(kFull, total, 0);
+        const unsigned av = __ballot_sync(kFull, mine > 0u);
+        if (av) {
+            const int l = __ffs(av) - 1;
+            cl = kWorkBins - 1 - l;
+            const uint32_t rr = __shfl_sync(kFull, r, l);
+            // near the end the CTAs take their share of what is left, so that none sits on 32 entries
+            want = min(want, max(1u, total / gridDim.x));
+            k = min(want, __shfl_sync(kFull, mine, l));
+            if (lane == 0) t0 = atomicAdd(a.feed.ctr + (kWorkBins + cl) * kFeedStride, k);
+            t0 = __shfl_sync(kFull, t0, 0);
+            const uint32_t t1 = t0 + k, good = min(t1, max(t0, rr));
+            if (good < t1 && lane == 0) { f->p_lo[cl] = good; f->p_hi[cl] = t1; }
+            k = good - t0;
+        }
+    }
+    if (k > 0) {
+        uint32_t tail = 0;
+        if (lane == 0) tail = f->tail;
+        tail = __shfl_sync(kFull, tail, 0);
+        if ((uint32_t)lane < k) {
+            const uint32_t t = t0 + lane;
+            const volatile unsigned long long *sl = reinterpret_cast<const volatile unsigned long long *>(
+                a.feed.slots + (size_t)cl * a.work_cap + (t >> gs));
+            unsigned long long v = 0;
+            // the slot was written right after its position was reserved: a short wait at most
+            for (uint32_t q = 0; q < kWatchdogSpins; q++) {
+                v = *sl;
+                if ((uint32_t)v == a.feed.gen) break;
+            }
+            if ((uint32_t)v != a.feed.gen) {  // cannot happen; counted.  The entry is pushed as a no-op (configuration n)
+                atomicAdd(a.c.counters + CNT_WATCHDOG, 1ULL);
+                atomicOr(a.c.counters + CNT_WATCHDOG_WHERE, 2ULL);
+                v = (unsigned long long)0xffffffffu << 32;
+            }
+            f->ring[(tail + lane) & (kFeedRing - 1)] = make_uint2((uint32_t)(v >> 32), t & ((1u << gs) - 1u));
+        }
+        __threadfence();  // the matrices of these entries were written before their slots
+        __syncwarp();
+        if (lane == 0) st_volatile(&f->tail, tail + k);
+    } else if (d == n_batches && !pv && !any_left) {
+        // the lists are final and hold nothing this CTA could still draw (a ticket range it keeps is void)
+        if (lane == 0) st_volatile(&f->done, 1u);
+    }
+}
+
+// FEED kernels: one batch of 32 configurations classified by one warp of the descent kernel (what a
+// warp of classify_kernel does in the two-launch form), flags written optimistically, the listed ones
+// appended to the per-class lists.  Not inlined: it runs between two descents and must not weigh on
+// the register allocation of the descent loop.
+__device__ __noinline__ void classify_batch(const CulledArgs &a, uint32_t b, int lane)
+{
+    const ClassifyArgs &k = a.k;
+    const unsigned lt = (1u << lane) - 1u;
+    const long i = (long)b * 32 + lane;
+    const bool in = i < k.n;
+    const Mat34 m = load_matrix(k.confs, in ? i : k.n - 1);
+    bool clear;
+    int inside;
+    classify_one(k, m, clear, inside);
+    clear = clear && in;
+    const bool work = in && !clear;
+    const unsigned mc = __ballot_sync(kFull, clear), mw = __ballot_sync(kFull, work);
+    if (in && k.valid) k.valid[i] = 1;  // optimistic: the descent only ever writes "invalid"
+    if (lane == 0 && k.bitmask) k.bitmask[i >> 5] = mc | mw;
+    if (mw) {
+        const int bin = cost_class(inside);
+        const unsigned peers = __match_any_sync(kFull, work ? bin : kWorkBins);
+        uint32_t pos = 0;
+        if (work) {
+            const int leader = __ffs(peers) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(a.feed.ctr + bin * kFeedStride, (uint32_t)__popc(peers));
+            pos = __shfl_sync(peers, base, leader) + __popc(peers & lt);
+            k.work_mat[3 * i + 0] = make_float4(m.r00, m.r01, m.r02, m.tx);
+            k.work_mat[3 * i + 1] = make_float4(m.r10, m.r11, m.r12, m.ty);
+            k.work_mat[3 * i + 2] = make_float4(m.r20, m.r21, m.r22, m.tz);
+        }
+        // flag, bitmask word and matrix first, then the slot that lets a descent start on them
+        __threadfence();
+        __syncwarp();
+        if (work) {
+            const unsigned long long v = (unsigned long long)a.feed.gen | ((unsigned long long)(uint32_t)i << 32);
+            *(volatile unsigned long long *)(a.feed.slots + (size_t)bin * k.work_cap + pos) = v;
+        }
+    }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) atomicAdd(a.feed.ctr + 17 * kFeedStride, 1u);  // the batch is done: its entries are visible before this count
+}
+
+// FEED kernels: the next entry of this warp -- (part << 32) | configuration -- or ~0 when the lists are
+// final and empty.  Classifies batches (the first cls_warps warps of the CTA, while any are left), else
+// pops an entry from the ring of the CTA, refilling it from the global lists when it runs low.
+__device__ __noinline__ unsigned long long feed_next(const CulledArgs &a, FeedShared *s_feed, int warp, int lane)
+{
+    const uint32_t n_batches = (uint32_t)((a.k.n + 31) >> 5);
+    for (uint32_t spins = 0;; spins++) {
+        // what other warps publish is read by one lane and broadcast: lanes reading the same
+        // word at different moments could take different branches of this loop
+        uint32_t fl = 0;
+        if (lane == 0) fl = (ld_volatile(&s_feed->bex) ? 1u : 0u) | (ld_volatile(&s_feed->done) ? 2u : 0u);
+        fl = __shfl_sync(kFull, fl, 0);
+        const uint32_t done = fl & 2u;  // read BEFORE the pop: nothing is pushed once it is set
+        if (warp < a.feed.cls_warps) {
+            // the first batch of every classifying warp is its own (thousands of atomicAdds on one word at
+            // the start of the kernel would queue up for microseconds), the rest are drawn
+            const uint32_t first = gridDim.x * (uint32_t)a.feed.cls_warps;
+            uint32_t b = 0xffffffffu;
+            if (lane == 0) {
+                if (!((ld_volatile(&s_feed->first) >> warp) & 1u)) {
+                    atomicOr(&s_feed->first, 1u << warp);
+                    b = blockIdx.x * (uint32_t)a.feed.cls_warps + (uint32_t)warp;
+                    if (first >= n_batches) st_volatile(&s_feed->bex, 1u);  // nothing will be left to draw
+                } else if (!(fl & 1u)) {
+                    b = first + atomicAdd(a.feed.ctr + 16 * kFeedStride, 1u);
+                    if (b >= n_batches) st_volatile(&s_feed->bex, 1u);
+                }
+            }
+            b = __shfl_sync(kFull, b, 0);
+            if (b < n_batches) {
+                classify_batch(a, b, lane);
+                continue;
+            }
+        }
+        // pop: the entry is read before the compare-and-swap that claims it (a refill never
+        // overwrites a position that has not been claimed)
+        uint32_t st = 0, left = 0;
+        unsigned long long e = 0;
+        if (lane == 0) {
+            for (;;) {
+                const uint32_t hd = ld_volatile(&s_feed->head), tl = ld_volatile(&s_feed->tail);
+                if (hd >= tl) break;
+                e = *reinterpret_cast<volatile unsigned long long *>(&s_feed->ring[hd & (kFeedRing - 1)]);
+                if (atomicCAS(&s_feed->head, hd, hd + 1u) == hd) {
+                    st = 1u; left = tl - hd - 1u;
+                    break;
+                }
+            }
+        }
+        st = __shfl_sync(kFull, st, 0);
+        const bool low = !st || __shfl_sync(kFull, left, 0) < 24u;
+        if (low && !done) {
+            uint32_t got = 0;
+            if (lane == 0) got = atomicCAS(&s_feed->lock, 0u, 1u) == 0u ? 1u : 0u;
+            got = __shfl_sync(kFull, got, 0);
+            if (got) {
+                feed_refill(a, s_feed, lane);
+                __syncwarp();
+                if (lane == 0) st_volatile(&s_feed->lock, 0u);
+            }
+        }
+        if (st) {
+            e = __shfl_sync(kFull, e, 0);
+            if ((uint32_t)e == 0xffffffffu) continue;  // a slot that never arrived (counted in feed_refill)
+            return e;
+        }
+        if (done || spins > kWatchdogSpins) {
+            if (!done && lane == 0) { atomicAdd(a.c.counters + CNT_WATCHDOG, 1ULL); atomicOr(a.c.counters + CNT_WATCHDOG_WHERE, 4ULL); }
+            return ~0ULL;
+        }
+        __nanosleep(spins < 8 ? 100 : 400);
+    }
+}
+
 // RL1 (with GOBS) = every leaf of the robot tree holds ONE triangle and the kernel knows its plane in
 // the robot frame: for an obstacle much finer than the robot (the subdivided obstacle: a robot triangle
 // is a thousand times the area of an obstacle triangle) the box of a four-triangle robot leaf is a poor
 // bound, while the slab of ONE robot triangle's plane culls every obstacle box that stays on one side
 // of it -- exactly the pairs the reference's first plane test rejects.
-template <bool STATS, int WARPS, bool GOBS, bool COP, bool RL1>
+template <bool STATS, int WARPS, bool GOBS, bool COP, bool RL1, bool FEED = false>
 __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __grid_constant__ CulledArgs a)
 {
     static_assert(!RL1 || GOBS, "one-triangle robot leaves are used with the obstacle in global memory");
+    static_assert(!FEED || !STATS, "the statistics kernels keep the two-launch form");
     constexpr int SH = GOBS ? 21 : 16;
     constexpr uint32_t LOW = (1u << SH) - 1u;
     constexpr int kStack = stack_cap_of(WARPS, GOBS);
@@ -346,6 +603,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
     uint32_t *s_wait = s_bin + kWorkBins + 1;  // [2 * WARPS] configuration a warp has finished but for its pieces: index, hit
     uint32_t *s_fetch = s_wait + 2 * WARPS;    // [2 * WARPS] entries of the list a warp has drawn: next, end
     uint32_t *s_seed = s_fetch + 2 * WARPS;    // [64] seed pairs of a whole descent  [256] seed pairs dealt out to split descents
+    static_assert(WARPS % 2 == 0, "an even number of words precedes s_feed, which holds 8-byte entries");
+    FeedShared *s_feed = reinterpret_cast<FeedShared *>(s_seed + 320);  // FEED kernels
     // obstacle accessors: shared memory, or the read-only global path
     auto obs_node = [&](int nb, int half) -> float4 {
         if constexpr (GOBS) return __ldg(a.obs_bvh + 2 * nb + half);
@@ -361,6 +620,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
         mbar_fence_init();
     }
     if (threadIdx.x < kMailSlots) s_mail[threadIdx.x].state = 0u;
+    if (FEED && threadIdx.x < sizeof(FeedShared) / 4) reinterpret_cast<uint32_t *>(s_feed)[threadIdx.x] = 0u;
     {
         // the seed pairs of every descent, encoded once per CTA (indexing the argument arrays per
         // configuration cost ~80 instructions each time)
@@ -390,8 +650,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
     }
     // everything above reads only the static tables; the work list, the flags and the bitmask
     // words come from classify_kernel: wait for that grid to complete (programmatic dependency)
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (threadIdx.x == 0) {
+    if constexpr (!FEED) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (FEED && threadIdx.x == 0) s_misc[0] = (uint32_t)a.feed.gs;
+    if (!FEED && threadIdx.x == 0) {
         uint32_t acc = 0;
         for (int o = 0; o < kWorkBins; o++) {
             s_bin[o] = acc;
@@ -408,7 +669,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
         s_misc[0] = gs;
     }
     __syncthreads();
-    mbar_wait(bar, 0);
+    // FEED kernels classify while the tables are still on their way: they wait before every descent
+    if constexpr (!FEED) mbar_wait(bar, 0);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
@@ -452,7 +714,23 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
 #endif
     for (;;) {
         uint32_t w = 0;
-        if (!dry && !waiting) {
+        if constexpr (FEED) {
+            if (!dry) {
+                // ---- single-launch form: feed_next classifies batches, pops the ring of the CTA and
+                // refills it (not inlined: the descent loop keeps the register allocation of the
+                // two-launch kernel)
+                const unsigned long long nx = feed_next(a, s_feed, warp, lane);
+                if (nx == ~0ULL) {
+                    dry = true;
+                    if (lane == 0) atomicAdd(s_idle, 1u);
+                } else {
+                    w = (uint32_t)nx;                                          // configuration index
+                    if (lane == 0) s_fetch[2 * warp] = (uint32_t)(nx >> 32);   // part
+                    __syncwarp();
+                }
+            }
+        }
+        if (!FEED && !dry && !waiting) {
             const uint32_t gs0 = s_misc[0];
             const uint32_t n_work = s_bin[kWorkBins] << gs0;  // entries: (configuration, part)
             uint32_t w_next = s_fetch[2 * warp], w_end = s_fetch[2 * warp + 1];
@@ -613,8 +891,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
             __syncwarp();
         } else {
             const uint32_t gs = s_misc[0];
-            const uint32_t wl = w >> gs, part = w & ((1u << gs) - 1u);
-            {
+            uint32_t part;
+            if constexpr (FEED) {
+                i = w;
+                part = s_fetch[2 * warp];
+            } else {
+                const uint32_t wl = w >> gs;
+                part = w & ((1u << gs) - 1u);
                 // list position -> (cost class, position in its list): dearest class first
                 const uint32_t o = __popc(__ballot_sync(kFull, lane >= 1 && lane < kWorkBins && wl >= s_bin[lane & (kWorkBins - 1)]));
                 i = __ldcg(a.work_idx + (size_t)(kWorkBins - 1 - o) * a.work_cap + (wl - s_bin[o]));
@@ -658,6 +941,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
             __syncwarp();
         }
         const int pend_slot = owner >= 0 ? owner : warp;
+        if constexpr (FEED) mbar_wait(bar, 0);  // the tables have landed (immediate after the first time)
 #ifdef RC_TIMELINE
         tl_entries++;
         if (dry) tl_got++;
@@ -1056,7 +1340,7 @@ static size_t culled_smem_bytes(const DeviceTables &t, int warps, bool gobs)
     else if (t.rob_leaf == 1)
         b += (size_t)t.n_rob_t * 16;  // robot triangle planes
     b += (size_t)warps * (stack_cap_of(warps, gobs) + kLeafQCap + kTailQCap) * 4;
-    b = (b + 15) / 16 * 16 + kMailSlots * sizeof(Mail) + (5 * (size_t)warps + 7 + kWorkBins + 1 + 2 + 320) * 4;  // + s_pend, s_idle, s_misc, s_bin, s_wait, s_fetch, s_seed
+    b = (b + 15) / 16 * 16 + kMailSlots * sizeof(Mail) + (5 * (size_t)warps + 7 + kWorkBins + 1 + 2 + 320) * 4 + 8 + sizeof(FeedShared);  // + s_pend, s_idle, s_misc, s_bin, s_wait, s_fetch, s_seed
     return b;
 }
 
@@ -1066,6 +1350,13 @@ static void (*pick_culled(int warps, int want_stats))(const CulledArgs)
     if (warps == 16) return want_stats ? check_culled_kernel<true, 16, GOBS, COP, RL1> : check_culled_kernel<false, 16, GOBS, COP, RL1>;
     if (warps == 32) return want_stats ? check_culled_kernel<true, 32, GOBS, COP, RL1> : check_culled_kernel<false, 32, GOBS, COP, RL1>;
     return want_stats ? check_culled_kernel<true, 24, GOBS, COP, RL1> : check_culled_kernel<false, 24, GOBS, COP, RL1>;
+}
+
+template <bool COP>
+static void (*pick_culled_feed(int warps))(const CulledArgs)
+{
+    // the single-launch form exists for the full-size CTA with the obstacle in shared memory
+    return warps == 32 ? check_culled_kernel<false, 32, false, COP, false, true> : nullptr;
 }
 
 // Obstacle tables go to shared memory when everything fits with at least 16 warps per CTA; otherwise
@@ -1147,7 +1438,7 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
     if (!ctx->d_work_idx || ctx->work_cap < n) return cudaErrorMemoryAllocation;  // rc_check sizes it
 
     // step 1: classify (thread per configuration); writes every bitmask word, so no memset
-    ClassifyArgs k;
+    ClassifyArgs &k = a.k;
     k.confs = d_confs; k.n = n; k.valid = d_valid; k.bitmask = d_bitmask; k.obs_box = t.obs_box;
     k.sph_x = a.sph_x; k.sph_y = a.sph_y; k.sph_z = a.sph_z; k.sph_r = a.sph_r;
     k.box_cx = a.box_cx; k.box_cy = a.box_cy; k.box_cz = a.box_cz;
@@ -1158,6 +1449,29 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
     k.work_cap = ctx->work_cap;
     k.counters = ctx->d_counters;
     k.optimistic = a.optimistic;
+    memset(&a.feed, 0, sizeof a.feed);
+    if (extras && extras->feed && !want_stats && !gobs && ctx->d_feed_slots && n <= ctx->work_cap && n < (1L << 28)) {
+        // single launch: the descent kernel classifies the configurations itself (FeedArgs)
+        void (*fk)(const CulledArgs) = ctx->coplanar_mode ? pick_culled_feed<true>(warps) : pick_culled_feed<false>(warps);
+        if (fk) {
+            a.feed.on = 1;
+            int gs = 0;
+            while ((2 << gs) <= a.split_max &&
+                   ((unsigned long long)n << (gs + 1)) <= (unsigned long long)a.split_load * grid * warps)
+                gs++;
+            a.feed.gs = gs;
+            a.feed.cls_warps = extras->feed_cls_warps > 0 ? min(warps, extras->feed_cls_warps) : min(warps, 8);
+            a.feed.gen = extras->feed_gen;
+            a.feed.slots = ctx->d_feed_slots;
+            a.feed.ctr = ctx->d_feed_ctr;
+            k.optimistic = 1;
+            cudaError_t e = cudaMemsetAsync(ctx->d_feed_ctr, 0, kFeedCounters * kFeedStride * sizeof(uint32_t), stream);
+            if (e != cudaSuccess) return e;
+            if ((e = cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+            fk<<<grid, warps * 32, smem, stream>>>(a);
+            return cudaGetLastError();
+        }
+    }
     void (*kern)(const CulledArgs);
     if (ctx->coplanar_mode)
         kern = rl1 ? pick_culled<true, true, true>(warps, want_stats)

@@ -118,6 +118,11 @@ struct rc_ctx {
     float4 *d_work_mat = nullptr;
     unsigned long long *d_work_count = nullptr;
     long work_cap = 0;
+    uint2 *d_feed_slots = nullptr;             // single-launch form: [kWorkBins][work_cap] (call number, configuration)
+    uint32_t *d_feed_ctr = nullptr;            // its 32 counters
+    uint32_t feed_gen = 0;                     // call number of the last single-launch check
+    int knob_feed = 1;                         // RC_FEED: 0 never, 1 rc_check_host (configurations read in place over PCIe), 2 rc_check too
+    int knob_feed_cls = 0;                     // RC_FEED_CLS: classifying warps per CTA (0 = automatic)
     uint32_t *d_block_counts = nullptr;        // scratch of rc_compact, grown on demand
     long block_counts_cap = 0;
     unsigned long long *d_queues = nullptr;    // [kHostChunks] work-queue counters of rc_check_host
@@ -186,6 +191,9 @@ struct GatherArgs {
 struct CheckExtras {
     const GatherArgs *gather = nullptr;      // culled mode: the last CTA pushes the bitmask slot to the peers
     uint32_t *hit_counts = nullptr;          // statistics kernels: hitting pairs per configuration, no early exit
+    int feed = 0;                            // culled mode: single launch, the descent kernel classifies (rc_culled.cuh: FeedArgs)
+    int feed_cls_warps = 0;                  // warps per CTA that classify (0 = all; 2 when the configurations are read over PCIe)
+    uint32_t feed_gen = 0;
 };
 
 // kernels.cu launchers (all asynchronous on `stream`)
