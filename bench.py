@@ -365,7 +365,10 @@ def main():
     h_valid = torch.zeros(n, dtype=torch.uint8).pin_memory()
     np_confs, np_valid = h_confs.numpy(), h_valid.numpy()
     lib = rc.lib()
-    e2e_api = "rc_check_host (pinned host buffers)"
+    feed = os.environ.get("RC_FEED", "1")
+    e2e_api = ("rc_check_host (pinned host buffers; single launch: the kernel reads the configurations from the "
+               "caller's buffer over PCIe, 2.4 MB per step, and classifies them itself; flags copied back)"
+               if feed != "0" else "rc_check_host (pinned host buffers; H2D copy, two launches, D2H copy)")
     h_mask_all = torch.zeros(world * words, dtype=torch.int32).pin_memory()
     d_stage = torch.empty(n * 6, dtype=torch.float32, device=dev)
     h_flat = h_confs.view(-1)

@@ -802,7 +802,7 @@ int rc_check_host(rc_ctx *ctx, const rc_config *h_confs, long n, uint8_t *h_vali
     if (direct || n < 4096) waves = 1;
     // Single launch, no host-to-device copy (RC_FEED >= 1, the default): the kernel reads the
     // configurations where they lie -- the caller's page-locked buffer, or the pinned staging area a
-    // pageable one was copied to -- over PCIe, two warps per CTA classifying batches as they come in while
+    // pageable one was copied to -- over PCIe, four warps per CTA classifying batches as they come in while
     // the other warps already run descents on the ones that need them.  The copy (2.4 MB, ~50 us for
     // 100,000 configurations), the classify step and the second launch no longer stand in front of the
     // descents.
@@ -816,7 +816,7 @@ int rc_check_host(rc_ctx *ctx, const rc_config *h_confs, long n, uint8_t *h_vali
     if (mapped_confs) {
         rc::CheckExtras x;
         x.feed = 1;
-        x.feed_cls_warps = 2;
+        x.feed_cls_warps = 4;
         cudaEventRecord(ctx->ev0, s);
         if ((rcode = check_on_stream(ctx, mapped_confs, n, d_out, nullptr, mode, s, &x, "rc_check_host launch (single)")) != RC_OK)
             return rcode;

@@ -1031,3 +1031,35 @@ def test_gather_two_ranks_on_one_device(rc, ctx, meshes):
     finally:
         for c in ranks:
             c.close()
+
+
+@pytest.mark.parametrize("feed", ["0", "1", "2"])
+def test_single_launch_form_every_size(rc, meshes, feed, monkeypatch):
+    """RC_FEED: the descent kernel classifies the configurations itself (rc_culled.cuh: FeedArgs).
+    0 = never (two launches, host buffers copied first), 1 = the host call reads the caller's buffer
+    in place over PCIe (default), 2 = device-resident checks use the form too.  Every size from one
+    configuration up -- one batch, ragged batches, split descents, a list longer than the grid -- against
+    the exhaustive kernel; page-locked and pageable host buffers; repeated calls on one context (the
+    list slots are tagged with the call number, not cleared)."""
+    torch = _torch()
+    monkeypatch.setenv("RC_FEED", feed)
+    confs = np.concatenate([rc.createAlphaBotConfigurations(20_000, True, 508),
+                            rc.createAlphaBotConfigurations(10_000, False, 510)])
+    confs = confs[np.random.default_rng(3).permutation(len(confs))]
+    c = rc.Context(meshes[0], meshes[1], device=0)
+    try:
+        want = run_check(c, confs, rc.RC_MODE_BRUTE)
+        pinned = torch.from_numpy(confs).pin_memory()
+        for n in (1, 31, 32, 33, 1000, 4737, 30_000):
+            for rep in range(2):
+                got, bits = run_check(c, confs[:n], rc.RC_MODE_CULLED, bitmask=True)
+                assert np.array_equal(got, want[:n]), (feed, n, rep, int((got != want[:n]).sum()))
+                assert np.array_equal(bits, want[:n])
+                assert np.array_equal(c.check_host(confs[:n]), want[:n]), (feed, n, rep, "pageable")
+                assert np.array_equal(c.check_host(pinned.numpy()[:n]), want[:n]), (feed, n, rep, "pinned")
+        # the reference's far sampler: nearly everything cleared by the classifying warps themselves
+        far = rc.createAlphaBotConfigurations(50_000, False, 511)
+        assert np.array_equal(c.check_host(far), run_check(c, far, rc.RC_MODE_BRUTE))
+        assert c.stats()["watchdog"] == 0
+    finally:
+        c.close()
