@@ -97,8 +97,13 @@ int rc_obstacle_aabb(const rc_ctx *ctx, rc_aabb *out);
  * pre-fill.  Asynchronous. */
 int rc_check(rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_valid, uint32_t *d_bitmask,
              int mode, void *stream);
-/* Same, host buffers: pinned staging, H2D, rc_check, D2H, synchronised on return.  This is the
- * call behind the broadPhaseFused_sep(std::vector<Configuration>&, bool*) shim. */
+/* Same, host buffers, synchronised on return.  This is the call behind the
+ * broadPhaseFused_sep(std::vector<Configuration>&, bool*) shim.  RC_MODE_CULLED runs as ONE launch
+ * with no host-to-device copy in front of it: the kernel reads the configurations where they lie -- the
+ * caller's buffer if it is page-locked (cudaMallocHost / cudaHostRegister), else the pinned staging
+ * area a pageable buffer is copied to first -- over PCIe, a few warps per CTA classifying batches of
+ * 32 as they come in while the other warps already run descents on the ones that need them; the flags
+ * are copied back.  RC_FEED=0 in the environment restores copy + two launches. */
 int rc_check_host(rc_ctx *ctx, const rc_config *h_confs, long n, uint8_t *h_valid, int mode);
 
 /* Single-process multi-GPU check (north_star: configurations shard across the GPUs of one box, the

@@ -1,0 +1,12 @@
+#!/bin/bash
+mkdir -p gpurun_out
+nvidia-smi -L | wc -l
+timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -q -x 2>&1 | tail -3
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 > gpurun_out/bench_r02_8gpu.json 2> gpurun_out/bench_r02_8gpu.err; echo rc=$?
+tail -3 gpurun_out/bench_r02_8gpu.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench_r02_8gpu.json').read().strip().splitlines()[-1])
+print({k:d[k] for k in ('value','ms_per_step','n_gpus','gpu_launches')}, 'e2e', d['e2e']['value'], d['config']['collective'][:60], d['config']['collective_check'])
+print({k:(v['value'], v['ms'], v['collective_check']) for k,v in d.items() if k.startswith('scale_')})
+PY
