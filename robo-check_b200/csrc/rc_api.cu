@@ -360,7 +360,7 @@ int rc_create(rc_ctx **out, const float *rob_x, const float *rob_y, const float 
         ctx->knob_donate_leaf = knob("RC_DONATE_LEAF", 16);
         ctx->knob_feed = knob("RC_FEED", 1);
         ctx->knob_feed_cls = knob("RC_FEED_CLS", 0);
-        ctx->knob_split_max = knob("RC_SPLIT_MAX", 16);
+        ctx->knob_split_max = knob("RC_SPLIT_MAX", 64);
         ctx->knob_split_load = knob("RC_SPLIT_LOAD", 8);
         ctx->knob_host_chunks = knob("RC_HOST_CHUNKS", 0);
     }

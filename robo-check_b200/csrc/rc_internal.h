@@ -138,7 +138,7 @@ struct rc_ctx {
     int knob_mail_slots = 4, knob_donate_min = 40, knob_donate_leaf = 16;  // RC_MAIL_SLOTS, RC_DONATE_MIN, RC_DONATE_LEAF
     int knob_host_direct = 0; // RC_HOST_DIRECT=1: rc_check_host stores the flags into the pinned buffer from the kernels instead of copying them back
     int knob_share = 1;      // RC_SHARE=0: warps of a CTA do not hand pieces of a deep descent to each other
-    int knob_split_max = 16;  // RC_SPLIT_MAX: parts a configuration may be cut into when the work list is short (1 = never)
+    int knob_split_max = 64;  // RC_SPLIT_MAX: parts a configuration may be cut into when the work list is short (1 = never)
     int knob_split_load = 8;  // RC_SPLIT_LOAD: split while entries <= this many per warp of the grid
     std::string last_error;
     std::vector<void *> allocations;
