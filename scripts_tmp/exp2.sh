@@ -1,5 +1,5 @@
 #!/bin/bash
-V=$PWD/ab/librobocheck_v2.so
+V=$PWD/ab/librobocheck_v5.so
 export RC_LIB=$V
 echo "== correctness, RC_FEED=2 (every culled check through the single-launch form)"
 RC_FEED=2 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "culled_matches_oracle or check_host_matches or empty_and_ragged or culled_equals_brute_large or golden or million or planner_sized or pipelined or full_size_workloads or coplanar_mode or scheduling_variants or different_streams" 2>&1 | tail -5

@@ -1,8 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-nvidia-smi -L | wc -l
-timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -q -x 2>&1 | tail -3
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 > gpurun_out/bench_r02_8gpu.json 2> gpurun_out/bench_r02_8gpu.err; echo rc=$?
+timeout 270 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 > gpurun_out/bench_r02_8gpu.json 2> gpurun_out/bench_r02_8gpu.err; echo rc=$?
 tail -3 gpurun_out/bench_r02_8gpu.err
 python - <<'PY'
 import json
