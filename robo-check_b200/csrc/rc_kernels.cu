@@ -133,46 +133,82 @@ __device__ __forceinline__ void publish(const CheckArgs &a, long i, bool valid, 
 // stages run at most once per lane and triangle between two warp-wide flushes, so the rare path
 // executes with several lanes instead of one.  `load_tri(j)` yields the world-space triangle.
 // COUNT: no early exit, every hitting pair is counted into `tails`' sibling `n_hits` (audit mode).
+constexpr int kSweepQueue = 128;  // words per warp: two queues of 64 (pairs that passed the first / both plane tests)
+
 template <bool COP, bool COUNT, class LoadTri>
 __device__ __forceinline__ bool exhaustive_sweep(LoadTri load_tri, int n_rob_t,
                                                  const float4 *__restrict__ s_obs_a,
                                                  const float4 *__restrict__ s_obs_b,
                                                  const float4 *__restrict__ s_obs_c,
                                                  const float *__restrict__ s_obs_d, int n_obs_t,
-                                                 int lane, unsigned long long &tails, uint32_t &n_hits)
+                                                 int lane, unsigned long long &tails, uint32_t &n_hits,
+                                                 uint32_t *__restrict__ q1)
 {
+    // The ~5 % of the pairs that pass the first plane test are not finished where they are found (a
+    // handful of lanes at a time: the kernel ran 23 of 32 lanes) but queued per warp as (robot triangle,
+    // obstacle triangle) and taken up 32 at a time: second plane test with full warps, its survivors
+    // queued again, intersection line and intervals with full warps.  The robot triangle of a queued
+    // pair is produced again by load_tri (bit-identical), so the queues outlive the pass they were
+    // filled in.  Which pairs are decided, and how, is unchanged: the order does not enter the result.
+    uint32_t *q2 = q1 + kSweepQueue / 2;
+    int n1 = 0, n2 = 0;
     bool hit = false;
+    const unsigned lt = (1u << lane) - 1u;
+
+    // the rest of the test for up to 32 queued pairs that passed both plane tests
+    auto finish = [&](int cnt) {
+        n2 -= cnt;
+        const bool act = lane < cnt;
+        const uint32_t e = q2[n2 + (act ? lane : 0)];
+        const int k = (int)(e & 0xffffu);
+        const Tri r = load_tri((int)(e >> 16));
+        const Plane pr = plane_of(r);
+        const float4 oa = s_obs_a[k], ob = s_obs_b[k], oc = s_obs_c[k];
+        const Tri o = {oa.x, oa.y, oa.z, ob.x, ob.y, ob.z, oc.x, oc.y, oc.z};
+        const Plane po = {oa.w, ob.w, oc.w, s_obs_d[k]};
+        const float dR0 = sdist(po, r.ax, r.ay, r.az), dR1 = sdist(po, r.bx, r.by, r.bz),
+                    dR2 = sdist(po, r.cx, r.cy, r.cz);
+        const float dO0 = sdist(pr, o.ax, o.ay, o.az), dO1 = sdist(pr, o.bx, o.by, o.bz),
+                    dO2 = sdist(pr, o.cx, o.cy, o.cz);
+        const int verdict = act ? pair_tail(r, pr, dR0, dR1, dR2, o, po, dO0, dO1, dO2) : kPairMiss;
+        bool h = verdict == kPairHit;
+        if constexpr (COP) {  // RC_COPLANAR_DECIDE
+            if (verdict == kPairCoplanar && coplanar_overlap(r, o, pr)) h = true;
+        }
+        const unsigned mh = __ballot_sync(kFull, h);
+        if (lane == 0) {
+            tails += (unsigned long long)cnt;
+            if (COUNT) n_hits += (uint32_t)__popc(mh);
+        }
+        if (mh) hit = true;
+        __syncwarp();
+    };
+    // the second plane test for up to 32 queued pairs that passed the first
+    auto second = [&](int cnt) {
+        n1 -= cnt;
+        const bool act = lane < cnt;
+        const uint32_t e = q1[n1 + (act ? lane : 0)];
+        const int k = (int)(e & 0xffffu);
+        const Tri r = load_tri((int)(e >> 16));
+        const float4 oa = s_obs_a[k], ob = s_obs_b[k], oc = s_obs_c[k];
+        const Plane po = {oa.w, ob.w, oc.w, s_obs_d[k]};
+        const bool pass = act && straddles(sdist(po, r.ax, r.ay, r.az), sdist(po, r.bx, r.by, r.bz),
+                                           sdist(po, r.cx, r.cy, r.cz));
+        const unsigned mp = __ballot_sync(kFull, pass);
+        __syncwarp();  // everybody has read its entry before the queues move
+        if (pass) q2[n2 + __popc(mp & lt)] = e;
+        n2 += __popc(mp);
+        __syncwarp();
+        if (n2 >= 32) finish(32);
+    };
+
     for (int jb = 0; jb < n_rob_t && (COUNT || !hit); jb += 64) {
-        const Tri r0 = load_tri(min(jb + lane, n_rob_t - 1));
-        const Tri r1 = load_tri(min(jb + 32 + lane, n_rob_t - 1));
+        const int j0 = min(jb + lane, n_rob_t - 1), j1 = min(jb + 32 + lane, n_rob_t - 1);
+        const Tri r0 = load_tri(j0);
+        const Tri r1 = load_tri(j1);
         const Plane p0 = plane_of(r0), p1 = plane_of(r1);
-
-        // second plane test and the rest for one (robot triangle, obstacle triangle k)
-        auto finish = [&](const Tri &r, const Plane &pr, int k) {
-            const float4 oa = s_obs_a[k], ob = s_obs_b[k], oc = s_obs_c[k];
-            const Tri o = {oa.x, oa.y, oa.z, ob.x, ob.y, ob.z, oc.x, oc.y, oc.z};
-            const Plane po = {oa.w, ob.w, oc.w, s_obs_d[k]};
-            const float dR0 = sdist(po, r.ax, r.ay, r.az), dR1 = sdist(po, r.bx, r.by, r.bz),
-                        dR2 = sdist(po, r.cx, r.cy, r.cz);
-            if (straddles(dR0, dR1, dR2)) {
-                tails++;
-                const float dO0 = sdist(pr, o.ax, o.ay, o.az), dO1 = sdist(pr, o.bx, o.by, o.bz),
-                            dO2 = sdist(pr, o.cx, o.cy, o.cz);
-                const int verdict = pair_tail(r, pr, dR0, dR1, dR2, o, po, dO0, dO1, dO2);
-                bool h = verdict == kPairHit;
-                if constexpr (COP) {  // RC_COPLANAR_DECIDE
-                    if (verdict == kPairCoplanar && coplanar_overlap(r, o, pr)) h = true;
-                }
-                if (h) {
-                    hit = true;
-                    if (COUNT) n_hits++;
-                }
-            }
-        };
-
-        // Obstacle triangles in blocks of 32: the first plane test of every pair sets a bit, the
-        // (rare, ~5 %) survivors of a block are finished together afterwards, one per lane and
-        // step, so the hot loop has no vote and the long path runs with many lanes.
+        // Obstacle triangles in blocks of 32: the first plane test of every pair sets a bit; the hot
+        // loop has no vote and no branch.
         for (int kb = 0; kb < n_obs_t; kb += 32) {
             uint32_t m0 = 0, m1 = 0;
             const int kn = min(32, n_obs_t - kb);
@@ -187,29 +223,32 @@ __device__ __forceinline__ bool exhaustive_sweep(LoadTri load_tri, int n_rob_t,
                 m0 |= (uint32_t)pass0 << q;
                 m1 |= (uint32_t)pass1 << q;
             }
-            if (COUNT) {  // lanes past the end re-test the last triangle: not counted twice
+            // lanes past the end re-test the last triangle: a duplicate cannot change "some pair hits",
+            // but it must not be counted twice
+            if (COUNT) {
                 if (jb + lane >= n_rob_t) m0 = 0u;
                 if (jb + 32 + lane >= n_rob_t) m1 = 0u;
             }
+            // queue the survivors, one per lane and step
             while (__any_sync(kFull, (m0 | m1) != 0u)) {
-                if (m0 | m1) {
-                    // one code path for both triangles of the lane (selects instead of branches)
-                    const bool first = m0 != 0u;
-                    const uint32_t mm = first ? m0 : m1;
-                    const int q = __ffs(mm) - 1;
-                    if (first) m0 &= m0 - 1; else m1 &= m1 - 1;
-                    const Tri r = {first ? r0.ax : r1.ax, first ? r0.ay : r1.ay, first ? r0.az : r1.az,
-                                   first ? r0.bx : r1.bx, first ? r0.by : r1.by, first ? r0.bz : r1.bz,
-                                   first ? r0.cx : r1.cx, first ? r0.cy : r1.cy, first ? r0.cz : r1.cz};
-                    const Plane pr = {first ? p0.nx : p1.nx, first ? p0.ny : p1.ny,
-                                      first ? p0.nz : p1.nz, first ? p0.s : p1.s};
-                    finish(r, pr, kb + q);
+                const bool has = (m0 | m1) != 0u, first = m0 != 0u;
+                const uint32_t mm = first ? m0 : m1;
+                const int q = has ? __ffs(mm) - 1 : 0;
+                if (first) m0 &= m0 - 1; else m1 &= m1 - 1;
+                const unsigned mp = __ballot_sync(kFull, has);
+                if (has) q1[n1 + __popc(mp & lt)] = ((uint32_t)(first ? j0 : j1) << 16) | (uint32_t)(kb + q);
+                n1 += __popc(mp);
+                __syncwarp();
+                if (n1 >= 32) {
+                    second(32);
+                    if (!COUNT && hit) break;
                 }
             }
-            if (!COUNT && __any_sync(kFull, hit)) break;
+            if (!COUNT && hit) break;
         }
-        hit = __any_sync(kFull, hit);
     }
+    while (n1 > 0 && (COUNT || !hit)) second(min(n1, 32));
+    while (n2 > 0 && (COUNT || !hit)) finish(min(n2, 32));
     return hit;
 }
 
@@ -227,6 +266,7 @@ __global__ void __launch_bounds__(kThreads, 2) check_brute_kernel(const CheckArg
     float4 *s_obs_c = s_obs_b + a.n_obs_t;
     float *s_obs_d = reinterpret_cast<float *>(s_obs_c + a.n_obs_t);
     uint2 *s_rob_t = reinterpret_cast<uint2 *>(s_obs_d + pad4(a.n_obs_t));
+    uint32_t *s_queue = reinterpret_cast<uint32_t *>(s_rob_t + a.n_rob_t + (a.n_rob_t & 1)) + (threadIdx.x >> 5) * kSweepQueue;
 
     // Stage the mesh tables with TMA bulk copies (one elected thread issues them, everybody
     // waits on the mbarrier's transaction count).
@@ -285,13 +325,13 @@ __global__ void __launch_bounds__(kThreads, 2) check_brute_kernel(const CheckArg
             uint32_t n_hits = 0;
             if (STATS && a.hit_counts) {
                 hit = exhaustive_sweep<COP, true>(load_tri, a.n_rob_t, s_obs_a, s_obs_b, s_obs_c, s_obs_d,
-                                                  a.n_obs_t, lane, st_tail, n_hits);
+                                                  a.n_obs_t, lane, st_tail, n_hits, s_queue);
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) n_hits += __shfl_xor_sync(kFull, n_hits, o);
                 if (lane == 0) a.hit_counts[i] = n_hits;
             } else {
                 hit = exhaustive_sweep<COP, false>(load_tri, a.n_rob_t, s_obs_a, s_obs_b, s_obs_c, s_obs_d,
-                                                   a.n_obs_t, lane, st_tail, n_hits);
+                                                   a.n_obs_t, lane, st_tail, n_hits, s_queue);
             }
             publish(a, i, !hit, lane);
             if (STATS) { if (hit) st_invalid++; else st_valid++; }
@@ -328,7 +368,7 @@ namespace rc {
 static size_t brute_smem_bytes(const DeviceTables &t)
 {
     return 16 + (size_t)t.n_rob_v_pad * 16 + (size_t)t.n_obs_t * 48 + (size_t)pad4(t.n_obs_t) * 4 +
-           (size_t)(t.n_rob_t + (t.n_rob_t & 1)) * 8;
+           (size_t)(t.n_rob_t + (t.n_rob_t & 1)) * 8 + (size_t)kWarpsPerCta * kSweepQueue * 4;
 }
 
 cudaError_t launch_check(const rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_valid,

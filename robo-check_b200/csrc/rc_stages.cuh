@@ -348,6 +348,7 @@ __global__ void __launch_bounds__(kThreads, 2) narrow_soa_kernel(const CheckArgs
     float4 *s_obs_c = s_obs_b + a.n_obs_t;
     float *s_obs_d = reinterpret_cast<float *>(s_obs_c + a.n_obs_t);
     uint2 *s_rob_t = reinterpret_cast<uint2 *>(s_obs_d + pad4(a.n_obs_t));
+    uint32_t *s_queue = reinterpret_cast<uint32_t *>(s_rob_t + a.n_rob_t + (a.n_rob_t & 1)) + (threadIdx.x >> 5) * kSweepQueue;
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         mbar_fence_init();
@@ -382,7 +383,7 @@ __global__ void __launch_bounds__(kThreads, 2) narrow_soa_kernel(const CheckArgs
         unsigned long long tails = 0;
         uint32_t n_hits = 0;
         const bool hit = exhaustive_sweep<COP, false>(load_tri, a.n_rob_t, s_obs_a, s_obs_b, s_obs_c, s_obs_d,
-                                                      a.n_obs_t, lane, tails, n_hits);
+                                                      a.n_obs_t, lane, tails, n_hits, s_queue);
         if (lane == 0) a.valid[i] = hit ? 0 : 1;
     }
 }
@@ -402,7 +403,7 @@ cudaError_t launch_narrow_soa(const rc_ctx *ctx, const float *d_x, const float *
     a.confs = nullptr; a.n = n; a.valid = d_valid; a.bitmask = nullptr;
     a.counters = ctx->d_counters; a.queue = ctx->d_counters + CNT_QUEUE; a.chunk = 1;
     const size_t smem = 16 + (size_t)t.n_obs_t * 48 + (size_t)pad4(t.n_obs_t) * 4 +
-                        (size_t)(t.n_rob_t + (t.n_rob_t & 1)) * 8;
+                        (size_t)(t.n_rob_t + (t.n_rob_t & 1)) * 8 + (size_t)kWarpsPerCta * kSweepQueue * 4;
     if (smem > (size_t)ctx->max_smem_optin) return cudaErrorInvalidConfiguration;
     auto kern = ctx->coplanar_mode ? narrow_soa_kernel<true> : narrow_soa_kernel<false>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
