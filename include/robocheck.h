@@ -98,7 +98,8 @@ int rc_obstacle_aabb(const rc_ctx *ctx, rc_aabb *out);
 int rc_check(rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_valid, uint32_t *d_bitmask,
              int mode, void *stream);
 /* Same, host buffers, synchronised on return.  This is the call behind the
- * broadPhaseFused_sep(std::vector<Configuration>&, bool*) shim.  RC_MODE_CULLED runs as ONE launch
+ * broadPhaseFused_sep(std::vector<Configuration>&, bool*) shim.  From 65,536 configurations on (below that the
+ * configurations are copied first: the copy is short there) RC_MODE_CULLED runs as ONE launch
  * with no host-to-device copy in front of it: the kernel reads the configurations where they lie -- the
  * caller's buffer if it is page-locked (cudaMallocHost / cudaHostRegister), else the pinned staging
  * area a pageable buffer is copied to first -- over PCIe, a few warps per CTA classifying batches of

@@ -591,6 +591,7 @@ int rc_obstacle_aabb(const rc_ctx *ctx, rc_aabb *out)
     return RC_OK;
 }
 
+constexpr long kFeedMinHost = 1L << 16;  // rc_check_host: smallest batch read in place (below: copy + two launches)
 constexpr long kFeedMax = 1L << 22;  // configurations per call of the single-launch form (64 B of list per configuration)
 
 static int check_on_stream(rc_ctx *ctx, const rc_config *d_confs, long n, uint8_t *d_valid, uint32_t *d_bitmask,
@@ -807,7 +808,11 @@ int rc_check_host(rc_ctx *ctx, const rc_config *h_confs, long n, uint8_t *h_vali
     // 100,000 configurations), the classify step and the second launch no longer stand in front of the
     // descents.
     const rc_config *mapped_confs = nullptr;
-    if (ctx->knob_feed >= 1 && mode == RC_MODE_CULLED && !ctx->stats_on && !ctx->t.gobs && n <= kFeedMax && waves <= 1) {
+    // ... for batches large enough that the copy is worth hiding: below ~64 k configurations the copy path
+    // is quicker (2,000 configurations 88 us against 97, 30,000: 200-223 against 254-264; 100,000: 360-470
+    // against 344-352, profiles/feed_r02.txt), RC_FEED=2 uses the form for any size
+    if (ctx->knob_feed >= 1 && (n >= kFeedMinHost || ctx->knob_feed >= 2) && mode == RC_MODE_CULLED && !ctx->stats_on &&
+        !ctx->t.gobs && n <= kFeedMax && waves <= 1) {
         void *mp = nullptr;
         if (cudaHostGetDevicePointer(&mp, const_cast<rc_config *>(src), 0) == cudaSuccess && mp)
             mapped_confs = static_cast<const rc_config *>(mp);

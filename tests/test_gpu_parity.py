@@ -1043,14 +1043,14 @@ def test_single_launch_form_every_size(rc, meshes, feed, monkeypatch):
     list slots are tagged with the call number, not cleared)."""
     torch = _torch()
     monkeypatch.setenv("RC_FEED", feed)
-    confs = np.concatenate([rc.createAlphaBotConfigurations(20_000, True, 508),
-                            rc.createAlphaBotConfigurations(10_000, False, 510)])
+    confs = np.concatenate([rc.createAlphaBotConfigurations(50_000, True, 508),
+                            rc.createAlphaBotConfigurations(20_000, False, 510)])
     confs = confs[np.random.default_rng(3).permutation(len(confs))]
     c = rc.Context(meshes[0], meshes[1], device=0)
     try:
         want = run_check(c, confs, rc.RC_MODE_BRUTE)
         pinned = torch.from_numpy(confs).pin_memory()
-        for n in (1, 31, 32, 33, 1000, 4737, 30_000):
+        for n in (1, 31, 32, 33, 1000, 4737, 30_000, 70_000):
             for rep in range(2):
                 got, bits = run_check(c, confs[:n], rc.RC_MODE_CULLED, bitmask=True)
                 assert np.array_equal(got, want[:n]), (feed, n, rep, int((got != want[:n]).sum()))
@@ -1058,7 +1058,7 @@ def test_single_launch_form_every_size(rc, meshes, feed, monkeypatch):
                 assert np.array_equal(c.check_host(confs[:n]), want[:n]), (feed, n, rep, "pageable")
                 assert np.array_equal(c.check_host(pinned.numpy()[:n]), want[:n]), (feed, n, rep, "pinned")
         # the reference's far sampler: nearly everything cleared by the classifying warps themselves
-        far = rc.createAlphaBotConfigurations(50_000, False, 511)
+        far = rc.createAlphaBotConfigurations(80_000, False, 511)
         assert np.array_equal(c.check_host(far), run_check(c, far, rc.RC_MODE_BRUTE))
         assert c.stats()["watchdog"] == 0
     finally:
