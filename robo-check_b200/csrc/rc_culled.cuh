@@ -1376,9 +1376,18 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
                                 cudaStream_t stream, unsigned long long *queue, const CheckExtras *extras)
 {
     const DeviceTables &t = ctx->t;
-    int warps = ctx->knob_warps;
-    if (warps != 16 && warps != 24 && warps != 32) warps = kCulledWarpsDefault;
     const bool gobs = t.gobs, rl1 = t.gobs && t.rob_leaf == 1;
+    int warps = ctx->knob_warps;
+    if (warps != 16 && warps != 24 && warps != 32) {
+        // Warps per CTA by batch size (obstacle in shared memory): a short call is bound by its longest
+        // descents, and a warp that shares its scheduler with 3 or 5 others instead of 7 gets through one
+        // faster (and has a deeper stack); a long call is bound by throughput and wants all 32.  Measured
+        // (profiles/ab_r02.txt 6): 512 hard configurations 42.0 -> 35.8 us with 16 warps, 10,000: 103.4 -> 89.2
+        // and 30,000: 154.7 -> 129.9 with 24, 100,000: 283.6 (32) against 287.8 (24) and 338.9 (16).
+        // With the obstacle in global memory the longest descents take milliseconds, so "short" reaches
+        // further: one C5 shard of 1.25 M configurations 2.53 -> 2.16 ms with 24 warps.
+        warps = gobs ? (n < (1L << 22) ? 24 : 32) : n <= 4096 ? 16 : n < 65536 ? 24 : 32;
+    }
     while (warps > 16 && culled_smem_bytes(t, warps, gobs) > (size_t)ctx->max_smem_optin) warps -= 8;
     const size_t smem = culled_smem_bytes(t, warps, gobs);
     if (smem > (size_t)ctx->max_smem_optin || t.n_rob_v > 65535) return cudaErrorInvalidConfiguration;
