@@ -1384,9 +1384,9 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
         // faster (and has a deeper stack); a long call is bound by throughput and wants all 32.  Measured
         // (profiles/ab_r02.txt 6): 512 hard configurations 42.0 -> 35.8 us with 16 warps, 10,000: 103.4 -> 89.2
         // and 30,000: 154.7 -> 129.9 with 24, 100,000: 283.6 (32) against 287.8 (24) and 338.9 (16).
-        // With the obstacle in global memory the longest descents take milliseconds, so "short" reaches
-        // further: one C5 shard of 1.25 M configurations 2.53 -> 2.16 ms with 24 warps.
-        warps = gobs ? (n < (1L << 22) ? 24 : 32) : n <= 4096 ? 16 : n < 65536 ? 24 : 32;
+        // With the obstacle in global memory the longest descents take milliseconds and bound calls of any
+        // size tried: 24 warps (one C5 shard of 1.25 M configurations 2.53 -> 2.16 ms, 10 M: 9.2-9.3 -> 8.9 ms).
+        warps = gobs ? 24 : n <= 4096 ? 16 : n < 65536 ? 24 : 32;
     }
     while (warps > 16 && culled_smem_bytes(t, warps, gobs) > (size_t)ctx->max_smem_optin) warps -= 8;
     const size_t smem = culled_smem_bytes(t, warps, gobs);
@@ -1413,7 +1413,7 @@ cudaError_t launch_check_culled(const rc_ctx *ctx, const rc_config *d_confs, lon
     // small chunks: the per-configuration cost varies 1:8 (cleared / full sweep / colliding)
     a.c.chunk = 1;  // the list-driven kernel sizes its chunks from the work count on the device
     a.tail_begin = (long)grid * warps * 4;
-    a.tail_thresh = 16; a.leaf_thresh = 8;
+    a.tail_thresh = gobs ? 32 : 16; a.leaf_thresh = 8;  // one-triangle robot leaves queue many finishing pairs: full rounds
     const int sd = ctx->knob_seed_depth < 0 ? 2 : min(3, ctx->knob_seed_depth);
     a.n_seed_r = t.n_seed_r[sd]; a.n_seed_o = t.n_seed_o[sd];
     for (int q = 0; q < 8; q++) { a.seed_r[q] = t.seed_r[sd][q]; a.seed_o[q] = t.seed_o[sd][q]; }

@@ -25,6 +25,9 @@ for n in (1_250_000, 10_000_000):
 print(os.environ.get("TAG"), out, "8x1.25M vs 10M speed-up bound: %.2f" % (out[1][1] / out[0][1]))
 '''
 open("/tmp/c5k.py", "w").write(code)
-for env in ({}, {"RC_SPLIT_LOAD": "32"}, {"RC_SPLIT_LOAD": "64"}, {"RC_SPLIT_LOAD": "256"}, {"RC_MAIL_SLOTS": "16"}, {"RC_SPLIT_LOAD": "64", "RC_MAIL_SLOTS": "16"}):
+for env in ({}, {"RC_CULLED_WARPS": "32"}, {"RC_CULLED_WARPS": "24"}, {"RC_CULLED_WARPS": "16"},
+            {"RC_DONATE_MIN": "64"}, {"RC_DONATE_MIN": "128"}, {"RC_MAIL_SLOTS": "8"}, {"RC_MAIL_SLOTS": "16"},
+            {"RC_MAIL_SLOTS": "16", "RC_DONATE_MIN": "128"}, {"RC_TAIL_THRESH": "32"}, {"RC_TAIL_THRESH": "8"},
+            {"RC_SHARE": "0"}, {}):
     e = dict(os.environ); e.update(env); e["TAG"] = json.dumps(env)
-    subprocess.run([sys.executable, "/tmp/c5k.py"], env=e)
+    subprocess.run([sys.executable, "/tmp/c5k.py"], env=e, timeout=200)
