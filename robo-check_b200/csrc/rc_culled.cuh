@@ -500,6 +500,15 @@ __device__ __noinline__ void classify_batch(const CulledArgs &a, uint32_t b, int
 __device__ __noinline__ unsigned long long feed_next(const CulledArgs &a, FeedShared *s_feed, int warp, int lane)
 {
     const uint32_t n_batches = (uint32_t)((a.k.n + 31) >> 5);
+#ifdef RC_TIMELINE
+    // diagnostic build: per warp [4] ns inside feed_next  [5] iterations that found the ring empty  [6] ns inside feed_refill  [7] refills
+    uint32_t *tlf = a.trace ? a.trace + 8 * (size_t)(blockIdx.x * (blockDim.x >> 5) + warp) : nullptr;
+    unsigned long long tl_in;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl_in));
+#define TLF_LEAVE() do { if (tlf && lane == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); tlf[4] += (uint32_t)(t_ - tl_in); } } while (0)
+#else
+#define TLF_LEAVE() do { } while (0)
+#endif
     for (uint32_t spins = 0;; spins++) {
         // what other warps publish is read by one lane and broadcast: lanes reading the same
         // word at different moments could take different branches of this loop
@@ -550,7 +559,14 @@ __device__ __noinline__ unsigned long long feed_next(const CulledArgs &a, FeedSh
             if (lane == 0) got = atomicCAS(&s_feed->lock, 0u, 1u) == 0u ? 1u : 0u;
             got = __shfl_sync(kFull, got, 0);
             if (got) {
+#ifdef RC_TIMELINE
+                unsigned long long t0_;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0_));
+#endif
                 feed_refill(a, s_feed, lane);
+#ifdef RC_TIMELINE
+                if (tlf && lane == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); tlf[6] += (uint32_t)(t_ - t0_); tlf[7] += 1u; }
+#endif
                 __syncwarp();
                 if (lane == 0) st_volatile(&s_feed->lock, 0u);
             }
@@ -558,12 +574,17 @@ __device__ __noinline__ unsigned long long feed_next(const CulledArgs &a, FeedSh
         if (st) {
             e = __shfl_sync(kFull, e, 0);
             if ((uint32_t)e == 0xffffffffu) continue;  // a slot that never arrived (counted in feed_refill)
+            TLF_LEAVE();
             return e;
         }
         if (done || spins > kWatchdogSpins) {
             if (!done && lane == 0) { atomicAdd(a.c.counters + CNT_WATCHDOG, 1ULL); atomicOr(a.c.counters + CNT_WATCHDOG_WHERE, 4ULL); }
+            TLF_LEAVE();
             return ~0ULL;
         }
+#ifdef RC_TIMELINE
+        if (tlf && lane == 0 && !st) tlf[5] += 1u;
+#endif
         __nanosleep(spins < 8 ? 100 : 400);
     }
 }
@@ -1291,7 +1312,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) check_culled_kernel(const __gri
         if (hit) st_invalid++; else st_valid++;
     }
 #ifdef RC_TIMELINE
-    if (tl && lane == 0) { tl[2] = tl_now(); tl[3] = tl_entries; tl[4] = tl_longest; tl[5] = tl_rounds; tl[6] = tl_given; tl[7] = tl_got; }
+    if (tl && lane == 0) { tl[2] = tl_now(); tl[3] = tl_entries; if (!FEED) { tl[4] = tl_longest; tl[5] = tl_rounds; tl[6] = tl_given; tl[7] = tl_got; } }
 #endif
     if (STATS) {
 #pragma unroll
