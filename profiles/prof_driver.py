@@ -1,5 +1,5 @@
 """Short driver for the ncu passes: a few launches of each kernel of the hot path.
-usage: prof_driver.py [all|culled|brute|stage|gobs|spheres|planner|gather] ..."""
+usage: prof_driver.py [all|culled|brute|stage|gobs|spheres|planner|gather|short] ..."""
 import os
 import sys
 
@@ -27,6 +27,12 @@ reps = 2
 if on("culled"):
     for _ in range(reps):
         ctx.check(d_confs, n, d_valid, d_mask, rc.RC_MODE_CULLED, s)
+if "short" in which:
+    # planner-sized calls: 2,000 configurations (16 warps per CTA, every configuration cut into parts) and
+    # 30,000 (24 warps per CTA) -- bound by their longest descents, not by throughput
+    for m in (2_000, 30_000):
+        for _ in range(reps):
+            ctx.check(d_confs, m, d_valid, d_mask, rc.RC_MODE_CULLED, s)
 if on("brute"):
     for _ in range(reps):
         ctx.check(d_confs, 16384, d_valid, None, rc.RC_MODE_BRUTE, s)
