@@ -531,6 +531,12 @@ def test_million_configurations_bitmask_and_sample(rc, ctx, po, omeshes):
     want = po.check(omeshes[0], omeshes[1], confs[sample], po.VARIANT_GPU)
     assert np.array_equal(got[sample], want)
     assert 0 < int((got == 0).sum()) < n // 100
+    # the host call at this size is the single-launch form (the kernel classifies, 31,251 batches drawn
+    # by the classifying warps, lists consumed while they grow): same flags, ragged tail included
+    assert np.array_equal(ctx.check_host(confs), got)
+    hard = rc.createAlphaBotConfigurations(400_001, True, 512)
+    assert np.array_equal(ctx.check_host(hard), run_check(ctx, hard, rc.RC_MODE_CULLED))
+    assert ctx.stats()["watchdog"] == 0
 
 
 @pytest.mark.parametrize("shape", ["tetra", "single", "strip7"])
