@@ -21,6 +21,11 @@
 //   D   the few pairs that pass both plane tests are queued and finished (coplanarity,
 //       intersection line, interval test) 32 at a time, so the long rare path runs with full
 //       warps instead of a handful of lanes; warp vote early exit.
+// Single-launch form (FEED kernels, RC_FEED): step 1 runs inside step 2 -- a few warps per CTA classify
+// batches of 32 configurations from wherever they lie (rc_check_host: the caller's pinned buffer, read
+// over PCIe) while the others already descend; see FeedArgs / FeedShared / feed_next below.
+// Warps per CTA follow the size of the call (16 / 24 / 32, launch_check_culled): short calls are bound
+// by their longest descents, long ones by instruction issue.
 #pragma once
 
 namespace rc {
